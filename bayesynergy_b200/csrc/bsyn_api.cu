@@ -1,0 +1,747 @@
+// bsyn_api.cu -- the C ABI of include/bsyn.h: host-side packing of problems into HBM, kernel dispatch.
+// Replaces the Rcpp module boundary rstan::stan_fit<model_gp_grid, ...> (reference
+// src/stanExports_gp_grid.cc:10-30) -- see INTEGRATION.md.  No CPU fallback: every compute entry point
+// needs a CUDA device.
+#include "../../include/bsyn.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bsyn_nuts.cuh"
+#include "bsyn_post.cuh"
+
+using namespace bsyn;
+
+static thread_local std::string g_err;
+static long long g_launches = 0;
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+            return BSYN_ERR_CUDA;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+constexpr int WPC = 4;   // warps (= chains) per CTA
+
+struct bsyn_batch {
+    int device = 0;
+    int n = 0;
+    int cpl = 0;
+    Flags F{};
+    bsyn_options opts{};
+    std::vector<ProbDesc> descs;
+    ProbDesc *d_descs = nullptr;
+    double *d_dpool = nullptr;
+    int *d_ipool = nullptr;
+    int *d_tri = nullptr;
+    int maxD = 0, maxOut = 0, maxN = 0, max_d_smem = 0, max_i_smem = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    // buffers of the last sampling call (device)
+    double *d_qdraws = nullptr, *d_sp = nullptr, *d_summary = nullptr, *d_chain_stats = nullptr;
+    double *d_arena = nullptr;
+    size_t qdraws_elems = 0, sp_elems = 0, arena_elems = 0, summary_elems = 0, cs_elems = 0;
+    int last_chains = 0, last_nsave = 0, last_nskip = 0;
+    unsigned long long *d_gradctr = nullptr;
+    int *d_workctr = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------
+static double host_inv_Phi(double p)
+{
+    // bisection + Newton on Phi(x) = erfc(-x/sqrt2)/2 (only used once per batch: tauLPTN, gp_grid.stan:37)
+    double lo = -40, hi = 40;
+    for (int it = 0; it < 200; ++it) {
+        double mid = 0.5 * (lo + hi);
+        if (0.5 * erfc(-mid / sqrt(2.0)) < p) lo = mid; else hi = mid;
+    }
+    double x = 0.5 * (lo + hi);
+    for (int it = 0; it < 4; ++it) {
+        double f = 0.5 * erfc(-x / sqrt(2.0)) - p;
+        double d = exp(-0.5 * x * x) / sqrt(2.0 * M_PI);
+        if (d > 0) x -= f / d;
+    }
+    return x;
+}
+
+static int make_flags(const bsyn_options &o, Flags &F)
+{
+    if (o.model != BSYN_MODEL_GP_GRID && o.model != BSYN_MODEL_NOINTERACTION) return fail(BSYN_ERR_ARG, "options.model must be 0 or 1");
+    F.model = o.model;
+    F.est_la = o.est_la ? 1 : 0;
+    F.robust = o.robust ? 1 : 0;
+    F.pcprior = o.pcprior ? 1 : 0;
+    F.het = o.heteroscedastic ? 1 : 0;
+    F.kernel = o.kernel; F.nu_matern = o.nu_matern; F.est_alpha = o.est_alpha ? 1 : 0;
+    if (o.model == BSYN_MODEL_GP_GRID) {
+        if (o.kernel < 1 || o.kernel > 3) return fail(BSYN_ERR_ARG, "options.kernel must be 1 (RBF), 2 (Matern) or 3 (RQ)");
+        if (o.kernel == 2 && (o.nu_matern < 1 || o.nu_matern > 3)) return fail(BSYN_ERR_ARG, "options.nu_matern must be 1, 2 or 3 for the Matern kernel");
+        if (o.kernel == 3 && !o.est_alpha) return fail(BSYN_ERR_ARG, "rational quadratic kernel needs est_alpha = 1 (alpha[1] is read, gp_grid.stan:139)");
+        if (o.kernel != 3 && o.est_alpha) return fail(BSYN_ERR_ARG, "est_alpha = 1 only makes sense with kernel = 3");
+    } else {
+        F.kernel = 0; F.nu_matern = 0; F.est_alpha = 0; F.pcprior = 0;
+    }
+    F.lambda = o.lambda;
+    F.tau = 0; F.lamL = 0; F.lptn_c0 = 0;
+    if (F.robust) {
+        if (!(o.rho > 0 && o.rho < 1)) return fail(BSYN_ERR_ARG, "rho must lie in (0,1)");
+        F.tau = host_inv_Phi((1.0 + o.rho) / 2.0);
+        F.lamL = 2.0 / (1.0 - o.rho) * exp(-0.5 * F.tau * F.tau - 0.5 * log(2.0 * M_PI)) * F.tau * log(F.tau);
+        F.lptn_c0 = -0.5 * F.tau * F.tau + log(F.tau) + (F.lamL + 1.0) * log(log(F.tau));
+    }
+    F.lam1 = F.lam2 = F.log_lam12 = 0;
+    if (F.pcprior) {
+        const double *h = o.pcprior_hypers;
+        F.lam1 = -log(h[1]) * h[0];      // gp_grid.stan:43  (d_half = 1)
+        F.lam2 = -log(h[3]) / h[2];      // gp_grid.stan:44
+        F.log_lam12 = log(F.lam1) + log(F.lam2);
+    }
+    unsigned m = 0;
+    if (F.est_la) m |= (1u << SL_LA1) | (1u << SL_LA2);
+    m |= (1u << SL_M1) | (1u << SL_M2) | (1u << SL_TH1) | (1u << SL_TH2) | (1u << SL_SL1) | (1u << SL_SL2);
+    if (F.model == 0) {
+        m |= (1u << SL_B1) | (1u << SL_B2) | (1u << SL_ELL) | (1u << SL_SIGF);
+        if (F.est_alpha) m |= (1u << SL_ALPHA);
+    }
+    m |= (1u << SL_S) | (1u << SL_S21) | (1u << SL_S22);
+    F.active_mask = m;
+    return BSYN_OK;
+}
+
+template <int CPL> static bool fits(int n1, int n2)
+{
+    return n1 * n2 <= Cfg<CPL>::GM && n1 <= Cfg<CPL>::NM && n2 <= Cfg<CPL>::NM && n1 + n2 <= 31;
+}
+
+static int ws_doubles(int cpl)
+{
+    switch (cpl) {
+        case 1: return Cfg<1>::WS_DOUBLES;
+        case 2: return Cfg<2>::WS_DOUBLES;
+        case 4: return Cfg<4>::WS_DOUBLES;
+        default: return Cfg<8>::WS_DOUBLES;
+    }
+}
+static int tr_entries(int cpl)
+{
+    switch (cpl) {
+        case 1: return Cfg<1>::TR;
+        case 2: return Cfg<2>::TR;
+        case 4: return Cfg<4>::TR;
+        default: return Cfg<8>::TR;
+    }
+}
+
+// shared memory layouts.  per_warp_problem: every warp has its own problem block (logp / write_array
+// kernels); otherwise one block per CTA (sampler).
+static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t *bytes)
+{
+    SmemLayout sl;
+    const int tr = tr_entries(b->cpl);
+    sl.tri_off = 0;
+    sl.pd_off = (tr + 1) / 2 + 1;
+    sl.pd_stride = b->max_d_smem + (b->max_d_smem & 1);
+    sl.pi_stride = (b->max_i_smem + 1) / 2 + 1;   // in doubles
+    const int nblk = per_warp_problem ? WPC : 1;
+    sl.pi_off = sl.pd_off + nblk * sl.pd_stride;
+    sl.ws_off = sl.pi_off + nblk * sl.pi_stride;
+    *bytes = sizeof(double) * (size_t)(sl.ws_off + WPC * ws_doubles(b->cpl));
+    return sl;
+}
+
+extern "C" const char *bsyn_last_error(void) { return g_err.c_str(); }
+extern "C" int bsyn_version(void) { return BSYN_VERSION; }
+extern "C" int64_t bsyn_launch_count(void) { return g_launches; }
+
+extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const bsyn_options *opts, int32_t device,
+                                 bsyn_batch **out)
+{
+    if (!problems || !opts || !out || n <= 0) return fail(BSYN_ERR_ARG, "bsyn_batch_create: null argument or n <= 0");
+    *out = nullptr;
+    Flags F;
+    int rc = make_flags(*opts, F);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(BSYN_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BSYN_ERR_ARG, "bsyn_batch_create: bad device ordinal");
+    CK(cudaSetDevice(device));
+    bsyn_batch *b = new bsyn_batch();
+    b->device = device; b->n = n; b->F = F; b->opts = *opts;
+    // pick the smallest kernel variant that fits every problem
+    int cpl = 1;
+    for (int k = 0; k < n; ++k) {
+        const bsyn_problem &p = problems[k];
+        if (p.n1 < 1 || p.n2 < 1 || p.N < 0 || !p.y || !p.ii_obs || !p.x1 || !p.x2) { delete b; return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": bad sizes or null pointer"); }
+        const long long Nexp = (long long)(p.n1 + p.n2 + p.n1 * p.n2 + 1) * p.nrep - p.nmissing;
+        if (Nexp != p.N) { delete b; return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": N != (n1+n2+n1*n2+1)*nrep - nmissing (gp_grid.stan:31)"); }
+        while (cpl <= 8) {
+            bool f = cpl == 1 ? fits<1>(p.n1, p.n2) : cpl == 2 ? fits<2>(p.n1, p.n2) : cpl == 4 ? fits<4>(p.n1, p.n2) : fits<8>(p.n1, p.n2);
+            if (f) break;
+            cpl *= 2;
+        }
+        if (cpl > 8) { delete b; return fail(BSYN_ERR_UNSUPPORTED, "problem " + std::to_string(k) + ": dose grid larger than 16 x 15 is not supported by the compiled kernel variants"); }
+    }
+    b->cpl = cpl;
+    std::vector<double> dpool;
+    std::vector<int> ipool;
+    b->descs.resize(n);
+    for (int k = 0; k < n; ++k) {
+        const bsyn_problem &p = problems[k];
+        ProbDesc &d = b->descs[k];
+        const int n1 = p.n1, n2 = p.n2, N = p.N, ncf = (n1 + 1) * (n2 + 1), nm = n1 + n2;
+        const int P1 = n1 * (n1 - 1) / 2, P2 = n2 * (n2 - 1) / 2, PP = P1 + P2;
+        d.n1 = n1; d.n2 = n2; d.N = N; d.G = n1 * n2; d.ncf = ncf;
+        const int gp = (F.model == 0);
+        d.D = gp ? 13 + 2 * F.est_la + F.est_alpha + n1 * n2 : 9 + 2 * F.est_la;
+        d.n_out = gp ? d.D + 3 * d.G + nm + 2 + N + 7 : d.D + d.G + nm + 2 + N + 4;
+        if (dpool.size() & 1) dpool.push_back(0.0);
+        d.off_d = (int)dpool.size();
+        d.off_i = (int)ipool.size();
+        for (int j = 0; j < n1; ++j) dpool.push_back(p.x1[j]);
+        for (int i = 0; i < n2; ++i) dpool.push_back(p.x2[i]);
+        // VUS trapezoid weights (include/VUS.stan): VUS(Z) = sum_ij w1[j] w2[i] Z[i,j]; 100/area folded into w1
+        {
+            double mn1 = p.x1[0], mx1 = p.x1[0], mn2 = p.x2[0], mx2 = p.x2[0];
+            for (int j = 0; j < n1; ++j) { mn1 = std::min(mn1, p.x1[j]); mx1 = std::max(mx1, p.x1[j]); }
+            for (int i = 0; i < n2; ++i) { mn2 = std::min(mn2, p.x2[i]); mx2 = std::max(mx2, p.x2[i]); }
+            const double area = (mx1 - mn1) * (mx2 - mn2);
+            for (int j = 0; j < n1; ++j) {
+                double w = 0;
+                if (j > 0) w += 0.5 * (p.x1[j] - p.x1[j - 1]);
+                if (j + 1 < n1) w += 0.5 * (p.x1[j + 1] - p.x1[j]);
+                dpool.push_back(100.0 * w / area);
+            }
+            for (int i = 0; i < n2; ++i) {
+                double w = 0;
+                if (i > 0) w += 0.5 * (p.x2[i] - p.x2[i - 1]);
+                if (i + 1 < n2) w += 0.5 * (p.x2[i + 1] - p.x2[i]);
+                dpool.push_back(w);
+            }
+        }
+        // pair distances (gp_grid.stan:47-62) and their (a,b) codes, lower triangle a > b
+        for (int a = 0; a < n1; ++a)
+            for (int c = 0; c < a; ++c) { dpool.push_back(sqrt((p.x1[a] - p.x1[c]) * (p.x1[a] - p.x1[c]))); ipool.push_back((a << 8) | c); }
+        for (int a = 0; a < n2; ++a)
+            for (int c = 0; c < a; ++c) { dpool.push_back(sqrt((p.x2[a] - p.x2[c]) * (p.x2[a] - p.x2[c]))); ipool.push_back((a << 8) | c); }
+        // per-cell sufficient statistics + observations sorted by cell
+        std::vector<double> cnt(ncf, 0.0), sum(ncf, 0.0), ss(ncf, 0.0);
+        std::vector<int> cstart(ncf + 1, 0);
+        for (int t = 0; t < N; ++t) {
+            const int c = p.ii_obs[t] - 1;
+            if (c < 0 || c >= ncf) { delete b; return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": ii_obs out of range"); }
+            if (!(p.y[t] == p.y[t])) { delete b; return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": y contains NaN (missing values must be removed, R/bayesynergy.R:153-154)"); }
+            cnt[c] += 1.0; sum[c] += p.y[t];
+        }
+        for (int c = 0; c < ncf; ++c) { if (cnt[c] > 0) sum[c] /= cnt[c]; cstart[c + 1] = cstart[c] + (int)cnt[c]; }
+        std::vector<double> ysort(N);
+        std::vector<int> fill(cstart.begin(), cstart.end() - 1);
+        for (int t = 0; t < N; ++t) {
+            const int c = p.ii_obs[t] - 1;
+            const double dy = p.y[t] - sum[c];
+            ss[c] += dy * dy;
+            ysort[fill[c]++] = p.y[t];
+        }
+        dpool.insert(dpool.end(), cnt.begin(), cnt.end());
+        dpool.insert(dpool.end(), sum.begin(), sum.end());
+        dpool.insert(dpool.end(), ss.begin(), ss.end());
+        d.n_d_smem = 2 * nm + PP + 3 * ncf + (F.robust ? N : 0);
+        dpool.insert(dpool.end(), ysort.begin(), ysort.end());
+        for (int t = 0; t < N; ++t) dpool.push_back(p.y[t]);
+        ipool.insert(ipool.end(), cstart.begin(), cstart.end());
+        d.n_i_smem = PP + (F.robust ? ncf + 1 : 0);
+        for (int t = 0; t < N; ++t) ipool.push_back(p.ii_obs[t] - 1);
+        b->maxD = std::max(b->maxD, d.D); b->maxOut = std::max(b->maxOut, d.n_out); b->maxN = std::max(b->maxN, N);
+        b->max_d_smem = std::max(b->max_d_smem, d.n_d_smem); b->max_i_smem = std::max(b->max_i_smem, d.n_i_smem);
+    }
+    // packed lower-triangular (r,c) table, row-major; valid for every n <= 16
+    std::vector<int> tri;
+    for (int r = 0; r < 16; ++r)
+        for (int c = 0; c <= r; ++c) tri.push_back((r << 8) | c);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    b->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&b->d_descs, sizeof(ProbDesc) * n));
+    CK(cudaMalloc(&b->d_dpool, sizeof(double) * std::max<size_t>(dpool.size(), 1)));
+    CK(cudaMalloc(&b->d_ipool, sizeof(int) * std::max<size_t>(ipool.size(), 1)));
+    CK(cudaMalloc(&b->d_tri, sizeof(int) * tri.size()));
+    CK(cudaMalloc(&b->d_gradctr, sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_workctr, sizeof(int)));
+    CK(cudaMemcpy(b->d_descs, b->descs.data(), sizeof(ProbDesc) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->d_dpool, dpool.data(), sizeof(double) * dpool.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->d_ipool, ipool.data(), sizeof(int) * ipool.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->d_tri, tri.data(), sizeof(int) * tri.size(), cudaMemcpyHostToDevice));
+    *out = b;
+    return BSYN_OK;
+}
+
+extern "C" void bsyn_batch_destroy(bsyn_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaFree(b->d_descs); cudaFree(b->d_dpool); cudaFree(b->d_ipool); cudaFree(b->d_tri);
+    cudaFree(b->d_qdraws); cudaFree(b->d_sp); cudaFree(b->d_summary); cudaFree(b->d_chain_stats); cudaFree(b->d_arena);
+    cudaFree(b->d_gradctr); cudaFree(b->d_workctr);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+extern "C" int32_t bsyn_num_params(const bsyn_batch *b, int32_t k) { return (b && k >= 0 && k < b->n) ? b->descs[k].D : -1; }
+extern "C" int32_t bsyn_num_outputs(const bsyn_batch *b, int32_t k) { return (b && k >= 0 && k < b->n) ? b->descs[k].n_out : -1; }
+extern "C" int32_t bsyn_max_params(const bsyn_batch *b) { return b ? b->maxD : -1; }
+extern "C" int32_t bsyn_max_outputs(const bsyn_batch *b) { return b ? b->maxOut : -1; }
+extern "C" int32_t bsyn_num_problems(const bsyn_batch *b) { return b ? b->n : -1; }
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone log_prob / grad_log_prob and write_array kernels: one warp per evaluation point
+template <int CPL, bool DBG>
+__global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const ProbDesc *__restrict__ descs,
+                                                        const double *__restrict__ dpool, const int *__restrict__ ipool,
+                                                        const int *__restrict__ tri_tab, const SmemLayout sl, const int B,
+                                                        const int *__restrict__ prob_idx, const double *__restrict__ u,
+                                                        const int ldu, const int jacobian, double *__restrict__ lp,
+                                                        double *__restrict__ grad, int *__restrict__ status,
+                                                        double *__restrict__ dbg, const int dbg_stride)
+{
+    using C = Cfg<CPL>;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *s_tri = reinterpret_cast<int *>(smem + sl.tri_off);
+    for (int e = threadIdx.x; e < C::TR; e += blockDim.x) s_tri[e] = tri_tab[e];
+    __syncthreads();
+    double *s_pd = smem + sl.pd_off + warp * sl.pd_stride;
+    int *s_pi = reinterpret_cast<int *>(smem + sl.pi_off + warp * sl.pi_stride);
+    double *ws = smem + sl.ws_off + warp * C::WS_DOUBLES;
+    int loaded = -1;
+    ProbS P;
+    int cell[CPL];
+    for (int pt = blockIdx.x * WPC + warp; pt < B; pt += gridDim.x * WPC) {
+        const int ip = prob_idx[pt];
+        const ProbDesc pd = descs[ip];
+        if (ip != loaded) {
+            __syncwarp();
+            for (int e = lane; e < pd.n_d_smem; e += 32) s_pd[e] = dpool[pd.off_d + e];
+            for (int e = lane; e < pd.n_i_smem; e += 32) s_pi[e] = ipool[pd.off_i + e];
+            __syncwarp();
+            bind_problem(P, pd, s_pd, s_pi, s_tri);
+            make_cells<CPL>(F, P, cell);
+            loaded = ip;
+        }
+        WVec<CPL> q, g;
+        load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
+        double lpv;
+        const bool ok = warp_logp_grad<CPL, DBG>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr);
+        if (!ok) {
+            lpv = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) g.z[t] = 0.0;
+            g.s = 0.0;
+        }
+        if (lane == 0) { lp[pt] = lpv; status[pt] = ok ? 0 : 1; }
+        if (grad) store_user_vec<CPL>(F, pd, cell, g, grad + (size_t)pt * ldu);
+    }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(32 * WPC) write_array_kernel(const Flags F, const ProbDesc *__restrict__ descs,
+                                                               const double *__restrict__ dpool, const int *__restrict__ ipool,
+                                                               const int *__restrict__ tri_tab, const SmemLayout sl, const int B,
+                                                               const int *__restrict__ prob_idx, const double *__restrict__ u,
+                                                               const int ldu, double *__restrict__ out, const int ldo,
+                                                               const unsigned long long seed, int *__restrict__ status)
+{
+    using C = Cfg<CPL>;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *s_tri = reinterpret_cast<int *>(smem + sl.tri_off);
+    for (int e = threadIdx.x; e < C::TR; e += blockDim.x) s_tri[e] = tri_tab[e];
+    __syncthreads();
+    double *s_pd = smem + sl.pd_off + warp * sl.pd_stride;
+    int *s_pi = reinterpret_cast<int *>(smem + sl.pi_off + warp * sl.pi_stride);
+    double *ws = smem + sl.ws_off + warp * C::WS_DOUBLES;
+    int loaded = -1;
+    ProbS P;
+    int cell[CPL];
+    for (int pt = blockIdx.x * WPC + warp; pt < B; pt += gridDim.x * WPC) {
+        const int ip = prob_idx[pt];
+        const ProbDesc pd = descs[ip];
+        if (ip != loaded) {
+            __syncwarp();
+            for (int e = lane; e < pd.n_d_smem; e += 32) s_pd[e] = dpool[pd.off_d + e];
+            for (int e = lane; e < pd.n_i_smem; e += 32) s_pi[e] = ipool[pd.off_i + e];
+            __syncwarp();
+            bind_problem(P, pd, s_pd, s_pi, s_tri);
+            make_cells<CPL>(F, P, cell);
+            loaded = ip;
+        }
+        WVec<CPL> q;
+        load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
+        RngKey rk;
+        rk.k0 = (uint32_t)seed; rk.k1 = (uint32_t)(seed >> 32); rk.chain = (uint32_t)pt;
+        double uz[4];
+        rng_u2(rk, RT_GQ, 0xFFu, 0, 0, uz[0], uz[1]);
+        rng_u2(rk, RT_GQ, 0xFFu, 0, 1, uz[2], uz[3]);
+        const bool ok = warp_write_array<CPL>(F, P, pd, ws, cell, q, dpool + pd.off_d + pool_y_off(pd),
+                                              ipool + pd.off_i + pool_ii_off(pd), uz, out + (size_t)pt * ldo, nullptr, nullptr);
+        if (lane == 0) status[pt] = ok ? 0 : 1;
+    }
+}
+
+#define DISPATCH_CPL(cpl, ...)                         \
+    switch (cpl) {                                     \
+        case 1: { constexpr int CPL = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int CPL = 2; __VA_ARGS__; } break; \
+        case 4: { constexpr int CPL = 4; __VA_ARGS__; } break; \
+        default: { constexpr int CPL = 8; __VA_ARGS__; } break; \
+    }
+
+static int launch_logp(bsyn_batch *b, int B, const int *d_idx, const double *d_u, int ldu, int jac, double *d_lp,
+                       double *d_grad, int *d_status, double *d_dbg, int dbg_stride, cudaStream_t st)
+{
+    size_t bytes;
+    SmemLayout sl = make_layout(b, true, &bytes);
+    int grid = std::min((B + WPC - 1) / WPC, b->num_sms * 8);
+    if (grid < 1) grid = 1;
+    DISPATCH_CPL(b->cpl, {
+        if (d_dbg) {
+            CK(cudaFuncSetAttribute(logp_kernel<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            logp_kernel<CPL, true><<<grid, 32 * WPC, bytes, st>>>(b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B, d_idx,
+                                                                d_u, ldu, jac, d_lp, d_grad, d_status, d_dbg, dbg_stride);
+        } else {
+            CK(cudaFuncSetAttribute(logp_kernel<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            logp_kernel<CPL, false><<<grid, 32 * WPC, bytes, st>>>(b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B, d_idx,
+                                                                 d_u, ldu, jac, d_lp, d_grad, d_status, nullptr, 0);
+        }
+    });
+    ++g_launches;
+    CK(cudaGetLastError());
+    return BSYN_OK;
+}
+
+extern "C" int bsyn_logp_grad_device(bsyn_batch *b, int32_t B, const int32_t *d_prob_idx, const double *d_u, int32_t ldu,
+                                     int32_t jacobian, double *d_lp, double *d_grad, int32_t *d_status, void *stream)
+{
+    if (!b || B < 0 || !d_prob_idx || !d_u || !d_lp || !d_status || ldu < b->maxD) return fail(BSYN_ERR_ARG, "bsyn_logp_grad_device: bad argument");
+    if (B == 0) return BSYN_OK;
+    CK(cudaSetDevice(b->device));
+    return launch_logp(b, B, d_prob_idx, d_u, ldu, jacobian, d_lp, d_grad, d_status, nullptr, 0, (cudaStream_t)stream);
+}
+
+// debug variant used by tests: also returns the kernel's intermediates (see bsyn_model.cuh DBG layout)
+extern "C" int bsyn_logp_grad_debug(bsyn_batch *b, int32_t B, const int32_t *prob_idx, const double *u, int32_t ldu,
+                                    int32_t jacobian, double *lp, double *grad, int32_t *status, double *dbg,
+                                    int32_t dbg_stride);
+
+static int logp_host(bsyn_batch *b, int B, const int *prob_idx, const double *u, int ldu, int jac, double *lp, double *grad,
+                     int *status, double *dbg, int dbg_stride)
+{
+    if (!b || B < 0 || !prob_idx || !u || !lp || !status || ldu < b->maxD) return fail(BSYN_ERR_ARG, "bsyn_logp_grad: bad argument (ldu must be >= bsyn_max_params)");
+    if (B == 0) return BSYN_OK;
+    for (int k = 0; k < B; ++k)
+        if (prob_idx[k] < 0 || prob_idx[k] >= b->n) return fail(BSYN_ERR_ARG, "bsyn_logp_grad: prob_idx out of range");
+    CK(cudaSetDevice(b->device));
+    int *d_idx = nullptr, *d_st = nullptr;
+    double *d_u = nullptr, *d_lp = nullptr, *d_g = nullptr, *d_dbg = nullptr;
+    CK(cudaMalloc(&d_idx, sizeof(int) * B)); CK(cudaMalloc(&d_st, sizeof(int) * B));
+    CK(cudaMalloc(&d_u, sizeof(double) * (size_t)B * ldu)); CK(cudaMalloc(&d_lp, sizeof(double) * B));
+    if (grad) { CK(cudaMalloc(&d_g, sizeof(double) * (size_t)B * ldu)); CK(cudaMemsetAsync(d_g, 0, sizeof(double) * (size_t)B * ldu, b->stream)); }
+    if (dbg) { CK(cudaMalloc(&d_dbg, sizeof(double) * (size_t)B * dbg_stride)); CK(cudaMemsetAsync(d_dbg, 0, sizeof(double) * (size_t)B * dbg_stride, b->stream)); }
+    CK(cudaMemcpyAsync(d_idx, prob_idx, sizeof(int) * B, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(d_u, u, sizeof(double) * (size_t)B * ldu, cudaMemcpyHostToDevice, b->stream));
+    int rc = launch_logp(b, B, d_idx, d_u, ldu, jac, d_lp, d_g, d_st, d_dbg, dbg_stride, b->stream);
+    if (rc == BSYN_OK) {
+        CK(cudaMemcpyAsync(lp, d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(status, d_st, sizeof(int) * B, cudaMemcpyDeviceToHost, b->stream));
+        if (grad) CK(cudaMemcpyAsync(grad, d_g, sizeof(double) * (size_t)B * ldu, cudaMemcpyDeviceToHost, b->stream));
+        if (dbg) CK(cudaMemcpyAsync(dbg, d_dbg, sizeof(double) * (size_t)B * dbg_stride, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    cudaFree(d_idx); cudaFree(d_st); cudaFree(d_u); cudaFree(d_lp); cudaFree(d_g); cudaFree(d_dbg);
+    return rc;
+}
+
+extern "C" int bsyn_logp_grad(bsyn_batch *b, int32_t B, const int32_t *prob_idx, const double *u, int32_t ldu,
+                              int32_t jacobian, double *lp, double *grad, int32_t *status)
+{
+    return logp_host(b, B, prob_idx, u, ldu, jacobian, lp, grad, status, nullptr, 0);
+}
+extern "C" int bsyn_logp_grad_debug(bsyn_batch *b, int32_t B, const int32_t *prob_idx, const double *u, int32_t ldu,
+                                    int32_t jacobian, double *lp, double *grad, int32_t *status, double *dbg,
+                                    int32_t dbg_stride)
+{
+    return logp_host(b, B, prob_idx, u, ldu, jacobian, lp, grad, status, dbg, dbg_stride);
+}
+extern "C" int bsyn_debug_layout(const bsyn_batch *b, int32_t *nm, int32_t *nn, int32_t *gm)
+{
+    if (!b) return BSYN_ERR_ARG;
+    int NM = b->cpl == 1 ? 6 : b->cpl == 2 ? 8 : b->cpl == 4 ? 12 : 16;
+    *nm = NM; *nn = NM * NM; *gm = 32 * b->cpl;
+    return BSYN_OK;
+}
+
+extern "C" int bsyn_write_array(bsyn_batch *b, int32_t B, const int32_t *prob_idx, const double *u, int32_t ldu,
+                                double *out, int32_t ldo, uint64_t seed, int32_t *status)
+{
+    if (!b || B < 0 || !prob_idx || !u || !out || !status || ldu < b->maxD || ldo < b->maxOut) return fail(BSYN_ERR_ARG, "bsyn_write_array: bad argument");
+    if (B == 0) return BSYN_OK;
+    for (int k = 0; k < B; ++k)
+        if (prob_idx[k] < 0 || prob_idx[k] >= b->n) return fail(BSYN_ERR_ARG, "bsyn_write_array: prob_idx out of range");
+    CK(cudaSetDevice(b->device));
+    int *d_idx = nullptr, *d_st = nullptr;
+    double *d_u = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_idx, sizeof(int) * B)); CK(cudaMalloc(&d_st, sizeof(int) * B));
+    CK(cudaMalloc(&d_u, sizeof(double) * (size_t)B * ldu)); CK(cudaMalloc(&d_out, sizeof(double) * (size_t)B * ldo));
+    CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)B * ldo, b->stream));
+    CK(cudaMemcpyAsync(d_idx, prob_idx, sizeof(int) * B, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(d_u, u, sizeof(double) * (size_t)B * ldu, cudaMemcpyHostToDevice, b->stream));
+    size_t bytes;
+    SmemLayout sl = make_layout(b, true, &bytes);
+    int grid = std::max(1, std::min((B + WPC - 1) / WPC, b->num_sms * 8));
+    DISPATCH_CPL(b->cpl, {
+        CK(cudaFuncSetAttribute(write_array_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        write_array_kernel<CPL><<<grid, 32 * WPC, bytes, b->stream>>>(b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B,
+                                                                    d_idx, d_u, ldu, d_out, ldo, seed, d_st);
+    });
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)B * ldo, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(status, d_st, sizeof(int) * B, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    cudaFree(d_idx); cudaFree(d_st); cudaFree(d_u); cudaFree(d_out);
+    return BSYN_OK;
+}
+
+// transform_inits (h:803-1075): constrained -> unconstrained, host arithmetic (lub_free / lb_free)
+extern "C" int bsyn_unconstrain(const bsyn_batch *b, int32_t k, const double *theta, double *u)
+{
+    if (!b || k < 0 || k >= b->n || !theta || !u) return fail(BSYN_ERR_ARG, "bsyn_unconstrain: bad argument");
+    const ProbDesc &d = b->descs[k];
+    const Flags &F = b->F;
+    int pos = 0;
+    auto lb = [&](double v) { if (!(v >= 0)) return false; u[pos] = log(v); ++pos; return true; };
+    if (F.est_la)
+        for (int t = 0; t < 2; ++t) {
+            double v = theta[pos];
+            if (!(v >= 0 && v <= 1)) return fail(BSYN_ERR_ARG, "bsyn_unconstrain: la out of [0,1]");
+            u[pos] = log(v / (1 - v)); ++pos;
+        }
+    for (int t = 0; t < 4; ++t) { u[pos] = theta[pos]; ++pos; }
+    for (int t = 0; t < 2; ++t) if (!lb(theta[pos])) return fail(BSYN_ERR_ARG, "bsyn_unconstrain: slope < 0");
+    if (F.model == 0) {
+        for (int t = 0; t < 4 + F.est_alpha; ++t) if (!lb(theta[pos])) return fail(BSYN_ERR_ARG, "bsyn_unconstrain: negative scale parameter");
+        for (int t = 0; t < d.G; ++t) { u[pos] = theta[pos]; ++pos; }
+    }
+    for (int t = 0; t < 3; ++t) if (!lb(theta[pos])) return fail(BSYN_ERR_ARG, "bsyn_unconstrain: negative variance parameter");
+    return BSYN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" void bsyn_sampler_defaults(bsyn_sampler_args *a)
+{
+    a->chains = 4; a->iter = 2000; a->warmup = 1000; a->thin = 1; a->seed = 1;
+    a->init_r = 2.0; a->adapt_delta = 0.9; a->stepsize = 1.0; a->stepsize_jitter = 0.0;
+    a->max_treedepth = 10; a->metric = 0;
+    a->adapt_gamma = 0.05; a->adapt_kappa = 0.75; a->adapt_t0 = 10.0;
+    a->adapt_init_buffer = 75; a->adapt_term_buffer = 50; a->adapt_window = 25;
+    a->save_warmup = 0;
+}
+
+static int ensure(double **p, size_t *have, size_t need)
+{
+    if (*have >= need && *p) return BSYN_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    if (cudaMalloc(p, sizeof(double) * std::max<size_t>(need, 1)) != cudaSuccess) return fail(BSYN_ERR_ALLOC, "device allocation failed");
+    *have = need;
+    return BSYN_OK;
+}
+
+struct DevSinks {
+    double *draws = nullptr, *udraws = nullptr, *cpo = nullptr, *inv_metric = nullptr;
+    long long ld_draws = 0, ld_u = 0;
+    int ld_cpo = 0, ld_im = 0;
+};
+
+static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks &ds, int64_t *total_grad, float *elapsed_ms)
+{
+    if (a->chains < 1 || a->iter < 1 || a->warmup < 0 || a->warmup > a->iter || a->thin < 1 || a->max_treedepth < 1 || a->max_treedepth > 20)
+        return fail(BSYN_ERR_ARG, "bsyn_sample: bad sampler arguments");
+    if (a->metric != 0) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample: metric = dense_e is not implemented yet (diag_e only)");
+    CK(cudaSetDevice(b->device));
+    SamplerParams sp{};
+    sp.n_problems = b->n; sp.chains = a->chains; sp.groups = (a->chains + WPC - 1) / WPC;
+    sp.iter = a->iter; sp.warmup = a->warmup; sp.thin = a->thin; sp.max_depth = a->max_treedepth; sp.save_warmup = a->save_warmup;
+    const int ns_samp = (a->iter - a->warmup + a->thin - 1) / a->thin, ns_warm = a->save_warmup ? (a->warmup + a->thin - 1) / a->thin : 0;
+    sp.n_save = ns_samp + ns_warm;
+    sp.init_r = a->init_r; sp.delta = a->adapt_delta; sp.stepsize0 = a->stepsize; sp.jitter = a->stepsize_jitter;
+    sp.gamma = a->adapt_gamma; sp.kappa = a->adapt_kappa; sp.t0 = a->adapt_t0;
+    sp.init_buffer = a->adapt_init_buffer; sp.term_buffer = a->adapt_term_buffer; sp.window = a->adapt_window;
+    sp.seed = a->seed; sp.jacobian = 1;
+    const size_t nrows = (size_t)b->n * a->chains * sp.n_save;
+    int rc;
+    if ((rc = ensure(&b->d_qdraws, &b->qdraws_elems, nrows * BSYN_NQ))) return rc;
+    if ((rc = ensure(&b->d_sp, &b->sp_elems, nrows * BSYN_NSP))) return rc;
+    if ((rc = ensure(&b->d_chain_stats, &b->cs_elems, (size_t)b->n * a->chains * 8))) return rc;
+    if ((rc = ensure(&b->d_summary, &b->summary_elems, (size_t)b->n * BSYN_NQ * 2))) return rc;
+    b->last_chains = a->chains; b->last_nsave = sp.n_save; b->last_nskip = ns_warm;
+    sp.qdraws = b->d_qdraws; sp.sp = b->d_sp; sp.chain_stats = b->d_chain_stats;
+    sp.draws = ds.draws; sp.ld_draws = ds.ld_draws; sp.udraws = ds.udraws; sp.ld_u = ds.ld_u;
+    sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im;
+    size_t bytes;
+    sp.sl = make_layout(b, false, &bytes);
+    // persistent grid: as many CTAs as fit, capped by the number of work items
+    int per_sm = 1;
+    DISPATCH_CPL(b->cpl, {
+        CK(cudaFuncSetAttribute(nuts_kernel<CPL, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nuts_kernel<CPL, WPC>, 32 * WPC, bytes));
+    });
+    if (per_sm < 1) return fail(BSYN_ERR_UNSUPPORTED, "sampler kernel does not fit on an SM");
+    const int n_items = b->n * sp.groups;
+    const int grid = std::max(1, std::min(n_items, per_sm * b->num_sms));
+    const int VS = (b->cpl + 1) * 32;
+    sp.arena_stride = (long long)arena_vectors(a->max_treedepth) * VS;
+    if ((rc = ensure(&b->d_arena, &b->arena_elems, (size_t)grid * WPC * sp.arena_stride))) return rc;
+    sp.arena = b->d_arena;
+    sp.grad_counter = b->d_gradctr; sp.work_counter = b->d_workctr;
+    CK(cudaMemsetAsync(b->d_gradctr, 0, sizeof(unsigned long long), b->stream));
+    CK(cudaMemsetAsync(b->d_workctr, 0, sizeof(int), b->stream));
+    CK(cudaMemsetAsync(b->d_qdraws, 0, sizeof(double) * nrows * BSYN_NQ, b->stream));
+    CK(cudaMemsetAsync(b->d_sp, 0, sizeof(double) * nrows * BSYN_NSP, b->stream));
+    CK(cudaMemsetAsync(b->d_chain_stats, 0, sizeof(double) * (size_t)b->n * a->chains * 8, b->stream));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, b->stream));
+    DISPATCH_CPL(b->cpl, {
+        nuts_kernel<CPL, WPC><<<grid, 32 * WPC, bytes, b->stream>>>(b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sp);
+    });
+    ++g_launches;
+    CK(cudaGetLastError());
+    // per-problem posterior summaries (mean, sd over all chains and saved sampling draws)
+    {
+        const int g2 = std::max(1, std::min((b->n + WPC - 1) / WPC, b->num_sms * 8));
+        summary_kernel<<<g2, 32 * WPC, 0, b->stream>>>(b->d_qdraws, b->n, a->chains, sp.n_save, ns_warm, b->d_summary);
+        ++g_launches;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(e1, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (elapsed_ms) *elapsed_ms = ms;
+    unsigned long long ng = 0;
+    CK(cudaMemcpy(&ng, b->d_gradctr, sizeof(ng), cudaMemcpyDeviceToHost));
+    if (total_grad) *total_grad = (int64_t)ng;
+    return BSYN_OK;
+}
+
+extern "C" int bsyn_sample_device(bsyn_batch *b, const bsyn_sampler_args *args, int64_t *total_grad_evals, float *elapsed_ms,
+                                  const double **d_qdraws, const double **d_sampler_params, const double **d_summary)
+{
+    if (!b || !args) return fail(BSYN_ERR_ARG, "bsyn_sample_device: null argument");
+    DevSinks ds;
+    int rc = run_sampler(b, args, ds, total_grad_evals, elapsed_ms);
+    if (rc) return rc;
+    if (d_qdraws) *d_qdraws = b->d_qdraws;
+    if (d_sampler_params) *d_sampler_params = b->d_sp;
+    if (d_summary) *d_summary = b->d_summary;
+    return BSYN_OK;
+}
+
+extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const bsyn_sample_sinks *sinks, int64_t *total_grad_evals)
+{
+    if (!b || !args || !sinks) return fail(BSYN_ERR_ARG, "bsyn_sample: null argument");
+    CK(cudaSetDevice(b->device));
+    const int ns_samp = (args->iter - args->warmup + args->thin - 1) / std::max(1, args->thin);
+    const int ns_warm = args->save_warmup ? (args->warmup + args->thin - 1) / std::max(1, args->thin) : 0;
+    const size_t n_save = (size_t)ns_samp + ns_warm;
+    const size_t nrows = (size_t)b->n * args->chains * n_save;
+    const size_t nch = (size_t)b->n * args->chains;
+    DevSinks ds;
+    int rc = BSYN_OK;
+    if (sinks->draws) {
+        if (sinks->ld_draws < b->maxOut) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_draws < bsyn_max_outputs");
+        ds.ld_draws = sinks->ld_draws;
+        if (cudaMalloc(&ds.draws, sizeof(double) * nrows * ds.ld_draws) != cudaSuccess) return fail(BSYN_ERR_ALLOC, "draws buffer does not fit on the device; use the summary sinks");
+        cudaMemsetAsync(ds.draws, 0, sizeof(double) * nrows * ds.ld_draws, b->stream);
+    }
+    if (sinks->udraws) {
+        if (sinks->ld_udraws < b->maxD) { cudaFree(ds.draws); return fail(BSYN_ERR_ARG, "bsyn_sample: ld_udraws < bsyn_max_params"); }
+        ds.ld_u = sinks->ld_udraws;
+        if (cudaMalloc(&ds.udraws, sizeof(double) * nrows * ds.ld_u) != cudaSuccess) { cudaFree(ds.draws); return fail(BSYN_ERR_ALLOC, "udraws buffer does not fit on the device"); }
+        cudaMemsetAsync(ds.udraws, 0, sizeof(double) * nrows * ds.ld_u, b->stream);
+    }
+    if (sinks->cpo_mean) {
+        if (sinks->ld_cpo < b->maxN) { cudaFree(ds.draws); cudaFree(ds.udraws); return fail(BSYN_ERR_ARG, "bsyn_sample: ld_cpo < max N"); }
+        ds.ld_cpo = b->maxN;
+        if (cudaMalloc(&ds.cpo, sizeof(double) * nch * std::max(1, ds.ld_cpo)) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); return fail(BSYN_ERR_ALLOC, "cpo buffer"); }
+        cudaMemsetAsync(ds.cpo, 0, sizeof(double) * nch * std::max(1, ds.ld_cpo), b->stream);
+    }
+    if (sinks->inv_metric) {
+        ds.ld_im = b->maxD;
+        if (cudaMalloc(&ds.inv_metric, sizeof(double) * nch * ds.ld_im) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); return fail(BSYN_ERR_ALLOC, "inv_metric buffer"); }
+        cudaMemsetAsync(ds.inv_metric, 0, sizeof(double) * nch * ds.ld_im, b->stream);
+    }
+    rc = run_sampler(b, args, ds, total_grad_evals, nullptr);
+    if (rc == BSYN_OK) {
+        cudaError_t e = cudaSuccess;
+        if (sinks->draws) e = cudaMemcpy(sinks->draws, ds.draws, sizeof(double) * nrows * ds.ld_draws, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sinks->udraws) e = cudaMemcpy(sinks->udraws, ds.udraws, sizeof(double) * nrows * ds.ld_u, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sinks->qdraws) e = cudaMemcpy(sinks->qdraws, b->d_qdraws, sizeof(double) * nrows * BSYN_NQ, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sinks->sampler_params) e = cudaMemcpy(sinks->sampler_params, b->d_sp, sizeof(double) * nrows * BSYN_NSP, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sinks->summary) e = cudaMemcpy(sinks->summary, b->d_summary, sizeof(double) * (size_t)b->n * BSYN_NQ * 2, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sinks->chain_stats) e = cudaMemcpy(sinks->chain_stats, b->d_chain_stats, sizeof(double) * nch * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sinks->inv_metric) e = cudaMemcpy(sinks->inv_metric, ds.inv_metric, sizeof(double) * nch * ds.ld_im, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sinks->cpo_mean) {
+            // mean over chains and sampling draws of CPO_n
+            std::vector<double> tmp(nch * std::max(1, ds.ld_cpo));
+            e = cudaMemcpy(tmp.data(), ds.cpo, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) {
+                for (int k = 0; k < b->n; ++k) {
+                    double *o = sinks->cpo_mean + (size_t)k * sinks->ld_cpo;
+                    for (int n = 0; n < b->descs[k].N; ++n) {
+                        double s = 0;
+                        for (int c = 0; c < args->chains; ++c) s += tmp[((size_t)k * args->chains + c) * ds.ld_cpo + n];
+                        o[n] = s / ((double)args->chains * ns_samp);
+                    }
+                }
+            }
+        }
+        if (e != cudaSuccess) rc = fail(BSYN_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
+    }
+    cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric);
+    return rc;
+}
+
+extern "C" int bsyn_ess(bsyn_batch *b, int32_t q, double *ess, double *rhat)
+{
+    if (!b || q < 0 || q >= BSYN_NQ || !ess) return fail(BSYN_ERR_ARG, "bsyn_ess: bad argument");
+    if (!b->d_qdraws || b->last_nsave - b->last_nskip < 8) return fail(BSYN_ERR_ARG, "bsyn_ess: no draws from a previous bsyn_sample call");
+    CK(cudaSetDevice(b->device));
+    double *d_out = nullptr;
+    CK(cudaMalloc(&d_out, sizeof(double) * 2 * b->n));
+    const int grid = std::max(1, std::min((b->n + WPC - 1) / WPC, b->num_sms * 16));
+    ess_kernel<<<grid, 32 * WPC, 0, b->stream>>>(b->d_qdraws, b->n, b->last_chains, b->last_nsave, b->last_nskip, q, d_out);
+    ++g_launches;
+    CK(cudaGetLastError());
+    std::vector<double> tmp(2 * (size_t)b->n);
+    CK(cudaMemcpyAsync(tmp.data(), d_out, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    cudaFree(d_out);
+    for (int k = 0; k < b->n; ++k) { ess[k] = tmp[2 * k]; if (rhat) rhat[k] = tmp[2 * k + 1]; }
+    return BSYN_OK;
+}

@@ -1,0 +1,152 @@
+// bsyn_common.cuh -- shared definitions for the sm_100a kernels of the gp_grid / nointeraction path.
+//
+// Mapping: ONE WARP = ONE CHAIN.  A D-vector (position, momentum, gradient ...) is
+// spread over the 32 lanes as
+//     zc[t]  (t < CPL)  : GP cell c = lane + 32*t  (cell c <-> z[i,j], i = c % n2, j = c / n2, the
+//                         reference's column-major z, src/stanExports_gp_grid.h:1190-1196)
+//     sc               : canonical scalar slot `lane` (lanes 0..15, see enum Slot)
+// so leapfrog updates, dot products and the per-cell model algebra are register-only.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace bsyn {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// canonical scalar slots (lane index).  Order = the reference's parameter order with la_k / alpha
+// always given a slot (inactive slots carry 0 and never move).
+enum Slot {
+    SL_LA1 = 0, SL_LA2, SL_M1, SL_M2, SL_TH1, SL_TH2, SL_SL1, SL_SL2, SL_B1, SL_B2, SL_ELL, SL_SIGF,
+    SL_ALPHA, SL_S, SL_S21, SL_S22, SL_COUNT
+};
+
+// Options uniform over a batch (the scalar Stan data fields) + derived constants
+// (gp_grid.stan:37-38, 43-44).
+struct Flags {
+    int model, est_la, robust, pcprior, het, kernel, nu_matern, est_alpha;
+    double lambda, tau, lamL, lam1, lam2;
+    double log_lam12; // log(lam1) + log(lam2)
+    double lptn_c0;   // -tau^2/2 + log(tau) + (lamL+1) log(log(tau))  (tail branch constant, without -log(2pi)/2)
+    unsigned active_mask;   // bit s set <=> scalar slot s is a parameter of this model
+};
+
+// Per-problem descriptor in global memory; all offsets index the batch-wide pools.
+struct ProbDesc {
+    int n1, n2, N, G;        // G = n1*n2
+    int ncf;                 // (n1+1)*(n2+1) cells of f
+    int D, n_out;
+    int off_d;               // doubles pool: x1[n1] x2[n2] vw1[n1] vw2[n2] dist[P1+P2] cnt[ncf] ybar[ncf] ss[ncf] ysort[N] y[N]
+    int off_i;               // ints pool: pr[P1+P2] cstart[ncf+1] ii0[N] (0-based f index, original order)
+    int n_d_smem;            // doubles copied to shared memory per CTA (without y[N]; without ysort if !robust)
+    int n_i_smem;            // ints copied to shared memory (cstart only, and only if robust)
+};
+
+template <int CPL> struct Cfg {
+    static constexpr int NM = (CPL == 1) ? 6 : (CPL == 2) ? 8 : (CPL == 4) ? 12 : 16;  // max n per axis
+    static constexpr int NN = NM * NM;
+    static constexpr int GM = 32 * CPL;                 // max GP cells
+    static constexpr int MB = (GM > NN) ? GM : NN;      // size of one matrix scratch buffer
+    static constexpr int PK = NM * (NM - 1);            // max off-diagonal pairs, both axes
+    static constexpr int TR = NM * (NM + 1) / 2;        // packed lower-triangular entries of one matrix
+    // per-warp scratch, in doubles
+    static constexpr int OFF_TH = 0;                    // th[16] constrained scalars, ur[16] raw (unconstrained)
+    static constexpr int OFF_UR = 16;
+    static constexpr int OFF_PM = 32;                   // pm[32]: p01 then p02
+    static constexpr int OFF_PMB = 64;                  // 3*32 mono backward products
+    static constexpr int OFF_INVD = 160;                // 2*16 inverse Cholesky diagonals
+    static constexpr int OFF_L1R = 192;
+    static constexpr int OFF_L2R = OFF_L1R + NN;
+    static constexpr int OFF_L2C = OFF_L2R + NN;
+    static constexpr int OFF_M0 = OFF_L2C + NN;
+    static constexpr int OFF_M1 = OFF_M0 + MB;
+    static constexpr int OFF_M2 = OFF_M1 + MB;
+    static constexpr int OFF_M3 = OFF_M2 + MB;
+    static constexpr int OFF_LB1 = OFF_M3 + MB;
+    static constexpr int OFF_LB2 = OFF_LB1 + NN;
+    static constexpr int OFF_EX = OFF_LB2 + NN;         // exp table per pair
+    static constexpr int WS_DOUBLES = OFF_EX + PK + (PK & 1);
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double half_sum(double v)   // sum within each half-warp
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Problem view in shared memory (one per CTA, shared by its warps)
+struct ProbS {
+    int n1, n2, N, G, ncf, P1, P2, T1, T2;
+    const double *xs;      // x1 then x2
+    const double *vw;      // VUS trapezoid weights: w1[n1] (incl. 100/area) then w2[n2]
+    const double *cnt, *ybar, *ss;
+    const double *ysort;   // robust only
+    const int *cstart;     // robust only
+    const double *dist;    // [P1+P2] pair distances
+    const int *pr;         // [P1+P2] (a<<8)|b, a > b
+    const int *tri;        // [TR] (r<<8)|c, c <= r, packed row-major lower triangle
+};
+
+// ---- Philox4x32-10 counter RNG (Salmon et al. 2011), stateless: every draw is a pure function of
+// (seed, chain, lane-or-warp tag, iteration, draw index), so no RNG state lives in registers. ----
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                           uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u01_from_bits(uint32_t a, uint32_t b)   // (0,1), 53 bits
+{
+    uint64_t v = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11);
+    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+// RNG stream tags (c2 low byte = lane, or 0xFF for warp-uniform draws)
+enum RngTag { RT_INIT = 1, RT_MOM = 2, RT_DIR = 3, RT_LEAF = 4, RT_TOP = 5, RT_JIT = 6, RT_GQ = 7, RT_ISTEP = 8 };
+
+struct RngKey {
+    uint32_t k0, k1, chain;
+};
+// two uniforms for (tag, lane_field, iter, idx)
+__device__ __forceinline__ void rng_u2(const RngKey &k, uint32_t tag, uint32_t lane_field, uint32_t iter,
+                                       uint32_t idx, double &ua, double &ub)
+{
+    uint32_t o[4];
+    philox4x32(idx, iter, lane_field | (tag << 8), k.chain, k.k0, k.k1, o);
+    ua = u01_from_bits(o[0], o[1]);
+    ub = u01_from_bits(o[2], o[3]);
+}
+// warp-uniform U(0,1): identical on every lane, no shuffle needed
+__device__ __forceinline__ double rng_warp_uniform(const RngKey &k, uint32_t tag, uint32_t iter, uint32_t idx)
+{
+    double a, b;
+    rng_u2(k, tag, 0xFFu, iter, idx, a, b);
+    return a;
+}
+// two independent N(0,1) per lane (Box-Muller)
+__device__ __forceinline__ void rng_lane_normal2(const RngKey &k, uint32_t tag, uint32_t iter, uint32_t idx,
+                                                 double &na, double &nb)
+{
+    double u1, u2, s, c;
+    rng_u2(k, tag, (uint32_t)(threadIdx.x & 31), iter, idx, u1, u2);
+    sincospi(2.0 * u2, &s, &c);
+    double r = sqrt(-2.0 * log(u1));
+    na = r * c;
+    nb = r * s;
+}
+
+}  // namespace bsyn

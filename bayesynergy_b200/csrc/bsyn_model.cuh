@@ -1,0 +1,699 @@
+// bsyn_model.cuh -- warp-cooperative log-density, hand-derived gradient and write_array of the
+// gp_grid / nointeraction models.  One warp evaluates one (combination, chain).
+//
+// What it computes = reference model_gp_grid::log_prob<false,jacobian,var> + reverse sweep
+// (src/stanExports_gp_grid.h:1076-1577; inst/stan/gp_grid.stan:64-233) and model_nointeraction::log_prob
+// (src/stanExports_nointeraction.h:660-955); write_array = h:1705-2235.  It is NOT a translation of the
+// generated C++: the Kronecker product uses the triangular structure, the Normal likelihoods use per-cell
+// sufficient statistics, the Delta transform is evaluated without the logit, and all adjoints are
+// hand-derived.
+#pragma once
+#include "bsyn_common.cuh"
+
+namespace bsyn {
+
+#define BSYN_LOG_2PI_HALF 0.91893853320467274178
+#define BSYN_LN10 2.30258509299404568402
+#define BSYN_LOG_PI 1.14472988584940017414
+#define BSYN_LOG_2 0.69314718055994530942
+#define BSYN_SQRT3 1.73205080756887729353
+#define BSYN_SQRT5 2.23606797749978969641
+// lgamma(2.25) - lgamma(1) - lgamma(1.25)  (beta(1,1.25) normaliser) = log(1.25)
+#define BSYN_BETA_C 0.22314355131420927
+#define BSYN_IG55_C 4.869135731822556          /* 5 log 5 - lgamma(5) */
+#define BSYN_IG32_C 1.38629436111989061883     /* 3 log 2 - lgamma(3) */
+#define BSYN_LOG_0_1 (-2.30258509299404568402)
+
+template <int CPL> struct WVec {
+    double z[CPL];
+    double s;
+};
+
+// cell descriptor per lane slot t: i | j<<8 | valid<<16 | (valid && z is a parameter)<<17
+template <int CPL> __device__ __forceinline__ void make_cells(const Flags &F, const ProbS &P, int (&cell)[CPL])
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+        int c = lane + 32 * t;
+        int valid = c < P.G;
+        int cc = valid ? c : 0;
+        int j = cc / P.n2, i = cc - j * P.n2;
+        cell[t] = i | (j << 8) | (valid << 16) | ((valid && F.model == 0) << 17);
+    }
+}
+
+// kernel value from the stored exponential (and, for the backward pass, its partials)
+__device__ __forceinline__ double kern_arg(const Flags &F, double d, double iell, double alpha)
+{
+    // argument x of ev = exp(x) (RQ: ev = exp(-alpha*log1p(w)) handled by the caller)
+    if (F.kernel == 1) return -0.5 * d * d * iell * iell;
+    if (F.nu_matern == 1) return -d * iell;
+    if (F.nu_matern == 2) return -BSYN_SQRT3 * d * iell;
+    return -BSYN_SQRT5 * d * iell;
+}
+__device__ __forceinline__ double kern_val(const Flags &F, double d, double iell, double ev)
+{
+    if (F.kernel == 2 && F.nu_matern == 2) { double r = BSYN_SQRT3 * d * iell; return (1.0 + r) * ev; }
+    if (F.kernel == 2 && F.nu_matern == 3) { double r = BSYN_SQRT5 * d * iell; return (1.0 + r + r * r * (1.0 / 3.0)) * ev; }
+    return ev;
+}
+__device__ __forceinline__ void kern_partials(const Flags &F, double d, double iell, double alpha, double ev,
+                                              double &kv, double &dk, double &da)
+{
+    da = 0.0;
+    if (F.kernel == 1) { kv = ev; dk = ev * d * d * iell * iell * iell; }
+    else if (F.kernel == 2) {
+        if (F.nu_matern == 1) { kv = ev; dk = ev * d * iell * iell; }
+        else if (F.nu_matern == 2) { double r = BSYN_SQRT3 * d * iell; kv = (1.0 + r) * ev; dk = r * r * ev * iell; }
+        else { double r = BSYN_SQRT5 * d * iell; kv = (1.0 + r + r * r * (1.0 / 3.0)) * ev; dk = r * r * (1.0 / 3.0) * (1.0 + r) * ev * iell; }
+    } else {
+        double w = d * d * iell * iell / (2.0 * alpha);
+        double iw = 1.0 / (1.0 + w);
+        kv = ev;
+        dk = 2.0 * alpha * w * ev * iw * iell;
+        da = ev * (-log1p(w) + w * iw);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GP forward: kernel matrices -> two Cholesky factors (one per half-warp, rows in registers, pivots and
+// columns exchanged by shuffles) -> GP = L2 * Z * L1^T with the triangular structure.
+// Leaves in scratch: L1r, L2r (row-major), L2c (column-major), invd (1/diag), exv (exp table),
+// M0 = Z, M1 = T = L2*Z.  Returns GP values of this lane's cells in Gv.
+template <int CPL>
+__device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, double *ws, const int (&cell)[CPL],
+                                           const double (&z)[CPL], double (&Gv)[CPL])
+{
+    using C = Cfg<CPL>;
+    constexpr int NM = C::NM;
+    const int lane = threadIdx.x & 31;
+    const int n1 = P.n1, n2 = P.n2;
+    const double *th = ws + C::OFF_TH;
+    double *invd = ws + C::OFF_INVD, *L1r = ws + C::OFF_L1R, *L2r = ws + C::OFF_L2R, *L2c = ws + C::OFF_L2C;
+    double *M0 = ws + C::OFF_M0, *M1 = ws + C::OFF_M1, *exv = ws + C::OFF_EX;
+    const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA];
+    const double iell = 1.0 / th[SL_ELL];
+    const int P1 = P.P1, Pn = P.P1 + P.P2;
+    for (int e0 = lane; e0 < Pn; e0 += 32) {
+        double d = P.dist[e0];
+        int ab = P.pr[e0], a = ab >> 8, b = ab & 255;
+        double ev;
+        if (F.kernel == 3) {
+            double w = d * d * iell * iell / (2.0 * alpha);
+            ev = exp(-alpha * log1p(w));
+        } else {
+            ev = exp(kern_arg(F, d, iell, alpha));
+        }
+        exv[e0] = ev;
+        double kv = kern_val(F, d, iell, ev);
+        if (e0 < P1) M0[a * NM + b] = sigf * kv; else M1[a * NM + b] = kv;
+    }
+    __syncwarp();
+    // Cholesky: half-warp h factorises matrix h; lane r of the half holds row r.
+    const int h = lane >> 4, r = lane & 15;
+    const int n = h ? n2 : n1;
+    bool ok = true;
+    {
+        const double *A = h ? M1 : M0;
+        const double dg = h ? (1.0 + 1e-10) : (sigf + 1e-10);
+        double a[NM];
+#pragma unroll
+        for (int k = 0; k < NM; ++k) {
+            double v = 0.0;
+            if (r < n && k < r) v = A[r * NM + k];
+            if (k == r) v = (r < n) ? dg : 1.0;
+            a[k] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < NM; ++k) {
+            double dkk = __shfl_sync(FULL, a[k], (lane & 16) + k);
+            ok = ok && (dkk > 0.0);
+            double inv = rsqrt(dkk);
+            a[k] *= inv;
+            if (r == k) invd[h * 16 + k] = inv;
+#pragma unroll
+            for (int j = k + 1; j < NM; ++j) {
+                double ljk = __shfl_sync(FULL, a[k], (lane & 16) + j);
+                if (r >= j) a[j] = fma(-a[k], ljk, a[j]);
+            }
+        }
+        __syncwarp();   // all reads of M0/M1 (A) are done before they are reused below
+        double *Lr = h ? L2r : L1r;
+        if (r < NM) {
+#pragma unroll
+            for (int k = 0; k < NM; ++k) {
+                Lr[r * NM + k] = a[k];
+                if (h) L2c[k * NM + r] = a[k];
+            }
+        }
+    }
+    // Z -> M0 ; T = L2*Z -> M1 ; G = T*L1^T
+#pragma unroll
+    for (int t = 0; t < CPL; ++t)
+        if (cell[t] >> 16) M0[lane + 32 * t] = z[t];
+    __syncwarp();
+    double acc[CPL];
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) acc[t] = 0.0;
+    for (int k = 0; k < n2; ++k) {
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) {
+            int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
+            if ((cell[t] >> 16) && k <= i) acc[t] = fma(L2c[k * NM + i], M0[k + j * n2], acc[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < CPL; ++t)
+        if (cell[t] >> 16) M1[lane + 32 * t] = acc[t];
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) Gv[t] = 0.0;
+    for (int l = 0; l < n1; ++l) {
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) {
+            int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
+            if ((cell[t] >> 16) && l <= j) Gv[t] = fma(M1[i + l * n2], L1r[j * NM + l], Gv[t]);
+        }
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Constrain this lane's scalar slot (h:1086-1215, Stan Math lub_constrain/lb_constrain semantics) and
+// publish th[16] / ur[16] to the warp scratch.  Returns the constrained value; e = exp(x) where
+// x = -|u| (la slots) or u (lb slots).
+__device__ __forceinline__ double constrain_slot(const Flags &F, double u, double *th, double *ur, double &e)
+{
+    const int lane = threadIdx.x & 31;
+    const bool act = (F.active_mask >> lane) & 1u;
+    const bool is_la = lane < 2, is_lb = (lane >= SL_SL1) && (lane < SL_COUNT);
+    e = exp(is_la ? -fabs(u) : u);
+    double thv;
+    if (is_la) {
+        double rr = 1.0 / (1.0 + e);
+        if (u > 0) { thv = rr; if (thv == 1.0) thv = 1.0 - 1e-15; }
+        else { thv = 1.0 - rr; if (thv == 0.0) thv = 1e-15; }
+    } else if (is_lb) {
+        thv = e;
+    } else {
+        thv = u;
+    }
+    if (!act) thv = 0.0;
+    if (lane < 16) { th[lane] = thv; ur[lane] = u; }
+    __syncwarp();
+    return thv;
+}
+
+// Likelihood of one cell of f (gp_grid.stan:212-232) from its sufficient statistics (Normal variants) or
+// its sorted observations (LPTN variants).  Adds to lpl / slogbar, returns d lp / d f.
+// The per-observation constants  -log(2pi)/2 - log(s)  are added once per evaluation by the caller.
+__device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int fc, double f, double s, double is2,
+                                           double &lpl, double &slogbar, bool &ok)
+{
+    const double n = P.cnt[fc];
+    if (n == 0.0) return 0.0;
+    double fbar;
+    if (!F.robust) {
+        const double d = P.ybar[fc] - f;
+        const double Q = fma(n * d, d, P.ss[fc]);
+        if (F.het) {
+            const double v = f + F.lambda;
+            if (!(v > 0.0)) { ok = false; return 0.0; }
+            const double iv = 1.0 / v;
+            lpl += -0.5 * n * log(v) - 0.5 * Q * is2 * iv;
+            fbar = iv * (-0.5 * n + is2 * (n * d + 0.5 * Q * iv));
+            slogbar += -n + Q * is2 * iv;
+        } else {
+            lpl += -0.5 * Q * is2;
+            fbar = n * d * is2;
+            slogbar += -n + Q * is2;
+        }
+    } else {
+        double iv = 0.0, isd = 1.0 / s;
+        if (F.het) {
+            const double v = f + F.lambda;
+            if (!(v > 0.0)) { ok = false; return 0.0; }
+            iv = 1.0 / v;
+            isd = rsqrt(v) / s;
+            lpl += -0.5 * n * log(v);
+        }
+        fbar = -0.5 * n * iv;
+        const int o1 = P.cstart[fc + 1];
+        for (int o = P.cstart[fc]; o < o1; ++o) {
+            const double r = (P.ysort[o] - f) * isd;
+            const double ar = fabs(r);
+            double dl;
+            if (ar <= F.tau) {
+                lpl += -0.5 * r * r;
+                dl = -r;
+            } else {
+                const double az = fmax(ar, 1.0001);
+                const double la = log(az);
+                lpl += F.lptn_c0 - la - (F.lamL + 1.0) * log(la);
+                dl = (ar > 1.0001) ? -copysign(1.0, r) / az * (1.0 + (F.lamL + 1.0) / la) : 0.0;
+            }
+            fbar += dl * (-isd - 0.5 * r * iv);
+            slogbar += -dl * r - 1.0;
+        }
+    }
+    return fbar;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// lp(u) and d lp / d u for one (problem, point), cooperatively on one warp.
+// q / g are in lane layout.  Returns false where the reference would throw (reject): lp/g undefined.
+// dbg (DBG only): global scratch for intermediate dumps (tests).
+template <int CPL, bool DBG>
+__device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, double *ws, const int (&cell)[CPL],
+                                            const WVec<CPL> &q, const int jacobian, double &lp_out, WVec<CPL> &g,
+                                            double *dbg)
+{
+    using C = Cfg<CPL>;
+    constexpr int NM = C::NM;
+    const int lane = threadIdx.x & 31;
+    const int n1 = P.n1, n2 = P.n2, nm = n1 + n2;
+    double *th = ws + C::OFF_TH, *ur = ws + C::OFF_UR, *pm = ws + C::OFF_PM, *pmb = ws + C::OFF_PMB;
+    double *invd = ws + C::OFF_INVD, *L1r = ws + C::OFF_L1R, *L2r = ws + C::OFF_L2R;
+    double *M0 = ws + C::OFF_M0, *M1 = ws + C::OFF_M1, *M2 = ws + C::OFF_M2, *M3 = ws + C::OFF_M3;
+    double *Lb1 = ws + C::OFF_LB1, *Lb2 = ws + C::OFF_LB2, *exv = ws + C::OFF_EX;
+    const bool gp = (F.model == 0);
+    const double J = jacobian ? 1.0 : 0.0;
+    const bool act = (F.active_mask >> lane) & 1u;
+    const bool is_la = lane < 2, is_lb = (lane >= SL_SL1) && (lane < SL_COUNT);
+
+    __syncwarp();   // previous users of the scratch are done
+    // ---- 1. scalars: constrain, Jacobian, priors (gp_grid.stan:177-209) -----------------------------
+    const double u = q.s;
+    double e;
+    const double thv = constrain_slot(F, u, th, ur, e);
+    double lpl = 0.0;   // lane-local part of lp
+    double tb = 0.0;    // d lp / d(constrained scalar of this lane)
+    {
+        const double l1 = log1p(is_la ? e : (lane == SL_S ? thv * thv : 0.0));
+        if (act) {
+            if (is_la) {
+                lpl += J * (-fabs(u) - 2.0 * l1);
+                lpl += BSYN_BETA_C + 0.25 * (-fmax(u, 0.0) - l1);   // beta(1,1.25): 0.25*log1m(theta)
+                tb += -0.25 / (1.0 - thv);
+            } else if (lane == SL_M1 || lane == SL_M2) {
+                const int k = lane - SL_M1;
+                const double d = thv - th[SL_TH1 + k], is2k = 1.0 / th[SL_S21 + k];
+                lpl += -BSYN_LOG_2PI_HALF - 0.5 * ur[SL_S21 + k] - 0.5 * d * d * is2k;
+                tb += -d * is2k;
+            } else if (lane == SL_TH1 || lane == SL_TH2) {
+                const int k = lane - SL_TH1;
+                const double d = th[SL_M1 + k] - thv, is2k = 1.0 / th[SL_S21 + k];
+                lpl += -0.5 * thv * thv - BSYN_LOG_2PI_HALF;
+                tb += -thv + d * is2k;
+            } else if (lane == SL_SL1 || lane == SL_SL2) {
+                lpl += -thv + J * u;
+                tb += -1.0;
+            } else if (lane == SL_B1 || lane == SL_B2) {
+                const double rr = (thv - 1.0) * 10.0;
+                lpl += -BSYN_LOG_2PI_HALF - BSYN_LOG_0_1 - 0.5 * rr * rr + J * u;
+                tb += -(thv - 1.0) * 100.0;
+            } else if (lane == SL_ELL) {
+                const double ie = 1.0 / thv;
+                if (F.pcprior) { lpl += F.log_lam12 - 2.0 * u - F.lam1 * ie + J * u; tb += -2.0 * ie + F.lam1 * ie * ie; }
+                else { lpl += BSYN_IG55_C - 6.0 * u - 5.0 * ie + J * u; tb += -6.0 * ie + 5.0 * ie * ie; }
+            } else if (lane == SL_SIGF) {
+                if (F.pcprior) { const double sq = sqrt(thv); lpl += -F.lam2 * sq - 0.5 * u + J * u; tb += -0.5 * F.lam2 / sq - 0.5 / thv; }
+                else { lpl += -BSYN_LOG_2PI_HALF - u - 0.5 * (u - 1.0) * (u - 1.0) + J * u; tb += -u / thv; }
+            } else if (lane == SL_ALPHA) {
+                lpl += -thv + J * u;
+                tb += -1.0;
+            } else if (lane == SL_S) {
+                lpl += BSYN_LOG_2 - BSYN_LOG_PI - l1 + J * u;
+                tb += -2.0 * thv / (1.0 + thv * thv);
+            } else {   // SL_S21, SL_S22: inv_gamma(3,2) + the N(theta_k, sqrt(s2_k)) prior of log10_ec50_k
+                const int k = lane - SL_S21;
+                const double ie = 1.0 / thv, d = th[SL_M1 + k] - th[SL_TH1 + k];
+                lpl += BSYN_IG32_C - 4.0 * u - 2.0 * ie + J * u;
+                tb += -4.0 * ie + 2.0 * ie * ie - 0.5 * ie + 0.5 * d * d * ie * ie;
+            }
+        }
+    }
+    // ---- 2-4. GP forward -----------------------------------------------------------------------------
+    double Gv[CPL];
+    bool ok = true;
+    if (gp) ok = gp_forward<CPL>(F, P, ws, cell, q.z, Gv);
+    // ---- 5. monotherapy curves (gp_grid.stan:154-157) ---------------------------------------------
+    double om = 0.0, pmv = 0.0, lam = 0.0;
+    if (lane < nm) {
+        const bool d1 = lane < n1;
+        const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
+        lam = th[d1 ? SL_LA1 : SL_LA2];
+        const double Em = exp(BSYN_LN10 * sl * (P.xs[lane] - mm));
+        om = 1.0 / (1.0 + Em);
+        pmv = fma(1.0 - lam, om, lam);
+        pm[lane] = pmv;
+        ok = ok && (pmv >= 0.0) && (pmv <= 1.0);
+    }
+    __syncwarp();
+    // ---- 6. cells: Bliss product, Delta transform, likelihood and their adjoints, fused ------------
+    const double s = th[SL_S];
+    const double is2 = 1.0 / (s * s);
+    const double b1 = th[SL_B1], b2 = th[SL_B2];
+    double b1bar = 0.0, b2bar = 0.0, slogbar = 0.0;
+    double Gbar[CPL];
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+        Gbar[t] = 0.0;
+        if (cell[t] >> 16) {
+            const int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
+            const double p0 = pm[j] * pm[n1 + i], q0 = 1.0 - p0;
+            double f = p0, dfdG = 0.0, dfdb1 = 0.0, dfdb2 = 0.0, dfdp0 = 1.0;
+            ok = ok && (p0 >= 0.0) && (p0 <= 1.0);
+            if (gp) {
+                const double B = Gv[t];
+                const double e1 = exp(b1 * B), e2 = exp(-b2 * B);
+                const double iD1 = 1.0 / fma(p0, e1, q0), iD2 = 1.0 / fma(q0, e2, p0);
+                const double t1 = q0 * iD1, u1 = p0 * e1 * iD1, t2 = p0 * iD2, u2 = q0 * e2 * iD2;
+                const double Delta = q0 * t2 - p0 * t1;
+                ok = ok && (Delta >= -1.0) && (Delta <= 1.0);
+                f = p0 + Delta;
+                const double w1 = p0 * t1 * u1, w2 = q0 * t2 * u2;
+                dfdG = w1 * b1 + w2 * b2;
+                dfdb1 = w1 * B;
+                dfdb2 = w2 * B;
+                dfdp0 = 1.0 - t1 - t2 + iD1 * u1 + iD2 * u2;
+                if (DBG) { dbg[2 * C::NN + lane + 32 * t] = B; dbg[2 * C::NN + C::GM + lane + 32 * t] = f; }
+            }
+            const int fc = (i + 1) + (j + 1) * (n2 + 1);
+            const double fbar = lik_cell(F, P, fc, f, s, is2, lpl, slogbar, ok);
+            Gbar[t] = fbar * dfdG;
+            b1bar = fma(fbar, dfdb1, b1bar);
+            b2bar = fma(fbar, dfdb2, b2bar);
+            M2[lane + 32 * t] = fbar * dfdp0;   // p0bar
+        }
+    }
+    // boundary cells of f: f[0,a] = p01[a-1], f[b,0] = p02[b-1], f[0,0] = 1 (gp_grid.stan:170-172)
+    double pmbar = 0.0;
+    if (lane <= nm) {
+        const int fc = lane < n1 ? (lane + 1) * (n2 + 1) : (lane < nm ? lane - n1 + 1 : 0);
+        pmbar = lik_cell(F, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, ok);
+    }
+    __syncwarp();
+    // ---- 7. adjoints of the monotherapy curves ------------------------------------------------------
+    if (lane < nm) {
+        if (lane < n1) { for (int i = 0; i < n2; ++i) pmbar = fma(M2[i + lane * n2], pm[n1 + i], pmbar); }
+        else { const int i = lane - n1; for (int j = 0; j < n1; ++j) pmbar = fma(M2[i + j * n2], pm[j], pmbar); }
+        const bool d1 = lane < n1;
+        const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
+        const double c = pmbar * (1.0 - lam) * BSYN_LN10 * (1.0 - om) * om;   // (1-la) E ln10/(1+E)^2
+        pmb[lane] = pmbar * (1.0 - om);            // d/d la = E/(1+E)
+        pmb[32 + lane] = -c * (P.xs[lane] - mm);   // d/d slope
+        pmb[64 + lane] = c * sl;                   // d/d log10_ec50
+    }
+    __syncwarp();
+    {
+        int which = -1, lo = 0, hi = 0;
+        if (lane == SL_LA1) { which = 0; lo = 0; hi = n1; }
+        else if (lane == SL_LA2) { which = 0; lo = n1; hi = nm; }
+        else if (lane == SL_SL1) { which = 1; lo = 0; hi = n1; }
+        else if (lane == SL_SL2) { which = 1; lo = n1; hi = nm; }
+        else if (lane == SL_M1) { which = 2; lo = 0; hi = n1; }
+        else if (lane == SL_M2) { which = 2; lo = n1; hi = nm; }
+        if (which >= 0) {
+            double sacc = 0.0;
+            for (int m = lo; m < hi; ++m) sacc += pmb[which * 32 + m];
+            tb += sacc;
+        }
+    }
+    // ---- 8-10. adjoints of the Kronecker product, the Cholesky factors and the kernels --------------
+    double ellbar = 0.0, sigfbar = 0.0, alphabar = 0.0;
+    if (gp) {
+        const int T1 = P.T1, Tn = P.T1 + P.T2;
+#pragma unroll
+        for (int t = 0; t < CPL; ++t)
+            if (cell[t] >> 16) M3[lane + 32 * t] = Gbar[t];
+        __syncwarp();
+        // W = Gbar * L1 -> M2   (W[i,l] = sum_{j>=l} Gbar[i,j] L1[j,l])
+        double acc[CPL];
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) acc[t] = 0.0;
+        for (int j = 0; j < n1; ++j) {
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                const int i = cell[t] & 255, l = (cell[t] >> 8) & 255;
+                if ((cell[t] >> 16) && j >= l) acc[t] = fma(M3[i + j * n2], L1r[j * NM + l], acc[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < CPL; ++t)
+            if (cell[t] >> 16) M2[lane + 32 * t] = acc[t];
+        __syncwarp();
+        // Zbar = L2^T * W   (Zbar[k,l] = sum_{i>=k} L2[i,k] W[i,l]);  + N(0,1) prior on z
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) acc[t] = 0.0;
+        for (int i = 0; i < n2; ++i) {
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                const int k = cell[t] & 255, l = (cell[t] >> 8) & 255;
+                if ((cell[t] >> 16) && i >= k) acc[t] = fma(L2r[i * NM + k], M2[i + l * n2], acc[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) {
+            const bool v = cell[t] >> 16;
+            g.z[t] = v ? acc[t] - q.z[t] : 0.0;
+            if (v) lpl = fma(-0.5 * q.z[t], q.z[t], lpl);
+            if (DBG && v) { dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gbar[t]; dbg[2 * C::NN + 3 * C::GM + lane + 32 * t] = acc[t]; }
+        }
+        // L1bar = tril(Gbar^T T), L2bar = tril(W Z^T): one packed lower-triangular entry per lane and round
+        for (int e0 = lane; e0 < Tn; e0 += 32) {
+            const bool m1 = e0 < T1;
+            const int rc = P.tri[m1 ? e0 : e0 - T1], rr = rc >> 8, cc = rc & 255;
+            double sacc = 0.0;
+            if (m1) { for (int i = 0; i < n2; ++i) sacc = fma(M3[i + rr * n2], M1[i + cc * n2], sacc); Lb1[rr * NM + cc] = sacc; }
+            else { for (int l = 0; l < n1; ++l) sacc = fma(M2[rr + l * n2], M0[cc + l * n2], sacc); Lb2[rr * NM + cc] = sacc; }
+        }
+        __syncwarp();
+        // Cholesky adjoint (Murray 2016): Xfull = L^-T (Phi + Phi^T) L^-1, Phi = tril(L^T Lbar), diag halved.
+        // Stage A: S = Phi + Phi^T -> M0 (matrix 1), M1 (matrix 2)
+        for (int e0 = lane; e0 < Tn; e0 += 32) {
+            const bool m1 = e0 < T1;
+            const int rc = P.tri[m1 ? e0 : e0 - T1], a = rc >> 8, b = rc & 255;
+            const double *L = m1 ? L1r : L2r, *Lb = m1 ? Lb1 : Lb2;
+            const int n = m1 ? n1 : n2;
+            double sacc = 0.0;
+            for (int i = a; i < n; ++i) sacc = fma(L[i * NM + a], Lb[i * NM + b], sacc);
+            double *S = m1 ? M0 : M1;
+            S[a * NM + b] = sacc;
+            S[b * NM + a] = sacc;
+        }
+        __syncwarp();
+        {
+            const int h = lane >> 4, r = lane & 15;
+            const int n = h ? n2 : n1;
+            const double *L = h ? L2r : L1r;
+            double *S = h ? M1 : M0, *Y = h ? M3 : M2;
+            const double *idg = invd + h * 16;
+            // Stage B: Y = L^-T S (column r of Y on lane r)
+            if (r < n) {
+                for (int rr = n - 1; rr >= 0; --rr) {
+                    double sacc = S[rr * NM + r];
+                    for (int k = rr + 1; k < n; ++k) sacc = fma(-L[k * NM + rr], Y[k * NM + r], sacc);
+                    Y[rr * NM + r] = sacc * idg[rr];
+                }
+            }
+            __syncwarp();
+            // Stage C: X = Y L^-1 (row r of X on lane r), stored transposed over S: X[r,c] at S[c*NM + r]
+            if (r < n) {
+                for (int c = n - 1; c >= 0; --c) {
+                    double sacc = Y[r * NM + c];
+                    for (int k = c + 1; k < n; ++k) sacc = fma(-S[k * NM + r], L[k * NM + c], sacc);
+                    S[c * NM + r] = sacc * idg[c];
+                }
+            }
+            __syncwarp();
+        }
+        if (DBG) {
+            for (int e0 = lane; e0 < C::NN; e0 += 32) {
+                dbg[e0] = L1r[e0]; dbg[C::NN + e0] = L2r[e0];
+                dbg[2 * C::NN + 4 * C::GM + e0] = Lb1[e0]; dbg[3 * C::NN + 4 * C::GM + e0] = Lb2[e0];
+                dbg[4 * C::NN + 4 * C::GM + e0] = M0[e0]; dbg[5 * C::NN + 4 * C::GM + e0] = M1[e0];
+            }
+        }
+        // contraction with d cov / d(ell, sigma_f, alpha): sum over all (a,b) of Sbar_sym * dcov
+        //   = sum_{a>b} Xfull[a,b] * dcov[a,b] + 1/2 sum_a Xfull[a,a] * dcov[a,a]
+        const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA], iell = 1.0 / th[SL_ELL];
+        const int P1 = P.P1, Pn = P.P1 + P.P2;
+        for (int e0 = lane; e0 < Pn; e0 += 32) {
+            const bool m1 = e0 < P1;
+            const int ab = P.pr[e0], a = ab >> 8, b = ab & 255;
+            const double X = (m1 ? M0 : M1)[b * NM + a];
+            double kv, dk, da;
+            kern_partials(F, P.dist[e0], iell, alpha, exv[e0], kv, dk, da);
+            const double sc = m1 ? sigf : 1.0;
+            ellbar = fma(X * sc, dk, ellbar);
+            alphabar = fma(X * sc, da, alphabar);
+            if (m1) sigfbar = fma(X, kv, sigfbar);
+        }
+        if (lane < n1) sigfbar = fma(0.5, M0[lane * NM + lane], sigfbar);
+    } else {
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) g.z[t] = 0.0;
+    }
+    // ---- 11. reductions and chain rule through the constraining transforms ---------------------------
+    double tot;
+    tot = warp_sum(b1bar); if (lane == SL_B1) tb += tot;
+    tot = warp_sum(b2bar); if (lane == SL_B2) tb += tot;
+    if (gp) {
+        tot = warp_sum(ellbar); if (lane == SL_ELL) tb += tot;
+        tot = warp_sum(sigfbar); if (lane == SL_SIGF) tb += tot;
+        if (F.est_alpha) { tot = warp_sum(alphabar); if (lane == SL_ALPHA) tb += tot; }
+    }
+    const double slog = warp_sum(slogbar);
+    double lp = warp_sum(lpl);
+    lp += -(double)P.N * (BSYN_LOG_2PI_HALF + ur[SL_S]);
+    if (gp) lp += -(double)P.G * BSYN_LOG_2PI_HALF;
+    double gs;
+    if (is_la) gs = tb * thv * (1.0 - thv) + J * (1.0 - 2.0 * thv);
+    else if (is_lb) gs = tb * thv + J;
+    else gs = tb;
+    if (lane == SL_S) gs += slog;
+    if (!act) gs = 0.0;
+    g.s = gs;
+    lp_out = lp;
+    ok = ok && (lp == lp);
+    return __all_sync(FULL, ok);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// write_array (h:1705-2235; gp_grid.stan:234-299): one warp writes one output row
+//   [constrained params | p0 | p01 | p02 | Delta | GP | ec50_1 ec50_2 | CPO[N] | dss_1 dss_2 |
+//    rVUS_f rVUS_p0 VUS_Delta VUS_syn VUS_ant]            (nointeraction: without Delta, GP, last three)
+// `row` may be NULL (screen path); qout[BSYN_NQ-ish] receives the generated scalars (lane 0 writes);
+// cpo_acc (may be NULL): per-chain accumulator of CPO_n, added to.
+// yglob/iiglob: this problem's y[N], ii0[N] in original order (global memory).
+template <int CPL>
+__device__ __noinline__ bool warp_write_array(const Flags &F, const ProbS &P, const ProbDesc &pd, double *ws,
+                                              const int (&cell)[CPL], const WVec<CPL> &q, const double *yglob,
+                                              const int *iiglob, double u_zero_fix[4], double *row, double *qout,
+                                              double *cpo_acc)
+{
+    using C = Cfg<CPL>;
+    const int lane = threadIdx.x & 31;
+    const int n1 = P.n1, n2 = P.n2, nm = n1 + n2, G = P.G;
+    double *th = ws + C::OFF_TH, *ur = ws + C::OFF_UR, *pm = ws + C::OFF_PM;
+    double *M2 = ws + C::OFF_M2;   // f grid (ncf <= (NM+1)^2 may exceed MB: f goes to M2..M3, contiguous)
+    const bool gp = (F.model == 0);
+    __syncwarp();
+    double e;
+    const double thv = constrain_slot(F, q.s, th, ur, e);
+    double Gv[CPL];
+    bool ok = true;
+    if (gp) ok = gp_forward<CPL>(F, P, ws, cell, q.z, Gv);
+    double pmv = 0.0;
+    if (lane < nm) {
+        const bool d1 = lane < n1;
+        const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2], lam = th[d1 ? SL_LA1 : SL_LA2];
+        const double Em = exp(BSYN_LN10 * sl * (P.xs[lane] - mm));
+        pmv = fma(1.0 - lam, 1.0 / (1.0 + Em), lam);
+        pm[lane] = pmv;
+        ok = ok && (pmv >= 0.0) && (pmv <= 1.0);
+    }
+    __syncwarp();
+    // output offsets
+    const int npre = 2 * F.est_la + 6 + (gp ? 4 + F.est_alpha : 0);
+    const int D = pd.D;
+    const int o_p0 = D, o_p01 = o_p0 + G, o_p02 = o_p01 + n1;
+    const int o_delta = o_p02 + n2, o_gp = o_delta + G;
+    const int o_ec = gp ? o_gp + G : o_p02 + n2;
+    const int o_cpo = o_ec + 2, o_dss = o_cpo + P.N, o_vus = o_dss + 2;
+    // constrained parameters in declaration order
+    if (row && lane < 16 && ((F.active_mask >> lane) & 1u)) {
+        int pos;
+        if (lane < SL_M1) pos = lane;
+        else if (lane <= SL_ALPHA) pos = lane - (F.est_la ? 0 : 2);
+        else pos = D - 3 + (lane - SL_S);
+        if (!gp && lane >= SL_B1 && lane <= SL_ALPHA) pos = -1;
+        if (pos >= 0) row[pos] = thv;
+    }
+    const double b1 = th[SL_B1], b2 = th[SL_B2], s = th[SL_S];
+    double v_f = 0.0, v_p0 = 0.0, v_d = 0.0, v_syn = 0.0, v_ant = 0.0;
+    const int ld = n2 + 1;
+    double *fg = M2;   // f on the (n2+1) x (n1+1) grid, column-major
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+        if (cell[t] >> 16) {
+            const int c = lane + 32 * t;
+            const int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
+            const double p0 = pm[j] * pm[n1 + i], q0 = 1.0 - p0;
+            ok = ok && (p0 >= 0.0) && (p0 <= 1.0);
+            double Delta = 0.0;
+            if (gp) {
+                const double B = Gv[t];
+                const double e1 = exp(b1 * B), e2 = exp(-b2 * B);
+                Delta = q0 * (p0 / fma(q0, e2, p0)) - p0 * (q0 / fma(p0, e1, q0));
+                ok = ok && (Delta >= -1.0) && (Delta <= 1.0);
+                if (row) { row[npre + c] = q.z[t]; row[o_delta + c] = Delta; row[o_gp + c] = B; }
+            }
+            if (row) row[o_p0 + c] = p0;
+            const double f = p0 + Delta;
+            fg[(i + 1) + (j + 1) * ld] = f;
+            const double w = P.vw[j] * P.vw[n1 + i];
+            v_f = fma(w, 1.0 - f, v_f);
+            v_p0 = fma(w, 1.0 - p0, v_p0);
+            v_d = fma(w, Delta, v_d);
+            v_syn = fma(w, fmin(Delta, 0.0), v_syn);
+            v_ant = fma(w, fmax(Delta, 0.0), v_ant);
+        }
+    }
+    if (lane <= nm) {
+        const int fc = lane < n1 ? (lane + 1) * ld : (lane < nm ? lane - n1 + 1 : 0);
+        fg[fc] = lane < nm ? pmv : 1.0;
+        if (row && lane < nm) row[o_p01 + lane] = pmv;   // p01 then p02 are contiguous
+    }
+    __syncwarp();
+    v_f = warp_sum(v_f); v_p0 = warp_sum(v_p0);
+    if (gp) { v_d = warp_sum(v_d); v_syn = warp_sum(v_syn); v_ant = warp_sum(v_ant); }
+    // CPO (always the Normal density, even when robust: gp_grid.stan:264-270)
+    if (row || cpo_acc) {
+        for (int n = lane; n < P.N; n += 32) {
+            const double f = fg[iiglob[n]];
+            const double sd = F.het ? s * sqrt(f + F.lambda) : s;
+            const double r = (yglob[n] - f) / sd;
+            const double cpo = exp(BSYN_LOG_2PI_HALF + log(sd) + 0.5 * r * r);
+            if (row) row[o_cpo + n] = cpo;
+            if (cpo_acc) cpo_acc[n] += cpo;
+        }
+    }
+    // ec50, dss (include/dss.stan) on lanes 0/1
+    double ec = 0.0, ds = 0.0;
+    if (lane < 2) {
+        const int n = lane ? n2 : n1;
+        const double *x = P.xs + (lane ? n1 : 0);
+        double c1 = x[0], c2 = x[0];
+        for (int k = 1; k < n; ++k) { c1 = fmin(c1, x[k]); c2 = fmax(c2, x[k]); }
+        const double la = th[SL_LA1 + lane], sl = th[SL_SL1 + lane], mm = th[SL_M1 + lane];
+        ec = exp(BSYN_LN10 * mm);
+        const double val = (c2 - c1) + (la - 1.0) / sl * (log10(1.0 + exp(BSYN_LN10 * sl * (c2 - mm))) -
+                                                          log10(1.0 + exp(BSYN_LN10 * sl * (c1 - mm))));
+        ds = 100.0 * (1.0 - val / (c2 - c1));
+    }
+    const double ec2 = __shfl_sync(FULL, ec, 1), ds2 = __shfl_sync(FULL, ds, 1);
+    // zero-valued integrals are replaced by U(1e-6,1e-4) draws (gp_grid.stan:294-297)
+    if (v_f == 0.0) v_f = 1e-6 + (1e-4 - 1e-6) * u_zero_fix[0];
+    if (v_p0 == 0.0) v_p0 = 1e-6 + (1e-4 - 1e-6) * u_zero_fix[1];
+    if (gp) {
+        if (v_syn == 0.0) v_syn = 1e-6 + (1e-4 - 1e-6) * u_zero_fix[2];
+        if (v_ant == 0.0) v_ant = 1e-6 + (1e-4 - 1e-6) * u_zero_fix[3];
+    }
+    if (lane == 0) {
+        if (row) {
+            row[o_ec] = ec; row[o_ec + 1] = ec2; row[o_dss] = ds; row[o_dss + 1] = ds2;
+            row[o_vus] = v_f; row[o_vus + 1] = v_p0;
+            if (gp) { row[o_vus + 2] = v_d; row[o_vus + 3] = v_syn; row[o_vus + 4] = v_ant; }
+        }
+        if (qout) {
+            qout[0] = ec; qout[1] = ec2; qout[2] = ds; qout[3] = ds2; qout[4] = s;
+            qout[5] = v_f; qout[6] = v_p0; qout[7] = v_d; qout[8] = v_syn; qout[9] = v_ant;
+        }
+    }
+    return __all_sync(FULL, ok);
+}
+
+}  // namespace bsyn

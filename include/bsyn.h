@@ -1,0 +1,202 @@
+/* bsyn.h -- C ABI of the B200-native gp_grid / nointeraction hot path of bayesynergy.
+ *
+ * This is the drop-in boundary: every entry point replaces one method of the Rcpp module
+ * class `rstantools_model_gp_grid` / `rstantools_model_nointeraction`
+ * (= rstan::stan_fit<model, ecuyer1988>, reference src/stanExports_gp_grid.cc:10-30,
+ *  src/stanExports_nointeraction.cc:10-30), batched over many experiments ("combinations") and chains.
+ * INTEGRATION.md shows the Rcpp stub that binds them.
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer passed in or out, the
+ * library owns the opaque batch handle.  No function throws; each returns BSYN_OK or an
+ * error code and bsyn_last_error() gives the text.  There is no CPU fallback: without a CUDA
+ * device every compute entry point returns BSYN_ERR_CUDA.
+ * All floating point is IEEE double; all indices int32.
+ */
+#ifndef BSYN_H
+#define BSYN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSYN_VERSION 100
+
+enum {
+    BSYN_OK = 0,
+    BSYN_ERR_ARG = 1,        /* invalid argument / inconsistent sizes */
+    BSYN_ERR_UNSUPPORTED = 2,/* grid too large for the compiled kernel variants, etc. */
+    BSYN_ERR_CUDA = 3,       /* CUDA runtime error or no device */
+    BSYN_ERR_ALLOC = 4
+};
+
+enum { BSYN_MODEL_GP_GRID = 0, BSYN_MODEL_NOINTERACTION = 1 };
+
+/* One experiment = the Stan data block of inst/stan/gp_grid.stan:10-29 (nointeraction.stan:7-23 reads a
+ * subset), i.e. the `stan_data` list built at R/bayesynergy.R:167-200; what the generated constructor
+ * reads at src/stanExports_gp_grid.h:510-636. */
+typedef struct bsyn_problem {
+    int32_t n1, n2;          /* number of non-zero dose levels of drug 1 / drug 2 */
+    int32_t nmissing, nrep;  /* only used to check N = (n1+n2+n1*n2+1)*nrep - nmissing */
+    int32_t N;               /* number of observations */
+    const double *y;         /* [N] */
+    const int32_t *ii_obs;   /* [N] 1-based index into the column-major (n2+1) x (n1+1) grid f */
+    const double *x1;        /* [n1] log10 doses */
+    const double *x2;        /* [n2] */
+} bsyn_problem;
+
+/* Model options: uniform over a batch, exactly the scalar data fields of the Stan programs. */
+typedef struct bsyn_options {
+    int32_t model;           /* BSYN_MODEL_* */
+    int32_t est_la, robust, pcprior, heteroscedastic;
+    int32_t kernel;          /* 1 RBF, 2 Matern, 3 rational quadratic (gp_grid.stan:112-141) */
+    int32_t nu_matern;       /* 1: nu=1/2, 2: 3/2, 3: 5/2 */
+    int32_t est_alpha;
+    double pcprior_hypers[4];
+    double rho;              /* LPTN */
+    double lambda;           /* heteroscedastic offset */
+} bsyn_options;
+
+typedef struct bsyn_batch bsyn_batch;   /* opaque: problems packed and resident in HBM */
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+/* Replaces: `new(rstantools_model_gp_grid, data, seed, cxxfun)` = the model ctor, once per experiment
+ * (src/stanExports_gp_grid.cc:12, src/stanExports_gp_grid.h:489-801).  `device` = CUDA ordinal. */
+int bsyn_batch_create(const bsyn_problem *problems, int32_t n_problems, const bsyn_options *opts,
+                      int32_t device, bsyn_batch **out);
+void bsyn_batch_destroy(bsyn_batch *b);
+const char *bsyn_last_error(void);
+int bsyn_version(void);
+
+/* ---- layout queries --------------------------------------------------------------------------------
+ * Replace: num_pars_unconstrained, param_names/param_dims/param_fnames_oi (cc:16-21, 29). */
+int32_t bsyn_num_params(const bsyn_batch *b, int32_t problem);     /* D, unconstrained */
+int32_t bsyn_num_outputs(const bsyn_batch *b, int32_t problem);    /* one write_array row (without lp__) */
+int32_t bsyn_max_params(const bsyn_batch *b);
+int32_t bsyn_max_outputs(const bsyn_batch *b);
+int32_t bsyn_num_problems(const bsyn_batch *b);
+
+/* ---- log density + gradient -----------------------------------------------------------------------
+ * Replaces: log_prob(upar, jacobian_adjust, gradient) / grad_log_prob (cc:24-25) =
+ * model::log_prob<propto=false*, jacobian>(...) + reverse sweep (src/stanExports_gp_grid.h:1076-1577).
+ * (* the Stan programs use `target +=`, so no constant is dropped either way.)
+ * B evaluation points; point k uses problem prob_idx[k] and u + k*ldu (first D entries).
+ * lp[B], grad[B*ldu] (may be NULL), status[B]: 0 ok, 1 = the reference would throw std::domain_error
+ * (non-PD kernel matrix, transformed parameter out of range, NaN): lp = -inf, grad = 0.
+ * Host pointers (copies are made inside the call). */
+int bsyn_logp_grad(bsyn_batch *b, int32_t B, const int32_t *prob_idx, const double *u, int32_t ldu,
+                   int32_t jacobian, double *lp, double *grad, int32_t *status);
+
+/* Same, with every pointer a DEVICE pointer on the batch's device (no copies; asynchronous on `stream`,
+ * a cudaStream_t passed as void*; NULL = default stream). */
+int bsyn_logp_grad_device(bsyn_batch *b, int32_t B, const int32_t *d_prob_idx, const double *d_u, int32_t ldu,
+                          int32_t jacobian, double *d_lp, double *d_grad, int32_t *d_status, void *stream);
+
+/* ---- write_array ----------------------------------------------------------------------------------
+ * Replaces: constrain_pars (cc:23) and the per-saved-draw model.write_array (h:1705-2235): constrained
+ * parameters, transformed parameters (p0, p01, p02, Delta, GP) and generated quantities
+ * (ec50_k, CPO[N], dss_k, rVUS_f, rVUS_p0, VUS_Delta, VUS_syn, VUS_ant), in the order of h:1588-1622.
+ * out[B*ldo].  seed drives the U(1e-6,1e-4) replacement of exact-zero VUS values (gp_grid.stan:294-297). */
+int bsyn_write_array(bsyn_batch *b, int32_t B, const int32_t *prob_idx, const double *u, int32_t ldu,
+                     double *out, int32_t ldo, uint64_t seed, int32_t *status);
+
+/* Replaces: unconstrain_pars (cc:22) / transform_inits (h:803-1075).  theta = the first D entries of a
+ * write_array row (constrained parameters in declaration order). Pure host arithmetic. */
+int bsyn_unconstrain(const bsyn_batch *b, int32_t problem, const double *theta, double *u);
+
+/* ---- sampling -------------------------------------------------------------------------------------
+ * Replaces: call_sampler(args) (cc:15) for method="sampling", algorithm="NUTS": Stan's adaptive NUTS
+ * (hmc_nuts_diag_e_adapt / hmc_nuts_dense_e_adapt) run for every problem x chain of the batch in ONE
+ * device-resident launch.  Field names and defaults follow rstan's `control` list. */
+typedef struct bsyn_sampler_args {
+    int32_t chains;          /* 4 */
+    int32_t iter;            /* 2000 (warmup + sampling, as in rstan) */
+    int32_t warmup;          /* 1000 */
+    int32_t thin;            /* 1 */
+    uint64_t seed;
+    double init_r;           /* 2.0: inits ~ U(-init_r, init_r) on the unconstrained scale */
+    double adapt_delta;      /* 0.9 (bayesynergy override of rstan's 0.8, R/bayesynergy.R:107-110) */
+    double stepsize;         /* 1.0 */
+    double stepsize_jitter;  /* 0 (0.5 when robust, R/bayesynergy.R:112-115) */
+    int32_t max_treedepth;   /* 10 */
+    int32_t metric;          /* 0 = diag_e, 1 = dense_e */
+    double adapt_gamma, adapt_kappa, adapt_t0;            /* 0.05, 0.75, 10 */
+    int32_t adapt_init_buffer, adapt_term_buffer, adapt_window;   /* 75, 50, 25 */
+    int32_t save_warmup;     /* 0 */
+} bsyn_sampler_args;
+
+void bsyn_sampler_defaults(bsyn_sampler_args *a);
+
+/* Number of generated scalars kept per saved draw for the screen path (see BSYN_Q_* below). */
+#define BSYN_NQ 12
+enum {
+    BSYN_Q_EC50_1 = 0, BSYN_Q_EC50_2, BSYN_Q_DSS_1, BSYN_Q_DSS_2, BSYN_Q_S,
+    BSYN_Q_RVUS_F, BSYN_Q_RVUS_P0, BSYN_Q_VUS_DELTA, BSYN_Q_VUS_SYN, BSYN_Q_VUS_ANT,
+    BSYN_Q_LP, BSYN_Q_LOGLIK_UNUSED
+};
+#define BSYN_NSP 7   /* accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, lp__ */
+
+/* Result sinks (host pointers; any may be NULL).  n_save = (iter - warmup)/thin (+ warmup/thin if
+ * save_warmup).  Strides are in doubles. */
+typedef struct bsyn_sample_sinks {
+    /* full write_array rows: [n_problems][chains][n_save][ld_draws]; what rstan::extract() reads
+     * (R/bayesynergy.R:244-291).  Large: intended for bayesynergy() on one / a few experiments. */
+    double *draws;
+    int64_t ld_draws;
+    /* unconstrained draws [n_problems][chains][n_save][ld_udraws] (bridge sampling) */
+    double *udraws;
+    int64_t ld_udraws;
+    /* the BSYN_NQ generated scalars per draw: [n_problems][chains][n_save][BSYN_NQ] */
+    double *qdraws;
+    /* sampler params per draw: [n_problems][chains][n_save][BSYN_NSP] (attr "sampler_params") */
+    double *sampler_params;
+    /* per-problem posterior summaries over all chains, what synergyscreen() puts in one screenSummary row
+     * (R/synergyscreen.R:185-218): [n_problems][BSYN_NQ][2] = mean, sd (sd with n-1 denominator, pooled) */
+    double *summary;
+    /* per-problem mean over draws of CPO_n: [n_problems][ld_cpo] -> LPML = -sum log(mean CPO) (R/bayesynergy.R:244-246) */
+    double *cpo_mean;
+    int64_t ld_cpo;
+    /* per problem x chain: [n_problems][chains][8] = stepsize, n_divergent, n_max_treedepth, n_leapfrog_total
+     * (warmup+sampling), n_leapfrog_sampling, mean accept_stat (sampling), init_failed, reserved */
+    double *chain_stats;
+    /* adapted diagonal inverse metric [n_problems][chains][ld_udraws'] -- uses bsyn_max_params() stride */
+    double *inv_metric;
+} bsyn_sample_sinks;
+
+/* Runs the whole screen.  total_grad_evals (may be NULL) receives the number of log-density gradient
+ * evaluations performed (all problems, chains, warmup + sampling). */
+int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const bsyn_sample_sinks *sinks,
+                int64_t *total_grad_evals);
+
+/* Device-resident variant for throughput measurement and for callers that post-process on the GPU:
+ * runs the sampler and leaves qdraws / sampler_params / summary in device buffers owned by the batch
+ * (valid until the next sampling call or destroy).  Pointers are returned through *d_qdraws etc. (may be NULL).
+ * elapsed_ms: device time of the sampling kernel(s), measured with CUDA events on the launch stream. */
+int bsyn_sample_device(bsyn_batch *b, const bsyn_sampler_args *args, int64_t *total_grad_evals,
+                       float *elapsed_ms, const double **d_qdraws, const double **d_sampler_params,
+                       const double **d_summary);
+
+/* Rank-normalisation-free split-chain bulk ESS (Geyer initial positive sequence on the pooled split chains,
+ * as rstan::summary's n_eff) of generated scalar `q` for every problem, computed on the device from the
+ * qdraws of the last sampling call.  ess[n_problems], rhat[n_problems] (may be NULL).  Host pointers. */
+int bsyn_ess(bsyn_batch *b, int32_t q, double *ess, double *rhat);
+
+/* Number of CUDA kernel launches issued by this library so far in this process (for bench accounting). */
+int64_t bsyn_launch_count(void);
+
+/* Register-resident DFMA microbenchmark: achieved FP64 FMA lane-operations per second on `device`
+ * (the measured denominator of the FP64 roofline; x2 = FLOP/s). */
+int bsyn_measure_fp64_peak(int32_t device, double *fma_per_sec);
+
+/* Test hooks (not part of the reference-facing surface): bsyn_logp_grad plus the kernel's intermediates. */
+int bsyn_logp_grad_debug(bsyn_batch *b, int32_t B, const int32_t *prob_idx, const double *u, int32_t ldu,
+                         int32_t jacobian, double *lp, double *grad, int32_t *status, double *dbg,
+                         int32_t dbg_stride);
+int bsyn_debug_layout(const bsyn_batch *b, int32_t *nm, int32_t *nn, int32_t *gm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSYN_H */

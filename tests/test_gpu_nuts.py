@@ -1,0 +1,91 @@
+"""GPU tests of the device-resident NUTS sampler against the oracle's NUTS (statistical agreement:
+posterior means within 3 Monte Carlo standard errors, the north_star's second correctness criterion),
+plus the on-device summaries / ESS against numpy."""
+import numpy as np
+import pytest
+
+from bayesynergy_b200 import _lib
+from bayesynergy_b200.dataprep import prepare, output_names
+from bayesynergy_b200.diagnostics import split_ess_rhat, mcse_mean
+from oracle.c_oracle import Problem, nuts_screen
+
+pytestmark = pytest.mark.gpu
+Q = _lib.Q_NAMES
+
+
+def _compare(res_q, outs, names, tag):
+    for qn in ("rVUS_f", "rVUS_p0", "VUS_Delta", "VUS_syn", "VUS_ant", "s", "dss_1", "dss_2"):
+        if qn not in names:
+            continue
+        a = res_q[:, :, Q.index(qn)]
+        c = outs[:, :, names.index(qn)]
+        se = np.hypot(mcse_mean(a), mcse_mean(c))
+        assert abs(a.mean() - c.mean()) <= 3.0 * se + 1e-6, (tag, qn, a.mean(), c.mean(), se)
+
+
+def test_nuts_matches_oracle_mathews(built, datasets):
+    for dname in ("mathews:ispinesib + ibrutinib", "mathews:canertinib + ibrutinib"):
+        y, x = datasets[dname]
+        sd = prepare(y, x)
+        b = _lib.Batch([sd])
+        res = b.sample(chains=4, iter=2000, warmup=1000, seed=11)
+        cs = res["chain_stats"][0]
+        assert (cs[:, 6] == 0).all() and (cs[:, 0] > 1e-3).all()            # initialised, sane step sizes
+        assert 0.75 < cs[:, 5].mean() < 0.99                                # adapt_delta = 0.9
+        sp = res["sampler_params"][0]
+        assert sp[:, :, 3].min() >= 1 and sp[:, :, 2].max() <= 10
+        ng, outs, spo = nuts_screen([Problem(sd)], n_chains=4, num_warmup=1000, num_samples=1000, seed=21)
+        _compare(res["qdraws"][0], outs[0], output_names(sd), dname)
+        # tree depths of the two implementations should be statistically alike
+        assert abs(sp[:, :, 2].mean() - spo[0, :, :, 2].mean()) < 0.6
+        # device summaries / ESS vs numpy on the returned draws
+        q = res["qdraws"][0]
+        for qi in (Q.index("VUS_syn"), Q.index("rVUS_f"), Q.index("s")):
+            assert abs(res["summary"][0, qi, 0] - q[:, :, qi].mean()) < 1e-9 * max(1, abs(q[:, :, qi].mean()))
+            assert abs(res["summary"][0, qi, 1] - q[:, :, qi].std(ddof=1)) < 1e-9 * max(1, q[:, :, qi].std())
+            ess_d, rhat_d = b.ess(qi)
+            ess_h, rhat_h = split_ess_rhat(q[:, :, qi])
+            assert abs(ess_d[0] - ess_h) < 1e-6 * ess_h and abs(rhat_d[0] - rhat_h) < 1e-9
+            assert rhat_h < 1.05
+        b.close()
+
+
+def test_nuts_draw_sinks_are_consistent(built, datasets):
+    y, x = datasets["mathews:ispinesib + ibrutinib"]
+    sd = prepare(y, x)
+    b = _lib.Batch([sd, sd])
+    names = output_names(sd)
+    res = b.sample(chains=2, iter=120, warmup=60, seed=4, want_draws=True, want_udraws=True, want_cpo=True,
+                   want_inv_metric=True)
+    assert res["draws"].shape == (2, 2, 60, b.max_outputs)
+    d, ud, q = res["draws"], res["udraws"], res["qdraws"]
+    for qn in ("ec50_1", "dss_2", "s", "rVUS_f", "VUS_syn", "VUS_ant"):
+        assert np.array_equal(d[..., names.index(qn)], q[..., Q.index(qn)])
+    # constrained draws are write_array of the unconstrained ones
+    out, st = b.write_array(ud[0, 1, :5, :b.num_params(0)], seed=1)
+    cols = [i for i, nm in enumerate(names) if nm not in ("VUS_syn", "VUS_ant", "rVUS_f", "rVUS_p0")]
+    assert np.allclose(out[:, cols], d[0, 1, :5][:, cols], rtol=1e-12, atol=1e-14)
+    # lp__ equals log_prob at the draw
+    lp, _, st = b.logp_grad(ud[1, 0, :5, :b.num_params(0)], prob_idx=np.ones(5, dtype=np.int32), want_grad=False)
+    assert np.allclose(lp, res["sampler_params"][1, 0, :5, 6], rtol=1e-12)
+    # LPML ingredients: mean CPO over draws
+    k0 = names.index("CPO[1]")
+    cpo = d[0][:, :, k0:k0 + sd.N].reshape(-1, sd.N).mean(axis=0)
+    assert np.allclose(res["cpo_mean"][0, :sd.N], cpo, rtol=1e-10)
+    assert (res["inv_metric"][0, :, :b.num_params(0)] > 0).all()
+    # the two identical problems use different RNG streams
+    assert not np.array_equal(q[0], q[1])
+    b.close()
+
+
+def test_nuts_options_run_and_agree(built, datasets):
+    """robust / RBF / nointeraction variants and a larger grid: sampler runs, no init failures, agrees with oracle."""
+    y, x = datasets["synthetic:7"]
+    for v, model in ((dict(), "gp_grid"), (dict(), "nointeraction"), (dict(type=2, robust=True), "gp_grid")):
+        sd = prepare(y, x, **v)
+        b = _lib.Batch([sd], model=model)
+        res = b.sample(chains=4, iter=600, warmup=300, seed=2)
+        assert (res["chain_stats"][0, :, 6] == 0).all()
+        ng, outs, spo = nuts_screen([Problem(sd, model)], n_chains=4, num_warmup=300, num_samples=300, seed=9)
+        _compare(res["qdraws"][0], outs[0], output_names(sd, model), (v, model))
+        b.close()

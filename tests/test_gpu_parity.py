@@ -1,0 +1,184 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the oracle
+and the committed golden vectors.  Tolerance: relative 1e-10 in FP64 (north_star) wherever the kernel
+matrices have condition number <= 1e8, scaled by cond/1e8 beyond (see tests/test_oracle.py::tol_for)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from bayesynergy_b200 import _lib
+from bayesynergy_b200.dataprep import prepare, output_names
+from oracle.c_oracle import Problem
+
+pytestmark = pytest.mark.gpu
+REL = 1e-10
+
+
+def tol_for(cond):
+    return max(REL, 1e-18 * cond)
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+def test_golden_vectors_through_c_abi(built, datasets, golden_cases):
+    groups = {}
+    for c in golden_cases:
+        key = (c["dataset"], tuple(sorted(c["variant"].items())), c["model"])
+        groups.setdefault(key, []).append(c)
+    worst_wc = 0.0
+    n = 0
+    for (dname, var, model), cs in groups.items():
+        y, x = datasets[dname]
+        sd = prepare(y, x, **dict(var))
+        b = _lib.Batch([sd], model=model)
+        U = np.array([c["u"] for c in cs])
+        lp, g, st = b.logp_grad(U)
+        D = b.num_params(0)
+        for k, c in enumerate(cs):
+            assert st[k] == 0
+            e = max(abs(lp[k] - c["lp"]) / max(1.0, abs(c["lp"])), relerr(g[k, :D], c["grad"]))
+            assert e <= tol_for(c["cond"]), (dname, dict(var), model, e, c["cond"])
+            if c["cond"] <= 1e6:
+                worst_wc = max(worst_wc, e)
+            n += 1
+        b.close()
+    assert n == len(golden_cases)
+    assert worst_wc <= 1e-11, worst_wc
+
+
+@pytest.mark.parametrize("dname", ["mathews:ispinesib + ibrutinib", "mathews:canertinib + ibrutinib",
+                                   "oneil_failed:0", "oneil_failed:1", "synthetic:7"])
+def test_random_points_against_oracle(built, datasets, dname):
+    y, x = datasets[dname]
+    rng = np.random.default_rng(abs(hash(dname)) % (2 ** 31))
+    variants = [dict(), dict(type=2), dict(type=4), dict(type=3, nu=0.5), dict(type=3, nu=2.5),
+                dict(robust=True), dict(heteroscedastic=False), dict(robust=True, heteroscedastic=False),
+                dict(pcprior=True, robust=True), dict(lower_asymptotes=False)]
+    for v in variants:
+        sd = prepare(y, x, **v)
+        for model in ("gp_grid", "nointeraction"):
+            P = Problem(sd, model)
+            b = _lib.Batch([sd], model=model)
+            assert b.num_params(0) == P.dim and b.num_outputs(0) == P.n_out
+            U = rng.uniform(-0.7, 0.7, size=(24, P.dim))      # moderate ell: well-conditioned kernel matrices
+            U[12:, P.dim - 3] = rng.uniform(-3.0, -1.5, size=12)    # small s: large residuals / LPTN tails
+            for jac in (True, False):
+                lp, g, st = b.logp_grad(U, jacobian=jac)
+                st_o, lp_o, g_o = P.logp_grad_batch(U, jacobian=jac)
+                assert np.array_equal(st, st_o) and (st == 0).all()
+                for k in range(U.shape[0]):
+                    assert abs(lp[k] - lp_o[k]) <= 5e-10 * max(1.0, abs(lp_o[k])), (dname, v, model, k, lp[k], lp_o[k])
+                    assert relerr(g[k, :P.dim], g_o[k]) <= 5e-10, (dname, v, model, k)
+            b.close()
+
+
+def test_intermediates_cholesky_and_kron(built, datasets):
+    """Kernel-internal checks: L1, L2 (two Choleskys) and GP = L2 z L1^T against numpy."""
+    import torch
+    from oracle.torch_oracle import _kernel_mats
+    for dname in ("mathews:ispinesib + ibrutinib", "synthetic:7", "oneil_failed:0"):
+        y, x = datasets[dname]
+        sd = prepare(y, x)
+        b = _lib.Batch([sd])
+        D = b.num_params(0)
+        U = np.random.default_rng(4).uniform(-0.5, 0.5, size=(3, D))
+        lp, g, st, dbg = b.logp_grad(U, debug=True)
+        NM, NN, GM = dbg["NM"], dbg["NN"], dbg["GM"]
+        for k in range(3):
+            raw = dbg["raw"][k]
+            k0 = 2 * sd.est_la + 6
+            ell, sigf = np.exp(U[k, k0 + 2]), np.exp(U[k, k0 + 3])
+            c1, c2 = _kernel_mats(sd, torch.tensor(ell), torch.tensor(sigf), None)
+            L1 = np.linalg.cholesky(c1.numpy())
+            L2 = np.linalg.cholesky(c2.numpy())
+            L1g = raw[:NN].reshape(NM, NM)[:sd.n1, :sd.n1]
+            L2g = raw[NN:2 * NN].reshape(NM, NM)[:sd.n2, :sd.n2]
+            assert relerr(L1g, L1) < 1e-10 and relerr(L2g, L2) < 1e-10
+            z = U[k, k0 + 4:k0 + 4 + sd.n1 * sd.n2].reshape(sd.n1, sd.n2).T
+            GP = L2 @ z @ L1.T
+            GPg = raw[2 * NN:2 * NN + sd.n1 * sd.n2].reshape(sd.n1, sd.n2).T
+            assert relerr(GPg, GP) < 1e-10
+        b.close()
+
+
+def test_heterogeneous_batch_and_status(built, datasets):
+    """Several experiments of different size in one handle, points addressed by prob_idx; domain errors."""
+    sds = [prepare(*datasets[k]) for k in ("mathews:ispinesib + ibrutinib", "oneil_failed:1", "synthetic:7",
+                                          "mathews:canertinib + ibrutinib")]
+    b = _lib.Batch(sds)
+    Ps = [Problem(sd) for sd in sds]
+    rng = np.random.default_rng(8)
+    idx = rng.integers(0, len(sds), size=40).astype(np.int32)
+    U = np.zeros((40, b.max_params))
+    for k in range(40):
+        U[k, :Ps[idx[k]].dim] = rng.uniform(-0.8, 0.8, Ps[idx[k]].dim)
+    bad = [3, 17]
+    for k in bad:
+        U[k, 2 * sds[idx[k]].est_la + 6 + 3] = 800.0     # sigma_f = inf -> not positive definite -> reject
+    lp, g, st = b.logp_grad(U, prob_idx=idx)
+    for k in range(40):
+        st_o, lp_o, g_o = Ps[idx[k]].logp_grad(U[k, :Ps[idx[k]].dim])
+        assert st[k] == st_o
+        if k in bad:
+            assert st[k] == 1 and lp[k] == -np.inf and not g[k].any()
+        else:
+            assert abs(lp[k] - lp_o) <= 5e-10 * max(1.0, abs(lp_o))
+            assert relerr(g[k, :Ps[idx[k]].dim], g_o) <= 5e-10
+            assert not g[k, Ps[idx[k]].dim:].any()
+    # empty call and argument errors
+    lp0, g0, st0 = b.logp_grad(np.zeros((0, b.max_params)))
+    assert lp0.shape == (0,)
+    with pytest.raises(_lib.BsynError):
+        b.logp_grad(U, prob_idx=np.full(40, 99, dtype=np.int32))
+    b.close()
+
+
+def test_write_array_against_oracle(built, datasets):
+    for dname, v in itertools.product(("mathews:ispinesib + ibrutinib", "synthetic:7", "oneil_failed:0"),
+                                      (dict(), dict(type=2, heteroscedastic=False), dict(robust=True, lower_asymptotes=False))):
+        y, x = datasets[dname]
+        sd = prepare(y, x, **v)
+        for model in ("gp_grid", "nointeraction"):
+            P = Problem(sd, model)
+            b = _lib.Batch([sd], model=model)
+            names = output_names(sd, model)
+            U = np.random.default_rng(2).uniform(-0.7, 0.7, size=(6, P.dim))
+            out, st = b.write_array(U)
+            for k in range(6):
+                st_o, out_o = P.write_array(U[k])
+                assert st[k] == st_o == 0
+                err = np.abs(out[k, :P.n_out] - out_o) / np.maximum(1.0, np.abs(out_o))
+                worst = int(np.argmax(err))
+                assert err.max() <= 1e-9, (dname, v, model, names[worst], out[k, worst], out_o[worst])
+            b.close()
+
+
+def test_write_array_zero_patching(built, datasets):
+    """Exact-zero VUS_syn / VUS_ant are replaced by U(1e-6, 1e-4) draws (gp_grid.stan:294-297)."""
+    y, x = datasets["mathews:ispinesib + ibrutinib"]
+    sd = prepare(y, x)
+    b = _lib.Batch([sd])
+    names = output_names(sd)
+    u = np.zeros(b.num_params(0))       # z = 0  =>  GP = 0  =>  Delta = 0 everywhere
+    out, st = b.write_array(u[None, :], seed=5)
+    for nm in ("VUS_syn", "VUS_ant"):
+        v = out[0, names.index(nm)]
+        assert 1e-6 <= v <= 1e-4
+    assert out[0, names.index("VUS_Delta")] == 0.0
+    b.close()
+
+
+def test_unconstrain_roundtrip(built, datasets):
+    y, x = datasets["synthetic:7"]
+    for model, v in (("gp_grid", dict(type=4)), ("nointeraction", dict()), ("gp_grid", dict(lower_asymptotes=False))):
+        sd = prepare(y, x, **v)
+        b = _lib.Batch([sd], model=model)
+        D = b.num_params(0)
+        u = np.random.default_rng(3).uniform(-1, 1, D)
+        out, st = b.write_array(u[None, :])
+        u2 = b.unconstrain(out[0, :D])
+        assert np.abs(u2 - u).max() < 1e-12
+        b.close()
