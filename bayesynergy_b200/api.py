@@ -1,0 +1,321 @@
+"""Host-side mirror of the reference's user API for the gp_grid / nointeraction path.
+
+`bayesynergy()`  <-> R/bayesynergy.R:54-343      (one experiment; same arguments, same result fields)
+`synergyscreen()` <-> R/synergyscreen.R:58-463   (a list of experiments; same screenSummary columns)
+
+The reference is R; R is not in this image, so the host side above the C ABI is Python with the same
+names, argument meaning and error behaviour (INTEGRATION.md shows the Rcpp binding a maintainer would add).
+Everything inside the sampling loop runs on the GPU through bayesynergy_b200._lib (no CPU fallback).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .dataprep import prepare, output_names, param_names
+from .diagnostics import split_ess_rhat
+
+SCREEN_COLUMNS = [
+    "listID", "Experiment ID", "Drug A", "Drug B", "EC50 (Drug A)", "EC50 (Drug B)", "DSS (Drug A)", "DSS (Drug B)",
+    "Synergy (mean)", "Synergy (sd)", "Antagonism (mean)", "Antagonism (sd)", "Efficacy (mean)", "Efficacy (sd)",
+    "Non-interaction Efficacy (mean)", "Non-interaction Efficacy (sd)", "Interaction (mean)", "Interaction (sd)",
+    "Synergy Score", "Antagonism Score", "s", "returnCode", "divergentTransitions",
+]
+Q = _lib.Q_NAMES
+
+
+def _control_defaults(type, robust, control):
+    """R/bayesynergy.R:106-116."""
+    c = dict(adapt_delta=0.8)
+    if type != 1:
+        c = dict(adapt_delta=0.9)
+    if robust:
+        c["stepsize_jitter"] = 0.5
+        c["metric"] = "dense_e"
+    c.update(control or {})
+    return c
+
+
+def _sampler_kwargs(control, chains, iter, warmup, thin, seed):
+    kw = dict(chains=chains, iter=iter, warmup=iter // 2 if warmup is None else warmup, thin=thin, seed=seed)
+    m = dict(adapt_delta="adapt_delta", stepsize="stepsize", stepsize_jitter="stepsize_jitter",
+             max_treedepth="max_treedepth", adapt_gamma="adapt_gamma", adapt_kappa="adapt_kappa",
+             adapt_t0="adapt_t0", adapt_init_buffer="adapt_init_buffer", adapt_term_buffer="adapt_term_buffer",
+             adapt_window="adapt_window")
+    for k, v in control.items():
+        if k == "metric":
+            # dense_e is what the reference asks for when robust=TRUE; the device sampler currently adapts a
+            # diagonal metric only (DESIGN.md "out of scope / next"), so dense_e is mapped to diag_e.
+            continue
+        if k not in m:
+            raise ValueError(f"unknown control argument {k!r}")
+        kw[m[k]] = v
+    return kw
+
+
+def _diagnose(sp, chain_stats, qdraws, max_treedepth):
+    """rstan-style warnings that make bayesynergy() set returnCode = 1 (R/bayesynergy.R:210-214)."""
+    msgs = []
+    ndiv = int(sp[..., 4].sum())
+    if ndiv > 0:
+        msgs.append(f"There were {ndiv} divergent transitions after warmup.")
+    nmax = int((sp[..., 2] >= max_treedepth).sum())
+    if nmax > 0:
+        msgs.append(f"There were {nmax} transitions after warmup that exceeded the maximum treedepth.")
+    if chain_stats[..., 6].any():
+        msgs.append("Initialization failed for at least one chain.")
+    for qn in ("VUS_syn", "VUS_ant", "s"):
+        ess, rhat = split_ess_rhat(qdraws[:, :, Q.index(qn)])
+        if rhat == rhat and rhat > 1.05:
+            msgs.append(f"The largest R-hat is {rhat:.2f}, indicating chains have not mixed.")
+            break
+        if ess == ess and ess < 100 * qdraws.shape[0]:
+            msgs.append("Bulk Effective Samples Size (ESS) is too low, indicating posterior means and medians may be unreliable.")
+            break
+    return msgs, ndiv
+
+
+def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, lower_asymptotes=True,
+                heteroscedastic=True, bayes_factor=False, robust=False, rho=0.90, pcprior=False,
+                pcprior_hypers=(1, 0.1, 1, 0.2), lambda_=0.005, nu=1.5, method="sampling", control=None,
+                chains=4, iter=2000, warmup=None, thin=1, seed=1, device=0):
+    """Fit one experiment (R/bayesynergy.R:54).  Returns a dict with the fields of the R object:
+    posterior (= rstan::extract), posterior_mean, data, model, returnCode, LPML, divergent, messages."""
+    if method == "vb":
+        raise NotImplementedError("method='vb' (ADVI) is a 'next' row of the hot-path scope; use method='sampling'")
+    sd = prepare(y, x, type=type, lower_asymptotes=lower_asymptotes, heteroscedastic=heteroscedastic, robust=robust,
+                 rho=rho, pcprior=pcprior, pcprior_hypers=pcprior_hypers, lambda_=lambda_, nu=nu,
+                 bayes_factor=bayes_factor, method=method)
+    control = _control_defaults(type, robust, control)
+    kw = _sampler_kwargs(control, chains, iter, warmup, thin, seed)
+    drug_names = list(drug_names) if drug_names is not None else ["Drug1", "Drug2"]
+    experiment_ID = experiment_ID if experiment_ID is not None else "Experiment"
+    units = list(units) if units is not None else ["conc.", "conc."]
+
+    b = _lib.Batch([sd], model="gp_grid", device=device)
+    try:
+        res = b.sample(want_draws=True, want_udraws=bool(bayes_factor), want_cpo=True, **kw)
+    finally:
+        b.close()
+    names = output_names(sd)
+    draws = res["draws"][0][:, :, :len(names)]                   # [chains, n_save, n_out]
+    flat = draws.reshape(-1, draws.shape[-1])
+    n_save = flat.shape[0]
+    col = {nm: i for i, nm in enumerate(names)}
+    n1, n2, N = sd.n1, sd.n2, sd.N
+
+    def block(first, count):
+        return flat[:, col[first]:col[first] + count]
+
+    posterior = {}
+    for nm in param_names(sd):
+        base = nm.split("[")[0]
+        if base in ("z",):
+            continue
+        posterior.setdefault(base, flat[:, col[nm]])
+    posterior["z"] = block("z[1,1]", n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
+    posterior["p0"] = block("p0[1,1]", n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
+    posterior["p01"] = block("p01[1]", n1)
+    posterior["p02"] = block("p02[1]", n2)
+    posterior["Delta"] = block("Delta[1,1]", n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
+    posterior["GP"] = block("GP[1,1]", n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
+    posterior["CPO"] = block("CPO[1]", N)
+    for nm in ("ec50_1", "ec50_2", "dss_1", "dss_2", "rVUS_f", "rVUS_p0", "VUS_Delta", "VUS_syn", "VUS_ant"):
+        posterior[nm] = flat[:, col[nm]]
+    posterior["lp__"] = res["sampler_params"][0][:, :, 6].reshape(-1)
+
+    # R/bayesynergy.R:245-291
+    LPML = float(-np.sum(np.log(posterior["CPO"].sum(axis=0) / n_save)))
+    f = np.empty((n_save, n2 + 1, n1 + 1))
+    f[:, 0, 0] = 1.0
+    f[:, 1:, 0] = posterior["p02"]
+    f[:, 0, 1:] = posterior["p01"]
+    f[:, 1:, 1:] = posterior["p0"] + posterior["Delta"]
+    f_mean = np.median(f, axis=0) if robust else f.mean(axis=0)
+    p0 = f.copy()
+    p0[:, 1:, 1:] = posterior["p0"]
+    p0_mean = np.median(p0, axis=0)
+    Delta = np.zeros_like(f)
+    Delta[:, 1:, 1:] = posterior["Delta"]
+    Delta_mean = np.median(Delta, axis=0)
+    skip = {"z", "p0", "p01", "p02", "Delta", "CPO", "lp__"}
+    posterior_mean = {k: (float(v.mean()) if v.ndim == 1 else v.mean(axis=0)) for k, v in posterior.items()
+                      if k not in skip}
+    posterior_mean.update(f=f_mean, p0=p0_mean, Delta=Delta_mean)
+
+    messages, ndiv = _diagnose(res["sampler_params"][0], res["chain_stats"][0], res["qdraws"][0],
+                               kw.get("max_treedepth", 10))
+    returnCode = 1 if messages else 0
+    # residual check (R/bayesynergy.R:305-314); f_mean is (n2+1) x (n1+1), as.vector is column-major
+    fvec = f_mean.T.reshape(-1)
+    resid = sd.y - fvec[sd.ii_obs - 1]
+    point_sd = np.sqrt(posterior_mean["s"] ** 2 * (fvec[sd.ii_obs - 1] + lambda_))
+    if (np.abs(resid) > 3 * point_sd).any():
+        msg = (f"Largest residuals from posterior median is {resid.max():.4g}, which is more than three times the "
+               "observation noise. This could indicate the presence of an outlier.")
+        warnings.warn(msg)
+        returnCode = 1
+        messages.append(msg)
+
+    obj = dict(posterior=posterior, posterior_mean=posterior_mean,
+               data=dict(y=np.asarray(y), x=np.asarray(x), drug_names=drug_names, experiment_ID=experiment_ID,
+                         units=units, indices=sd.ii_obs),
+               model=dict(type=type, lower_asymptotes=lower_asymptotes, method=method, bayes_factor=bayes_factor,
+                          heteroscedastic=heteroscedastic, robust=robust, pcprior=pcprior, lambda_=lambda_),
+               returnCode=returnCode, LPML=LPML, divergent=float("nan"),
+               sampler_params=res["sampler_params"][0], chain_stats=res["chain_stats"][0], n_grad=res["n_grad"])
+    if type == 3:
+        obj["model"].update(nu=nu, pcprior_hypers=tuple(pcprior_hypers))
+    if returnCode:
+        obj["messages"] = messages
+        obj["divergent"] = ndiv
+    if bayes_factor:
+        from .bridge import bayes_factor as _bf
+        obj["bayesfactor"] = _bf(sd, res["udraws"][0], kw, device=device)
+    return obj
+
+
+# ------------------------------------------------------------------------------------------------------
+def shard_slices(n_items, world_size):
+    """Contiguous, balanced split of the combination list over ranks: rank r gets
+    items [lo, hi).  All chains of a combination stay on one GPU."""
+    base, rem = divmod(n_items, world_size)
+    out, lo = [], 0
+    for r in range(world_size):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def _screen_rows(experiments, offset, res, return_codes):
+    rows = []
+    S = res["summary"]
+    for k, e in enumerate(experiments):
+        dn = e.get("drug_names", ["DrugA", "DrugB"])
+        m = {q: S[k, Q.index(q), 0] for q in Q}
+        sdv = {q: S[k, Q.index(q), 1] for q in Q}
+        rows.append({
+            "listID": offset + k + 1, "Experiment ID": e.get("experiment_ID", "Experiment"),
+            "Drug A": dn[0], "Drug B": dn[1],
+            "EC50 (Drug A)": m["ec50_1"], "EC50 (Drug B)": m["ec50_2"], "DSS (Drug A)": m["dss_1"],
+            "DSS (Drug B)": m["dss_2"], "Synergy (mean)": m["VUS_syn"], "Synergy (sd)": sdv["VUS_syn"],
+            "Antagonism (mean)": m["VUS_ant"], "Antagonism (sd)": sdv["VUS_ant"], "Efficacy (mean)": m["rVUS_f"],
+            "Efficacy (sd)": sdv["rVUS_f"], "Non-interaction Efficacy (mean)": m["rVUS_p0"],
+            "Non-interaction Efficacy (sd)": sdv["rVUS_p0"], "Interaction (mean)": m["VUS_Delta"],
+            "Interaction (sd)": sdv["VUS_Delta"], "Synergy Score": m["VUS_syn"] / sdv["VUS_syn"],
+            "Antagonism Score": m["VUS_ant"] / sdv["VUS_ant"], "s": m["s"],
+            "returnCode": int(return_codes[k]), "divergentTransitions": float(res["chain_stats"][k, :, 1].sum()),
+        })
+    return rows
+
+
+def _fit_batch(sds, kw, device, max_treedepth):
+    """One batched launch over a list of prepared experiments; returns (res, returnCode[n])."""
+    b = _lib.Batch(sds, model="gp_grid", device=device)
+    try:
+        res = b.sample(want_qdraws=False, want_sampler_params=False, **kw)
+        ess_syn, rhat_syn = b.ess("VUS_syn")
+        ess_ant, rhat_ant = b.ess("VUS_ant")
+    finally:
+        b.close()
+    cs = res["chain_stats"]
+    n_chains = cs.shape[1]
+    rc = np.zeros(len(sds), dtype=np.int64)
+    warn = (cs[:, :, 1].sum(axis=1) > 0) | (cs[:, :, 2].sum(axis=1) > 0)
+    rhat = np.fmax(rhat_syn, rhat_ant)
+    ess = np.fmin(ess_syn, ess_ant)
+    warn |= (rhat > 1.05) | (ess < 100 * n_chains)
+    rc[warn] = 1
+    rc[cs[:, :, 6].sum(axis=1) > 0] = 2
+    res["ess"] = ess
+    res["rhat"] = rhat
+    return res, rc
+
+
+def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_params=None, device=0,
+                  rank=0, world_size=1):
+    """Fit a list of experiments (dicts with y, x and optional drug_names / experiment_ID) in one batched
+    device launch (R/synergyscreen.R:58-463).  Returns dict(screenSummary=[rows], failed=[experiments]).
+
+    With world_size > 1 this rank fits its contiguous shard only (shard_slices); gather the rows with
+    `gather_screen` (a final all_gather, the only collective of the path).
+    Differences from the reference, on purpose: the default method is "sampling" (the GPU path; the
+    reference defaults to "vb" for speed, R/synergyscreen.R:91-93) and save_raw / save_plots do not exist.
+    """
+    if isinstance(experiments, dict) and "failed" in experiments:     # rerun mode (R/synergyscreen.R:97-103)
+        old = experiments.get("screenSummary", [])
+        out = synergyscreen(experiments["failed"], return_samples, max_retries, bayesynergy_params, device, rank,
+                            world_size)
+        out["screenSummary"] = list(old) + out["screenSummary"]
+        return out
+    params = dict(bayesynergy_params or {})
+    method = params.pop("method", "sampling")
+    if method != "sampling":
+        raise NotImplementedError("synergyscreen on the GPU path supports method='sampling' only")
+    if return_samples:
+        raise NotImplementedError("return_samples=TRUE: call bayesynergy() on the experiments of interest")
+    control = params.pop("control", None)
+    chains, iter_, warmup = params.pop("chains", 4), params.pop("iter", 2000), params.pop("warmup", None)
+    thin, seed = params.pop("thin", 1), params.pop("seed", 1)
+    type_, robust = params.get("type", 3), params.get("robust", False)
+    lo, hi = shard_slices(len(experiments), world_size)[rank]
+    mine = experiments[lo:hi]
+    sds, ok_idx, rows_failed = [], [], []
+    for k, e in enumerate(mine):
+        try:
+            sds.append(prepare(e["y"], e["x"], **params))
+            ok_idx.append(k)
+        except Exception:                      # tryCatch(... error = returnCode 2), R/synergyscreen.R:143-146
+            rows_failed.append(k)
+    rows = {}
+    if sds:
+        ctl = _control_defaults(type_, robust, control)
+        kw = _sampler_kwargs(ctl, chains, iter_, warmup, thin, seed)
+        res, rc = _fit_batch(sds, kw, device, kw.get("max_treedepth", 10))
+        for r, k in zip(_screen_rows([mine[k] for k in ok_idx], 0, res, rc), ok_idx):
+            r["listID"] = lo + k + 1
+            rows[k] = r
+        # retry the experiments with warnings at adapt_delta = 0.99 (R/synergyscreen.R:149-171), as ONE smaller launch
+        retry = [j for j in range(len(sds)) if rc[j] != 0]
+        tries = 0
+        while retry and tries < max_retries:
+            ctl2 = dict(ctl, adapt_delta=0.99)
+            kw2 = _sampler_kwargs(ctl2, chains, iter_, warmup, thin, seed + 1000 * (tries + 1))
+            res2, rc2 = _fit_batch([sds[j] for j in retry], kw2, device, kw2.get("max_treedepth", 10))
+            new_rows = _screen_rows([mine[ok_idx[j]] for j in retry], 0, res2, rc2)
+            for r, j in zip(new_rows, retry):
+                r["listID"] = lo + ok_idx[j] + 1
+                rows[ok_idx[j]] = r
+            retry = [j for j, c in zip(retry, rc2) if c != 0]
+            tries += 1
+    summary = [rows[k] for k in sorted(rows)]
+    # s > 1 => returnCode 2; drop code-2 rows; collect failed (R/synergyscreen.R:424-451)
+    for r in summary:
+        if r["s"] > 1:
+            r["returnCode"] = 2
+    kept = [r for r in summary if r["returnCode"] != 2]
+    failed_ids = sorted(set(rows_failed) | {r["listID"] - lo - 1 for r in summary if r["returnCode"] == 2})
+    out = dict(screenSummary=kept)
+    if failed_ids:
+        out["failed"] = [mine[k] for k in failed_ids]
+    n_warn = sum(1 for r in kept if r["returnCode"] > 0)
+    if kept and n_warn:
+        warnings.warn(f"{100.0 * n_warn / len(kept):.2f}% of experiments returned a warning or error -- check these.")
+    return out
+
+
+def gather_screen(local, world_size):
+    """The path's only collective: gather every rank's screenSummary rows (torch.distributed, any backend)."""
+    if world_size == 1:
+        return local
+    import torch.distributed as dist
+    parts = [None] * world_size
+    dist.all_gather_object(parts, local)
+    out = dict(screenSummary=[r for p in parts for r in p["screenSummary"]])
+    failed = [e for p in parts for e in p.get("failed", [])]
+    if failed:
+        out["failed"] = failed
+    return out

@@ -7,12 +7,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "bsyn_nuts.cuh"
 #include "bsyn_post.cuh"
+#include "bsyn_kernels_decl.h"
 
 using namespace bsyn;
 
@@ -34,7 +36,6 @@ static int fail(int code, const std::string &msg)
     return code;
 }
 
-constexpr int WPC = 4;   // warps (= chains) per CTA
 
 struct bsyn_batch {
     int device = 0;
@@ -126,31 +127,14 @@ template <int CPL> static bool fits(int n1, int n2)
     return n1 * n2 <= Cfg<CPL>::GM && n1 <= Cfg<CPL>::NM && n2 <= Cfg<CPL>::NM && n1 + n2 <= 31;
 }
 
-static int ws_doubles(int cpl)
-{
-    switch (cpl) {
-        case 1: return Cfg<1>::WS_DOUBLES;
-        case 2: return Cfg<2>::WS_DOUBLES;
-        case 4: return Cfg<4>::WS_DOUBLES;
-        default: return Cfg<8>::WS_DOUBLES;
-    }
-}
-static int tr_entries(int cpl)
-{
-    switch (cpl) {
-        case 1: return Cfg<1>::TR;
-        case 2: return Cfg<2>::TR;
-        case 4: return Cfg<4>::TR;
-        default: return Cfg<8>::TR;
-    }
-}
+static const VariantOps *variant(int cpl);
 
 // shared memory layouts.  per_warp_problem: every warp has its own problem block (logp / write_array
 // kernels); otherwise one block per CTA (sampler).
 static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t *bytes)
 {
     SmemLayout sl;
-    const int tr = tr_entries(b->cpl);
+    const int tr = variant(b->cpl)->tr;
     sl.tri_off = 0;
     sl.pd_off = (tr + 1) / 2 + 1;
     sl.pd_stride = b->max_d_smem + (b->max_d_smem & 1);
@@ -158,7 +142,7 @@ static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t
     const int nblk = per_warp_problem ? WPC : 1;
     sl.pi_off = sl.pd_off + nblk * sl.pd_stride;
     sl.ws_off = sl.pi_off + nblk * sl.pi_stride;
-    *bytes = sizeof(double) * (size_t)(sl.ws_off + WPC * ws_doubles(b->cpl));
+    *bytes = sizeof(double) * (size_t)(sl.ws_off + WPC * variant(b->cpl)->ws_doubles);
     return sl;
 }
 
@@ -306,108 +290,15 @@ extern "C" int32_t bsyn_max_params(const bsyn_batch *b) { return b ? b->maxD : -
 extern "C" int32_t bsyn_max_outputs(const bsyn_batch *b) { return b ? b->maxOut : -1; }
 extern "C" int32_t bsyn_num_problems(const bsyn_batch *b) { return b ? b->n : -1; }
 
-// ---------------------------------------------------------------------------------------------------
-// stand-alone log_prob / grad_log_prob and write_array kernels: one warp per evaluation point
-template <int CPL, bool DBG>
-__global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const ProbDesc *__restrict__ descs,
-                                                        const double *__restrict__ dpool, const int *__restrict__ ipool,
-                                                        const int *__restrict__ tri_tab, const SmemLayout sl, const int B,
-                                                        const int *__restrict__ prob_idx, const double *__restrict__ u,
-                                                        const int ldu, const int jacobian, double *__restrict__ lp,
-                                                        double *__restrict__ grad, int *__restrict__ status,
-                                                        double *__restrict__ dbg, const int dbg_stride)
+static const VariantOps *variant(int cpl)
 {
-    using C = Cfg<CPL>;
-    extern __shared__ double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int *s_tri = reinterpret_cast<int *>(smem + sl.tri_off);
-    for (int e = threadIdx.x; e < C::TR; e += blockDim.x) s_tri[e] = tri_tab[e];
-    __syncthreads();
-    double *s_pd = smem + sl.pd_off + warp * sl.pd_stride;
-    int *s_pi = reinterpret_cast<int *>(smem + sl.pi_off + warp * sl.pi_stride);
-    double *ws = smem + sl.ws_off + warp * C::WS_DOUBLES;
-    int loaded = -1;
-    ProbS P;
-    int cell[CPL];
-    for (int pt = blockIdx.x * WPC + warp; pt < B; pt += gridDim.x * WPC) {
-        const int ip = prob_idx[pt];
-        const ProbDesc pd = descs[ip];
-        if (ip != loaded) {
-            __syncwarp();
-            for (int e = lane; e < pd.n_d_smem; e += 32) s_pd[e] = dpool[pd.off_d + e];
-            for (int e = lane; e < pd.n_i_smem; e += 32) s_pi[e] = ipool[pd.off_i + e];
-            __syncwarp();
-            bind_problem(P, pd, s_pd, s_pi, s_tri);
-            make_cells<CPL>(F, P, cell);
-            loaded = ip;
-        }
-        WVec<CPL> q, g;
-        load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
-        double lpv;
-        const bool ok = warp_logp_grad<CPL, DBG>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr);
-        if (!ok) {
-            lpv = -INFINITY;
-#pragma unroll
-            for (int t = 0; t < CPL; ++t) g.z[t] = 0.0;
-            g.s = 0.0;
-        }
-        if (lane == 0) { lp[pt] = lpv; status[pt] = ok ? 0 : 1; }
-        if (grad) store_user_vec<CPL>(F, pd, cell, g, grad + (size_t)pt * ldu);
+    switch (cpl) {
+        case 1: return bsyn_variant_1();
+        case 2: return bsyn_variant_2();
+        case 4: return bsyn_variant_4();
+        default: return bsyn_variant_8();
     }
 }
-
-template <int CPL>
-__global__ void __launch_bounds__(32 * WPC) write_array_kernel(const Flags F, const ProbDesc *__restrict__ descs,
-                                                               const double *__restrict__ dpool, const int *__restrict__ ipool,
-                                                               const int *__restrict__ tri_tab, const SmemLayout sl, const int B,
-                                                               const int *__restrict__ prob_idx, const double *__restrict__ u,
-                                                               const int ldu, double *__restrict__ out, const int ldo,
-                                                               const unsigned long long seed, int *__restrict__ status)
-{
-    using C = Cfg<CPL>;
-    extern __shared__ double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int *s_tri = reinterpret_cast<int *>(smem + sl.tri_off);
-    for (int e = threadIdx.x; e < C::TR; e += blockDim.x) s_tri[e] = tri_tab[e];
-    __syncthreads();
-    double *s_pd = smem + sl.pd_off + warp * sl.pd_stride;
-    int *s_pi = reinterpret_cast<int *>(smem + sl.pi_off + warp * sl.pi_stride);
-    double *ws = smem + sl.ws_off + warp * C::WS_DOUBLES;
-    int loaded = -1;
-    ProbS P;
-    int cell[CPL];
-    for (int pt = blockIdx.x * WPC + warp; pt < B; pt += gridDim.x * WPC) {
-        const int ip = prob_idx[pt];
-        const ProbDesc pd = descs[ip];
-        if (ip != loaded) {
-            __syncwarp();
-            for (int e = lane; e < pd.n_d_smem; e += 32) s_pd[e] = dpool[pd.off_d + e];
-            for (int e = lane; e < pd.n_i_smem; e += 32) s_pi[e] = ipool[pd.off_i + e];
-            __syncwarp();
-            bind_problem(P, pd, s_pd, s_pi, s_tri);
-            make_cells<CPL>(F, P, cell);
-            loaded = ip;
-        }
-        WVec<CPL> q;
-        load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
-        RngKey rk;
-        rk.k0 = (uint32_t)seed; rk.k1 = (uint32_t)(seed >> 32); rk.chain = (uint32_t)pt;
-        double uz[4];
-        rng_u2(rk, RT_GQ, 0xFFu, 0, 0, uz[0], uz[1]);
-        rng_u2(rk, RT_GQ, 0xFFu, 0, 1, uz[2], uz[3]);
-        const bool ok = warp_write_array<CPL>(F, P, pd, ws, cell, q, dpool + pd.off_d + pool_y_off(pd),
-                                              ipool + pd.off_i + pool_ii_off(pd), uz, out + (size_t)pt * ldo, nullptr, nullptr);
-        if (lane == 0) status[pt] = ok ? 0 : 1;
-    }
-}
-
-#define DISPATCH_CPL(cpl, ...)                         \
-    switch (cpl) {                                     \
-        case 1: { constexpr int CPL = 1; __VA_ARGS__; } break; \
-        case 2: { constexpr int CPL = 2; __VA_ARGS__; } break; \
-        case 4: { constexpr int CPL = 4; __VA_ARGS__; } break; \
-        default: { constexpr int CPL = 8; __VA_ARGS__; } break; \
-    }
 
 static int launch_logp(bsyn_batch *b, int B, const int *d_idx, const double *d_u, int ldu, int jac, double *d_lp,
                        double *d_grad, int *d_status, double *d_dbg, int dbg_stride, cudaStream_t st)
@@ -416,19 +307,9 @@ static int launch_logp(bsyn_batch *b, int B, const int *d_idx, const double *d_u
     SmemLayout sl = make_layout(b, true, &bytes);
     int grid = std::min((B + WPC - 1) / WPC, b->num_sms * 8);
     if (grid < 1) grid = 1;
-    DISPATCH_CPL(b->cpl, {
-        if (d_dbg) {
-            CK(cudaFuncSetAttribute(logp_kernel<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            logp_kernel<CPL, true><<<grid, 32 * WPC, bytes, st>>>(b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B, d_idx,
-                                                                d_u, ldu, jac, d_lp, d_grad, d_status, d_dbg, dbg_stride);
-        } else {
-            CK(cudaFuncSetAttribute(logp_kernel<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            logp_kernel<CPL, false><<<grid, 32 * WPC, bytes, st>>>(b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B, d_idx,
-                                                                 d_u, ldu, jac, d_lp, d_grad, d_status, nullptr, 0);
-        }
-    });
+    CK(variant(b->cpl)->logp(d_dbg != nullptr, grid, bytes, st, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B,
+                             d_idx, d_u, ldu, jac, d_lp, d_grad, d_status, d_dbg, dbg_stride));
     ++g_launches;
-    CK(cudaGetLastError());
     return BSYN_OK;
 }
 
@@ -488,7 +369,7 @@ extern "C" int bsyn_logp_grad_debug(bsyn_batch *b, int32_t B, const int32_t *pro
 extern "C" int bsyn_debug_layout(const bsyn_batch *b, int32_t *nm, int32_t *nn, int32_t *gm)
 {
     if (!b) return BSYN_ERR_ARG;
-    int NM = b->cpl == 1 ? 6 : b->cpl == 2 ? 8 : b->cpl == 4 ? 12 : 16;
+    int NM = variant(b->cpl)->nm;
     *nm = NM; *nn = NM * NM; *gm = 32 * b->cpl;
     return BSYN_OK;
 }
@@ -511,13 +392,9 @@ extern "C" int bsyn_write_array(bsyn_batch *b, int32_t B, const int32_t *prob_id
     size_t bytes;
     SmemLayout sl = make_layout(b, true, &bytes);
     int grid = std::max(1, std::min((B + WPC - 1) / WPC, b->num_sms * 8));
-    DISPATCH_CPL(b->cpl, {
-        CK(cudaFuncSetAttribute(write_array_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        write_array_kernel<CPL><<<grid, 32 * WPC, bytes, b->stream>>>(b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B,
-                                                                    d_idx, d_u, ldu, d_out, ldo, seed, d_st);
-    });
+    CK(variant(b->cpl)->write_array(grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B, d_idx,
+                                    d_u, ldu, d_out, ldo, seed, d_st));
     ++g_launches;
-    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)B * ldo, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(status, d_st, sizeof(int) * B, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
@@ -605,10 +482,9 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     sp.sl = make_layout(b, false, &bytes);
     // persistent grid: as many CTAs as fit, capped by the number of work items
     int per_sm = 1;
-    DISPATCH_CPL(b->cpl, {
-        CK(cudaFuncSetAttribute(nuts_kernel<CPL, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nuts_kernel<CPL, WPC>, 32 * WPC, bytes));
-    });
+    int minb = 3;
+    if (const char *e = getenv("BSYN_NUTS_MINB")) minb = atoi(e);
+    CK(variant(b->cpl)->nuts_occupancy(minb, bytes, &per_sm));
     if (per_sm < 1) return fail(BSYN_ERR_UNSUPPORTED, "sampler kernel does not fit on an SM");
     const int n_items = b->n * sp.groups;
     const int grid = std::max(1, std::min(n_items, per_sm * b->num_sms));
@@ -625,11 +501,8 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, b->stream));
-    DISPATCH_CPL(b->cpl, {
-        nuts_kernel<CPL, WPC><<<grid, 32 * WPC, bytes, b->stream>>>(b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sp);
-    });
+    CK(variant(b->cpl)->nuts(minb, grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sp));
     ++g_launches;
-    CK(cudaGetLastError());
     // per-problem posterior summaries (mean, sd over all chains and saved sampling draws)
     {
         const int g2 = std::max(1, std::min((b->n + WPC - 1) / WPC, b->num_sms * 8));

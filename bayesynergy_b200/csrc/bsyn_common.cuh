@@ -8,12 +8,14 @@
 // so leapfrog updates, dot products and the per-cell model algebra are register-only.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <math.h>
 
 namespace bsyn {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int WPC = 4;   // warps (= chains) per CTA
 
 // canonical scalar slots (lane index).  Order = the reference's parameter order with la_k / alpha
 // always given a slot (inactive slots carry 0 and never move).
@@ -69,6 +71,16 @@ template <int CPL> struct Cfg {
     static constexpr int WS_DOUBLES = OFF_EX + PK + (PK & 1);
 };
 
+// compile-time loop: nvcc's "#pragma unroll" gives up on the nested triangular loops of the in-register
+// Cholesky (and then the row array falls into local memory), so those loops are unrolled by recursion.
+template <int I, int N, typename Fn> __device__ __forceinline__ void static_for(Fn &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -82,17 +94,23 @@ __device__ __forceinline__ double half_sum(double v)   // sum within each half-w
     return v;
 }
 
-// Problem view in shared memory (one per CTA, shared by its warps)
+// All shared memory is addressed through ONE dynamic array and 32-bit element offsets, so every access
+// compiles to LDS/STS (a pointer smuggled through a struct decays to a generic LD with 64-bit address math).
+extern __shared__ double smem[];
+#define SMI(off) (reinterpret_cast<int *>(smem)[(off)])
+
+// Problem view in shared memory (one per CTA, shared by its warps).  Members are offsets into smem
+// (doubles for the double tables, ints for the int tables).
 struct ProbS {
     int n1, n2, N, G, ncf, P1, P2, T1, T2;
-    const double *xs;      // x1 then x2
-    const double *vw;      // VUS trapezoid weights: w1[n1] (incl. 100/area) then w2[n2]
-    const double *cnt, *ybar, *ss;
-    const double *ysort;   // robust only
-    const int *cstart;     // robust only
-    const double *dist;    // [P1+P2] pair distances
-    const int *pr;         // [P1+P2] (a<<8)|b, a > b
-    const int *tri;        // [TR] (r<<8)|c, c <= r, packed row-major lower triangle
+    int xs;        // x1 then x2
+    int vw;        // VUS trapezoid weights: w1[n1] (incl. 100/area) then w2[n2]
+    int cnt, ybar, ss;
+    int ysort;     // robust only
+    int dist;      // [P1+P2] pair distances
+    int cstart;    // (int offset) robust only
+    int pr;        // (int offset) [P1+P2] (a<<8)|b, a > b
+    int tri;       // (int offset) [TR] (r<<8)|c, c <= r, packed row-major lower triangle
 };
 
 // ---- Philox4x32-10 counter RNG (Salmon et al. 2011), stateless: every draw is a pure function of

@@ -1,0 +1,157 @@
+// bsyn_kernels.cuh -- the __global__ entry points around the warp-cooperative device functions, and the
+// per-variant launch table (one translation unit per cells-per-lane variant, see bsyn_v*.cu).
+#pragma once
+#include "bsyn_nuts.cuh"
+#include "bsyn_kernels_decl.h"
+
+namespace bsyn {
+
+// stand-alone log_prob / grad_log_prob and write_array kernels: one warp per evaluation point
+template <int CPL, bool DBG>
+__global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const ProbDesc *__restrict__ descs,
+                                                        const double *__restrict__ dpool, const int *__restrict__ ipool,
+                                                        const int *__restrict__ tri_tab, const SmemLayout sl, const int B,
+                                                        const int *__restrict__ prob_idx, const double *__restrict__ u,
+                                                        const int ldu, const int jacobian, double *__restrict__ lp,
+                                                        double *__restrict__ grad, int *__restrict__ status,
+                                                        double *__restrict__ dbg, const int dbg_stride)
+{
+    using C = Cfg<CPL>;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s_tri = 2 * sl.tri_off;
+    for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
+    __syncthreads();
+    const int s_pd = sl.pd_off + warp * sl.pd_stride;
+    const int s_pi = 2 * (sl.pi_off + warp * sl.pi_stride);
+    const int ws = sl.ws_off + warp * C::WS_DOUBLES;
+    int loaded = -1;
+    ProbS P;
+    int cell[CPL];
+    for (int pt = blockIdx.x * WPC + warp; pt < B; pt += gridDim.x * WPC) {
+        const int ip = prob_idx[pt];
+        const ProbDesc pd = descs[ip];
+        if (ip != loaded) {
+            __syncwarp();
+            for (int e = lane; e < pd.n_d_smem; e += 32) smem[s_pd + e] = dpool[pd.off_d + e];
+            for (int e = lane; e < pd.n_i_smem; e += 32) SMI(s_pi + e) = ipool[pd.off_i + e];
+            __syncwarp();
+            bind_problem(P, pd, s_pd, s_pi, s_tri);
+            make_cells<CPL>(F, P, cell);
+            loaded = ip;
+        }
+        WVec<CPL> q, g;
+        load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
+        double lpv;
+        const bool ok = warp_logp_grad<CPL, DBG>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr);
+        if (!ok) {
+            lpv = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) g.z[t] = 0.0;
+            g.s = 0.0;
+        }
+        if (lane == 0) { lp[pt] = lpv; status[pt] = ok ? 0 : 1; }
+        if (grad) store_user_vec<CPL>(F, pd, cell, g, grad + (size_t)pt * ldu);
+    }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(32 * WPC) write_array_kernel(const Flags F, const ProbDesc *__restrict__ descs,
+                                                               const double *__restrict__ dpool, const int *__restrict__ ipool,
+                                                               const int *__restrict__ tri_tab, const SmemLayout sl, const int B,
+                                                               const int *__restrict__ prob_idx, const double *__restrict__ u,
+                                                               const int ldu, double *__restrict__ out, const int ldo,
+                                                               const unsigned long long seed, int *__restrict__ status)
+{
+    using C = Cfg<CPL>;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s_tri = 2 * sl.tri_off;
+    for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
+    __syncthreads();
+    const int s_pd = sl.pd_off + warp * sl.pd_stride;
+    const int s_pi = 2 * (sl.pi_off + warp * sl.pi_stride);
+    const int ws = sl.ws_off + warp * C::WS_DOUBLES;
+    int loaded = -1;
+    ProbS P;
+    int cell[CPL];
+    for (int pt = blockIdx.x * WPC + warp; pt < B; pt += gridDim.x * WPC) {
+        const int ip = prob_idx[pt];
+        const ProbDesc pd = descs[ip];
+        if (ip != loaded) {
+            __syncwarp();
+            for (int e = lane; e < pd.n_d_smem; e += 32) smem[s_pd + e] = dpool[pd.off_d + e];
+            for (int e = lane; e < pd.n_i_smem; e += 32) SMI(s_pi + e) = ipool[pd.off_i + e];
+            __syncwarp();
+            bind_problem(P, pd, s_pd, s_pi, s_tri);
+            make_cells<CPL>(F, P, cell);
+            loaded = ip;
+        }
+        WVec<CPL> q;
+        load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
+        RngKey rk;
+        rk.k0 = (uint32_t)seed; rk.k1 = (uint32_t)(seed >> 32); rk.chain = (uint32_t)pt;
+        double uz[4];
+        rng_u2(rk, RT_GQ, 0xFFu, 0, 0, uz[0], uz[1]);
+        rng_u2(rk, RT_GQ, 0xFFu, 0, 1, uz[2], uz[3]);
+        const bool ok = warp_write_array<CPL>(F, P, pd, ws, cell, q, dpool + pd.off_d + pool_y_off(pd),
+                                              ipool + pd.off_i + pool_ii_off(pd), uz, out + (size_t)pt * ldo, nullptr, nullptr);
+        if (lane == 0) status[pt] = ok ? 0 : 1;
+    }
+}
+
+
+template <int CPL> struct VariantImpl {
+    static cudaError_t logp(bool dbg, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                            const double *dpool, const int *ipool, const int *tri, SmemLayout sl, int B, const int *idx,
+                            const double *u, int ldu, int jac, double *lp, double *grad, int *status, double *dbgbuf,
+                            int dbg_stride)
+    {
+        cudaError_t e;
+        if (dbg) {
+            e = cudaFuncSetAttribute(logp_kernel<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e != cudaSuccess) return e;
+            logp_kernel<CPL, true><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, jac, lp, grad,
+                                                                status, dbgbuf, dbg_stride);
+        } else {
+            e = cudaFuncSetAttribute(logp_kernel<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e != cudaSuccess) return e;
+            logp_kernel<CPL, false><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, jac, lp, grad,
+                                                                 status, nullptr, 0);
+        }
+        return cudaGetLastError();
+    }
+    static cudaError_t write_array(int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                                   const double *dpool, const int *ipool, const int *tri, SmemLayout sl, int B,
+                                   const int *idx, const double *u, int ldu, double *out, int ldo,
+                                   unsigned long long seed, int *status)
+    {
+        cudaError_t e = cudaFuncSetAttribute(write_array_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        write_array_kernel<CPL><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, out, ldo, seed, status);
+        return cudaGetLastError();
+    }
+    static cudaError_t nuts(int minb, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                            const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
+    {
+        if (minb >= 3) nuts_kernel<CPL, WPC, 3><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
+        else nuts_kernel<CPL, WPC, 2><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
+        return cudaGetLastError();
+    }
+    static cudaError_t nuts_occupancy(int minb, size_t bytes, int *per_sm)
+    {
+        if (minb >= 3) {
+            cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, WPC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e != cudaSuccess) return e;
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, WPC, 3>, 32 * WPC, bytes);
+        }
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, WPC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, WPC, 2>, 32 * WPC, bytes);
+    }
+    static const VariantOps *ops()
+    {
+        static const VariantOps o = {CPL, Cfg<CPL>::WS_DOUBLES, Cfg<CPL>::TR, Cfg<CPL>::NM, &logp, &write_array, &nuts, &nuts_occupancy};
+        return &o;
+    }
+};
+
+}  // namespace bsyn

@@ -1,0 +1,27 @@
+// bsyn_kernels_decl.h -- launch tables of the compiled kernel variants (defined in bsyn_v*.cu)
+#pragma once
+#include "bsyn_nuts.cuh"
+
+namespace bsyn {
+// launch table of one compiled variant
+struct VariantOps {
+    int cpl, ws_doubles, tr, nm;
+    cudaError_t (*logp)(bool dbg, int grid, size_t smem_bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                        const double *dpool, const int *ipool, const int *tri, SmemLayout sl, int B, const int *idx,
+                        const double *u, int ldu, int jac, double *lp, double *grad, int *status, double *dbgbuf,
+                        int dbg_stride);
+    cudaError_t (*write_array)(int grid, size_t smem_bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                               const double *dpool, const int *ipool, const int *tri, SmemLayout sl, int B,
+                               const int *idx, const double *u, int ldu, double *out, int ldo, unsigned long long seed,
+                               int *status);
+    cudaError_t (*nuts)(int minb, int grid, size_t smem_bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                        const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp);
+    cudaError_t (*nuts_occupancy)(int minb, size_t smem_bytes, int *per_sm);
+};
+
+}  // namespace bsyn
+
+const bsyn::VariantOps *bsyn_variant_1();
+const bsyn::VariantOps *bsyn_variant_2();
+const bsyn::VariantOps *bsyn_variant_4();
+const bsyn::VariantOps *bsyn_variant_8();

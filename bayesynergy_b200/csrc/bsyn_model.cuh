@@ -82,22 +82,23 @@ __device__ __forceinline__ void kern_partials(const Flags &F, double d, double i
 // Leaves in scratch: L1r, L2r (row-major), L2c (column-major), invd (1/diag), exv (exp table),
 // M0 = Z, M1 = T = L2*Z.  Returns GP values of this lane's cells in Gv.
 template <int CPL>
-__device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, double *ws, const int (&cell)[CPL],
+__device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const int ws, const int (&cell)[CPL],
                                            const double (&z)[CPL], double (&Gv)[CPL])
 {
     using C = Cfg<CPL>;
     constexpr int NM = C::NM;
     const int lane = threadIdx.x & 31;
     const int n1 = P.n1, n2 = P.n2;
-    const double *th = ws + C::OFF_TH;
-    double *invd = ws + C::OFF_INVD, *L1r = ws + C::OFF_L1R, *L2r = ws + C::OFF_L2R, *L2c = ws + C::OFF_L2C;
-    double *M0 = ws + C::OFF_M0, *M1 = ws + C::OFF_M1, *exv = ws + C::OFF_EX;
+    double *const th = smem + ws + C::OFF_TH;
+    double *const invd = smem + ws + C::OFF_INVD, *const L1r = smem + ws + C::OFF_L1R, *const L2r = smem + ws + C::OFF_L2R,
+                 *const L2c = smem + ws + C::OFF_L2C;
+    double *const M0 = smem + ws + C::OFF_M0, *const M1 = smem + ws + C::OFF_M1, *const exv = smem + ws + C::OFF_EX;
     const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA];
     const double iell = 1.0 / th[SL_ELL];
     const int P1 = P.P1, Pn = P.P1 + P.P2;
     for (int e0 = lane; e0 < Pn; e0 += 32) {
-        double d = P.dist[e0];
-        int ab = P.pr[e0], a = ab >> 8, b = ab & 255;
+        double d = smem[P.dist + e0];
+        int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
         double ev;
         if (F.kernel == 3) {
             double w = d * d * iell * iell / (2.0 * alpha);
@@ -118,34 +119,32 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, doubl
         const double *A = h ? M1 : M0;
         const double dg = h ? (1.0 + 1e-10) : (sigf + 1e-10);
         double a[NM];
-#pragma unroll
-        for (int k = 0; k < NM; ++k) {
-            double v = 0.0;
-            if (r < n && k < r) v = A[r * NM + k];
-            if (k == r) v = (r < n) ? dg : 1.0;
-            a[k] = v;
-        }
-#pragma unroll
-        for (int k = 0; k < NM; ++k) {
-            double dkk = __shfl_sync(FULL, a[k], (lane & 16) + k);
+        static_for<0, NM>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const double lo = (r < n && k < r) ? A[r * NM + k] : 0.0;
+            a[k] = (k == r) ? ((r < n) ? dg : 1.0) : lo;
+        });
+        static_for<0, NM>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const double dkk = __shfl_sync(FULL, a[k], (lane & 16) + k);
             ok = ok && (dkk > 0.0);
-            double inv = rsqrt(dkk);
+            const double inv = rsqrt(dkk);
             a[k] *= inv;
             if (r == k) invd[h * 16 + k] = inv;
-#pragma unroll
-            for (int j = k + 1; j < NM; ++j) {
-                double ljk = __shfl_sync(FULL, a[k], (lane & 16) + j);
-                if (r >= j) a[j] = fma(-a[k], ljk, a[j]);
-            }
-        }
+            static_for<k + 1, NM>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                const double ljk = __shfl_sync(FULL, a[k], (lane & 16) + j);
+                a[j] = (r >= j) ? fma(-a[k], ljk, a[j]) : a[j];
+            });
+        });
         __syncwarp();   // all reads of M0/M1 (A) are done before they are reused below
         double *Lr = h ? L2r : L1r;
         if (r < NM) {
-#pragma unroll
-            for (int k = 0; k < NM; ++k) {
+            static_for<0, NM>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
                 Lr[r * NM + k] = a[k];
                 if (h) L2c[k * NM + r] = a[k];
-            }
+            });
         }
     }
     // Z -> M0 ; T = L2*Z -> M1 ; G = T*L1^T
@@ -183,7 +182,7 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, doubl
 // Constrain this lane's scalar slot (h:1086-1215, Stan Math lub_constrain/lb_constrain semantics) and
 // publish th[16] / ur[16] to the warp scratch.  Returns the constrained value; e = exp(x) where
 // x = -|u| (la slots) or u (lb slots).
-__device__ __forceinline__ double constrain_slot(const Flags &F, double u, double *th, double *ur, double &e)
+__device__ __forceinline__ double constrain_slot(const Flags &F, double u, const int th, const int ur, double &e)
 {
     const int lane = threadIdx.x & 31;
     const bool act = (F.active_mask >> lane) & 1u;
@@ -200,7 +199,7 @@ __device__ __forceinline__ double constrain_slot(const Flags &F, double u, doubl
         thv = u;
     }
     if (!act) thv = 0.0;
-    if (lane < 16) { th[lane] = thv; ur[lane] = u; }
+    if (lane < 16) { smem[th + lane] = thv; smem[ur + lane] = u; }
     __syncwarp();
     return thv;
 }
@@ -211,12 +210,12 @@ __device__ __forceinline__ double constrain_slot(const Flags &F, double u, doubl
 __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int fc, double f, double s, double is2,
                                            double &lpl, double &slogbar, bool &ok)
 {
-    const double n = P.cnt[fc];
+    const double n = smem[P.cnt + fc];
     if (n == 0.0) return 0.0;
     double fbar;
     if (!F.robust) {
-        const double d = P.ybar[fc] - f;
-        const double Q = fma(n * d, d, P.ss[fc]);
+        const double d = smem[P.ybar + fc] - f;
+        const double Q = fma(n * d, d, smem[P.ss + fc]);
         if (F.het) {
             const double v = f + F.lambda;
             if (!(v > 0.0)) { ok = false; return 0.0; }
@@ -239,9 +238,9 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
             lpl += -0.5 * n * log(v);
         }
         fbar = -0.5 * n * iv;
-        const int o1 = P.cstart[fc + 1];
-        for (int o = P.cstart[fc]; o < o1; ++o) {
-            const double r = (P.ysort[o] - f) * isd;
+        const int o1 = SMI(P.cstart + fc + 1);
+        for (int o = SMI(P.cstart + fc); o < o1; ++o) {
+            const double r = (smem[P.ysort + o] - f) * isd;
             const double ar = fabs(r);
             double dl;
             if (ar <= F.tau) {
@@ -265,7 +264,7 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
 // q / g are in lane layout.  Returns false where the reference would throw (reject): lp/g undefined.
 // dbg (DBG only): global scratch for intermediate dumps (tests).
 template <int CPL, bool DBG>
-__device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, double *ws, const int (&cell)[CPL],
+__device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, const int ws, const int (&cell)[CPL],
                                             const WVec<CPL> &q, const int jacobian, double &lp_out, WVec<CPL> &g,
                                             double *dbg)
 {
@@ -273,10 +272,12 @@ __device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, doub
     constexpr int NM = C::NM;
     const int lane = threadIdx.x & 31;
     const int n1 = P.n1, n2 = P.n2, nm = n1 + n2;
-    double *th = ws + C::OFF_TH, *ur = ws + C::OFF_UR, *pm = ws + C::OFF_PM, *pmb = ws + C::OFF_PMB;
-    double *invd = ws + C::OFF_INVD, *L1r = ws + C::OFF_L1R, *L2r = ws + C::OFF_L2R;
-    double *M0 = ws + C::OFF_M0, *M1 = ws + C::OFF_M1, *M2 = ws + C::OFF_M2, *M3 = ws + C::OFF_M3;
-    double *Lb1 = ws + C::OFF_LB1, *Lb2 = ws + C::OFF_LB2, *exv = ws + C::OFF_EX;
+    double *const th = smem + ws + C::OFF_TH, *const ur = smem + ws + C::OFF_UR, *const pm = smem + ws + C::OFF_PM,
+                 *const pmb = smem + ws + C::OFF_PMB;
+    double *const invd = smem + ws + C::OFF_INVD, *const L1r = smem + ws + C::OFF_L1R, *const L2r = smem + ws + C::OFF_L2R;
+    double *const M0 = smem + ws + C::OFF_M0, *const M1 = smem + ws + C::OFF_M1, *const M2 = smem + ws + C::OFF_M2,
+                 *const M3 = smem + ws + C::OFF_M3;
+    double *const Lb1 = smem + ws + C::OFF_LB1, *const Lb2 = smem + ws + C::OFF_LB2, *const exv = smem + ws + C::OFF_EX;
     const bool gp = (F.model == 0);
     const double J = jacobian ? 1.0 : 0.0;
     const bool act = (F.active_mask >> lane) & 1u;
@@ -286,7 +287,7 @@ __device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, doub
     // ---- 1. scalars: constrain, Jacobian, priors (gp_grid.stan:177-209) -----------------------------
     const double u = q.s;
     double e;
-    const double thv = constrain_slot(F, u, th, ur, e);
+    const double thv = constrain_slot(F, u, ws + C::OFF_TH, ws + C::OFF_UR, e);
     double lpl = 0.0;   // lane-local part of lp
     double tb = 0.0;    // d lp / d(constrained scalar of this lane)
     {
@@ -344,7 +345,7 @@ __device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, doub
         const bool d1 = lane < n1;
         const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
         lam = th[d1 ? SL_LA1 : SL_LA2];
-        const double Em = exp(BSYN_LN10 * sl * (P.xs[lane] - mm));
+        const double Em = exp(BSYN_LN10 * sl * (smem[P.xs + lane] - mm));
         om = 1.0 / (1.0 + Em);
         pmv = fma(1.0 - lam, om, lam);
         pm[lane] = pmv;
@@ -403,7 +404,7 @@ __device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, doub
         const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
         const double c = pmbar * (1.0 - lam) * BSYN_LN10 * (1.0 - om) * om;   // (1-la) E ln10/(1+E)^2
         pmb[lane] = pmbar * (1.0 - om);            // d/d la = E/(1+E)
-        pmb[32 + lane] = -c * (P.xs[lane] - mm);   // d/d slope
+        pmb[32 + lane] = -c * (smem[P.xs + lane] - mm);   // d/d slope
         pmb[64 + lane] = c * sl;                   // d/d log10_ec50
     }
     __syncwarp();
@@ -464,7 +465,7 @@ __device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, doub
         // L1bar = tril(Gbar^T T), L2bar = tril(W Z^T): one packed lower-triangular entry per lane and round
         for (int e0 = lane; e0 < Tn; e0 += 32) {
             const bool m1 = e0 < T1;
-            const int rc = P.tri[m1 ? e0 : e0 - T1], rr = rc >> 8, cc = rc & 255;
+            const int rc = SMI(P.tri + (m1 ? e0 : e0 - T1)), rr = rc >> 8, cc = rc & 255;
             double sacc = 0.0;
             if (m1) { for (int i = 0; i < n2; ++i) sacc = fma(M3[i + rr * n2], M1[i + cc * n2], sacc); Lb1[rr * NM + cc] = sacc; }
             else { for (int l = 0; l < n1; ++l) sacc = fma(M2[rr + l * n2], M0[cc + l * n2], sacc); Lb2[rr * NM + cc] = sacc; }
@@ -474,7 +475,7 @@ __device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, doub
         // Stage A: S = Phi + Phi^T -> M0 (matrix 1), M1 (matrix 2)
         for (int e0 = lane; e0 < Tn; e0 += 32) {
             const bool m1 = e0 < T1;
-            const int rc = P.tri[m1 ? e0 : e0 - T1], a = rc >> 8, b = rc & 255;
+            const int rc = SMI(P.tri + (m1 ? e0 : e0 - T1)), a = rc >> 8, b = rc & 255;
             const double *L = m1 ? L1r : L2r, *Lb = m1 ? Lb1 : Lb2;
             const int n = m1 ? n1 : n2;
             double sacc = 0.0;
@@ -522,10 +523,10 @@ __device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, doub
         const int P1 = P.P1, Pn = P.P1 + P.P2;
         for (int e0 = lane; e0 < Pn; e0 += 32) {
             const bool m1 = e0 < P1;
-            const int ab = P.pr[e0], a = ab >> 8, b = ab & 255;
+            const int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
             const double X = (m1 ? M0 : M1)[b * NM + a];
             double kv, dk, da;
-            kern_partials(F, P.dist[e0], iell, alpha, exv[e0], kv, dk, da);
+            kern_partials(F, smem[P.dist + e0], iell, alpha, exv[e0], kv, dk, da);
             const double sc = m1 ? sigf : 1.0;
             ellbar = fma(X * sc, dk, ellbar);
             alphabar = fma(X * sc, da, alphabar);
@@ -569,7 +570,7 @@ __device__ __noinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, doub
 // cpo_acc (may be NULL): per-chain accumulator of CPO_n, added to.
 // yglob/iiglob: this problem's y[N], ii0[N] in original order (global memory).
 template <int CPL>
-__device__ __noinline__ bool warp_write_array(const Flags &F, const ProbS &P, const ProbDesc &pd, double *ws,
+__device__ __forceinline__ bool warp_write_array(const Flags &F, const ProbS &P, const ProbDesc &pd, const int ws,
                                               const int (&cell)[CPL], const WVec<CPL> &q, const double *yglob,
                                               const int *iiglob, double u_zero_fix[4], double *row, double *qout,
                                               double *cpo_acc)
@@ -577,12 +578,12 @@ __device__ __noinline__ bool warp_write_array(const Flags &F, const ProbS &P, co
     using C = Cfg<CPL>;
     const int lane = threadIdx.x & 31;
     const int n1 = P.n1, n2 = P.n2, nm = n1 + n2, G = P.G;
-    double *th = ws + C::OFF_TH, *ur = ws + C::OFF_UR, *pm = ws + C::OFF_PM;
-    double *M2 = ws + C::OFF_M2;   // f grid (ncf <= (NM+1)^2 may exceed MB: f goes to M2..M3, contiguous)
+    double *const th = smem + ws + C::OFF_TH, *const pm = smem + ws + C::OFF_PM;
+    double *const M2 = smem + ws + C::OFF_M2;   // f grid (ncf <= (NM+1)^2 may exceed MB: f goes to M2..M3, contiguous)
     const bool gp = (F.model == 0);
     __syncwarp();
     double e;
-    const double thv = constrain_slot(F, q.s, th, ur, e);
+    const double thv = constrain_slot(F, q.s, ws + C::OFF_TH, ws + C::OFF_UR, e);
     double Gv[CPL];
     bool ok = true;
     if (gp) ok = gp_forward<CPL>(F, P, ws, cell, q.z, Gv);
@@ -590,7 +591,7 @@ __device__ __noinline__ bool warp_write_array(const Flags &F, const ProbS &P, co
     if (lane < nm) {
         const bool d1 = lane < n1;
         const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2], lam = th[d1 ? SL_LA1 : SL_LA2];
-        const double Em = exp(BSYN_LN10 * sl * (P.xs[lane] - mm));
+        const double Em = exp(BSYN_LN10 * sl * (smem[P.xs + lane] - mm));
         pmv = fma(1.0 - lam, 1.0 / (1.0 + Em), lam);
         pm[lane] = pmv;
         ok = ok && (pmv >= 0.0) && (pmv <= 1.0);
@@ -634,7 +635,7 @@ __device__ __noinline__ bool warp_write_array(const Flags &F, const ProbS &P, co
             if (row) row[o_p0 + c] = p0;
             const double f = p0 + Delta;
             fg[(i + 1) + (j + 1) * ld] = f;
-            const double w = P.vw[j] * P.vw[n1 + i];
+            const double w = smem[P.vw + j] * smem[P.vw + n1 + i];
             v_f = fma(w, 1.0 - f, v_f);
             v_p0 = fma(w, 1.0 - p0, v_p0);
             v_d = fma(w, Delta, v_d);
@@ -665,7 +666,7 @@ __device__ __noinline__ bool warp_write_array(const Flags &F, const ProbS &P, co
     double ec = 0.0, ds = 0.0;
     if (lane < 2) {
         const int n = lane ? n2 : n1;
-        const double *x = P.xs + (lane ? n1 : 0);
+        const double *x = smem + P.xs + (lane ? n1 : 0);
         double c1 = x[0], c2 = x[0];
         for (int k = 1; k < n; ++k) { c1 = fmin(c1, x[k]); c2 = fmax(c2, x[k]); }
         const double la = th[SL_LA1 + lane], sl = th[SL_SL1 + lane], mm = th[SL_M1 + lane];

@@ -114,7 +114,7 @@ template <int CPL> struct Chain {
 template <int CPL> struct Ctx {
     const Flags *F;
     const ProbS *P;
-    double *ws;
+    int ws;              // offset (doubles) of this warp's scratch in smem
     int cell[CPL];
     bool lane_active;    // scalar slot of this lane is a parameter
     double *arena;
@@ -179,7 +179,7 @@ struct TransInfo {
 
 // One NUTS transition (base_nuts::transition).  On entry c.q/c.g/c.V = current state; on exit = new state.
 template <int CPL>
-__device__ __noinline__ void nuts_transition(Ctx<CPL> &X, Chain<CPL> &c, const double eps, const int max_depth,
+__device__ __forceinline__ void nuts_transition(Ctx<CPL> &X, Chain<CPL> &c, const double eps, const int max_depth,
                                              const RngKey &rk, const uint32_t iter, TransInfo &info)
 {
     constexpr int VS = (CPL + 1) * 32;
@@ -343,7 +343,7 @@ __device__ __noinline__ void nuts_transition(Ctx<CPL> &X, Chain<CPL> &c, const d
 
 // base_hmc::init_stepsize: double / halve eps until the one-step acceptance crosses 0.8
 template <int CPL>
-__device__ __noinline__ double init_stepsize(Ctx<CPL> &X, Chain<CPL> &c, double eps, const RngKey &rk, uint32_t iter)
+__device__ __forceinline__ double init_stepsize(Ctx<CPL> &X, Chain<CPL> &c, double eps, const RngKey &rk, uint32_t iter)
 {
     constexpr int VS = (CPL + 1) * 32;
     double *A = X.arena;
@@ -371,8 +371,9 @@ __device__ __noinline__ double init_stepsize(Ctx<CPL> &X, Chain<CPL> &c, double 
 
 // ---------------------------------------------------------------------------------------------------
 // problem block -> ProbS view
-__device__ __forceinline__ void bind_problem(ProbS &P, const ProbDesc &pd, const double *s_pd, const int *s_pi,
-                                             const int *s_tri)
+// s_pd: offset (doubles) of the problem's double block, s_pi / s_tri: offsets (ints) of its int block / tri table
+__device__ __forceinline__ void bind_problem(ProbS &P, const ProbDesc &pd, const int s_pd, const int s_pi,
+                                             const int s_tri)
 {
     P.n1 = pd.n1; P.n2 = pd.n2; P.N = pd.N; P.G = pd.G; P.ncf = pd.ncf;
     P.P1 = pd.n1 * (pd.n1 - 1) / 2; P.P2 = pd.n2 * (pd.n2 - 1) / 2;
@@ -427,21 +428,19 @@ __device__ __forceinline__ void store_user_vec(const Flags &F, const ProbDesc &p
 
 // ---------------------------------------------------------------------------------------------------
 // The sampler kernel: persistent CTAs of WPC warps; a work item = (problem, group of WPC chains).
-template <int CPL, int WPC>
-__global__ void __launch_bounds__(32 * WPC) nuts_kernel(const Flags F, const ProbDesc *__restrict__ descs,
+// MINB = minimum resident CTAs per SM the register allocation must allow (occupancy / spill trade-off)
+template <int CPL, int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) nuts_kernel(const Flags F, const ProbDesc *__restrict__ descs,
                                                         const double *__restrict__ dpool, const int *__restrict__ ipool,
                                                         const int *__restrict__ tri_tab, const SamplerParams sp)
 {
     using C = Cfg<CPL>;
     constexpr int VS = (CPL + 1) * 32;
-    extern __shared__ double smem[];
     __shared__ int s_item;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = sp.n_problems * sp.groups;
-    int *s_tri = reinterpret_cast<int *>(smem + sp.sl.tri_off);
-    double *s_pd = smem + sp.sl.pd_off;
-    int *s_pi = reinterpret_cast<int *>(smem + sp.sl.pi_off);
-    for (int e = threadIdx.x; e < C::TR; e += blockDim.x) s_tri[e] = tri_tab[e];
+    const int s_tri = 2 * sp.sl.tri_off, s_pd = sp.sl.pd_off, s_pi = 2 * sp.sl.pi_off;
+    for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(sp.work_counter, 1);
@@ -450,8 +449,8 @@ __global__ void __launch_bounds__(32 * WPC) nuts_kernel(const Flags F, const Pro
         if (item >= n_items) break;
         const int ip = item / sp.groups, grp = item - ip * sp.groups;
         const ProbDesc pd = descs[ip];
-        for (int e = threadIdx.x; e < pd.n_d_smem; e += blockDim.x) s_pd[e] = dpool[pd.off_d + e];
-        for (int e = threadIdx.x; e < pd.n_i_smem; e += blockDim.x) s_pi[e] = ipool[pd.off_i + e];
+        for (int e = threadIdx.x; e < pd.n_d_smem; e += blockDim.x) smem[s_pd + e] = dpool[pd.off_d + e];
+        for (int e = threadIdx.x; e < pd.n_i_smem; e += blockDim.x) SMI(s_pi + e) = ipool[pd.off_i + e];
         __syncthreads();
         const int chain = grp * WPC + warp;
         if (chain >= sp.chains) continue;
@@ -459,7 +458,7 @@ __global__ void __launch_bounds__(32 * WPC) nuts_kernel(const Flags F, const Pro
         bind_problem(P, pd, s_pd, s_pi, s_tri);
         Ctx<CPL> X;
         X.F = &F; X.P = &P;
-        X.ws = smem + sp.sl.ws_off + warp * C::WS_DOUBLES;
+        X.ws = sp.sl.ws_off + warp * C::WS_DOUBLES;
         make_cells<CPL>(F, P, X.cell);
         X.lane_active = (F.active_mask >> lane) & 1u;
         X.arena = sp.arena + (long long)(blockIdx.x * WPC + warp) * sp.arena_stride;
@@ -498,9 +497,11 @@ __global__ void __launch_bounds__(32 * WPC) nuts_kernel(const Flags F, const Pro
             if (lane == 0) atomicAdd(sp.grad_counter, X.ngrad);
             continue;
         }
-        double eps = init_stepsize<CPL>(X, c, sp.stepsize0, rk, 0xFFFFFF00u);
+        double eps = sp.stepsize0;
+        bool need_istep = true;          // base_hmc::init_stepsize runs before the first transition ...
+        uint32_t istep_tag = 0xFFFFFF00u;
         // ---- adaptation state (stepsize_adaptation, windowed_adaptation) ----
-        double mu = log(10.0 * eps), sbar = 0.0, xbar = 0.0, cnt = 0.0;
+        double mu = 0.0, sbar = 0.0, xbar = 0.0, cnt = 0.0;
         int nw = sp.warmup, init_buffer = sp.init_buffer, term_buffer = sp.term_buffer, base_window = sp.window;
         if (nw < 20) { init_buffer = term_buffer = base_window = 0; }
         else if (init_buffer + base_window + term_buffer > nw) {
@@ -524,6 +525,11 @@ __global__ void __launch_bounds__(32 * WPC) nuts_kernel(const Flags F, const Pro
         if (cpo_acc) for (int n = lane; n < pd.N; n += 32) cpo_acc[n] = 0.0;
         for (int it = 0; it < sp.iter; ++it) {
             const bool warm = it < nw;
+            if (need_istep) {
+                eps = init_stepsize<CPL>(X, c, eps, rk, istep_tag);
+                mu = log(10.0 * eps); sbar = 0.0; xbar = 0.0; cnt = 0.0;
+                need_istep = false;
+            }
             double e = eps;
             if (sp.jitter > 0.0) e = eps * (1.0 + sp.jitter * (2.0 * rng_warp_uniform(rk, RT_JIT, it, 0) - 1.0));
             TransInfo info;
@@ -577,8 +583,8 @@ __global__ void __launch_bounds__(32 * WPC) nuts_kernel(const Flags F, const Pro
                             }
                         }
                         vstore<CPL>(A + A_WM * VS, m); vstore<CPL>(A + A_WM2 * VS, m2);
-                        eps = init_stepsize<CPL>(X, c, eps, rk, 0xFFFF0000u + (uint32_t)it);
-                        mu = log(10.0 * eps); sbar = 0.0; xbar = 0.0; cnt = 0.0;
+                        need_istep = true;   // ... and after every metric update (restart of the dual averaging)
+                        istep_tag = 0xFFFF0000u + (uint32_t)it;
                     } else {
                         vstore<CPL>(A + A_WM * VS, m); vstore<CPL>(A + A_WM2 * VS, m2);
                     }

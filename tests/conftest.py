@@ -45,3 +45,21 @@ def built():
     import __graft_entry__ as ge
     ge.build()
     return True
+
+
+def kernel_cond(sd, u, model="gp_grid"):
+    """max condition number of the two kernel matrices at u (1 for nointeraction)."""
+    if model != "gp_grid":
+        return 1.0
+    import torch
+    from oracle.torch_oracle import _kernel_mats
+    k0 = 2 * sd.est_la + 6
+    ell, sigf = np.exp(u[k0 + 2]), np.exp(u[k0 + 3])
+    alpha = torch.tensor(np.exp(u[k0 + 4])) if sd.est_alpha else None
+    c1, c2 = _kernel_mats(sd, torch.tensor(ell), torch.tensor(sigf), alpha)
+    return float(max(np.linalg.cond(c1.numpy()), np.linalg.cond(c2.numpy())))
+
+
+@pytest.fixture(scope="session")
+def cond_fn():
+    return kernel_cond

@@ -36,8 +36,6 @@ def test_nuts_matches_oracle_mathews(built, datasets):
         assert sp[:, :, 3].min() >= 1 and sp[:, :, 2].max() <= 10
         ng, outs, spo = nuts_screen([Problem(sd)], n_chains=4, num_warmup=1000, num_samples=1000, seed=21)
         _compare(res["qdraws"][0], outs[0], output_names(sd), dname)
-        # tree depths of the two implementations should be statistically alike
-        assert abs(sp[:, :, 2].mean() - spo[0, :, :, 2].mean()) < 0.6
         # device summaries / ESS vs numpy on the returned draws
         q = res["qdraws"][0]
         for qi in (Q.index("VUS_syn"), Q.index("rVUS_f"), Q.index("s")):
@@ -89,3 +87,23 @@ def test_nuts_options_run_and_agree(built, datasets):
         ng, outs, spo = nuts_screen([Problem(sd, model)], n_chains=4, num_warmup=300, num_samples=300, seed=9)
         _compare(res["qdraws"][0], outs[0], output_names(sd, model), (v, model))
         b.close()
+
+
+def test_tree_statistics_match_oracle(built, datasets):
+    """The iterative tree builder against the oracle's recursive base_nuts over many chains: adapted step size,
+    tree depth and leapfrogs per iteration must agree in distribution (chain-to-chain spread averaged out)."""
+    y, x = datasets["mathews:ispinesib + ibrutinib"]
+    sd = prepare(y, x)
+    nrep = 6                                  # 6 copies x 4 chains = 24 chains each side
+    b = _lib.Batch([sd] * nrep)
+    res = b.sample(chains=4, iter=800, warmup=400, seed=17)
+    sp = res["sampler_params"]
+    ng, outs, spo = nuts_screen([Problem(sd)] * nrep, n_chains=4, num_warmup=400, num_samples=400, seed=29)
+    eps_g, eps_o = np.log(sp[..., 1].mean(axis=2)).ravel(), np.log(spo[..., 1].mean(axis=2)).ravel()
+    dep_g, dep_o = sp[..., 2].mean(axis=2).ravel(), spo[..., 2].mean(axis=2).ravel()
+    se_eps = np.hypot(eps_g.std(ddof=1), eps_o.std(ddof=1)) / np.sqrt(len(eps_g))
+    se_dep = np.hypot(dep_g.std(ddof=1), dep_o.std(ddof=1)) / np.sqrt(len(dep_g))
+    assert abs(eps_g.mean() - eps_o.mean()) < 4 * se_eps + 0.05, (eps_g.mean(), eps_o.mean(), se_eps)
+    assert abs(dep_g.mean() - dep_o.mean()) < 4 * se_dep + 0.1, (dep_g.mean(), dep_o.mean(), se_dep)
+    assert abs(sp[..., 0].mean() - spo[..., 0].mean()) < 0.03          # accept_stat ~ adapt_delta on both sides
+    b.close()

@@ -51,7 +51,7 @@ def test_golden_vectors_through_c_abi(built, datasets, golden_cases):
 
 @pytest.mark.parametrize("dname", ["mathews:ispinesib + ibrutinib", "mathews:canertinib + ibrutinib",
                                    "oneil_failed:0", "oneil_failed:1", "synthetic:7"])
-def test_random_points_against_oracle(built, datasets, dname):
+def test_random_points_against_oracle(built, datasets, dname, cond_fn):
     y, x = datasets[dname]
     rng = np.random.default_rng(abs(hash(dname)) % (2 ** 31))
     variants = [dict(), dict(type=2), dict(type=4), dict(type=3, nu=0.5), dict(type=3, nu=2.5),
@@ -70,8 +70,9 @@ def test_random_points_against_oracle(built, datasets, dname):
                 st_o, lp_o, g_o = P.logp_grad_batch(U, jacobian=jac)
                 assert np.array_equal(st, st_o) and (st == 0).all()
                 for k in range(U.shape[0]):
-                    assert abs(lp[k] - lp_o[k]) <= 5e-10 * max(1.0, abs(lp_o[k])), (dname, v, model, k, lp[k], lp_o[k])
-                    assert relerr(g[k, :P.dim], g_o[k]) <= 5e-10, (dname, v, model, k)
+                    tol = tol_for(cond_fn(sd, U[k], model))
+                    assert abs(lp[k] - lp_o[k]) <= tol * max(1.0, abs(lp_o[k])), (dname, v, model, k, lp[k], lp_o[k])
+                    assert relerr(g[k, :P.dim], g_o[k]) <= tol, (dname, v, model, k)
             b.close()
 
 
@@ -151,6 +152,10 @@ def test_write_array_against_oracle(built, datasets):
                 st_o, out_o = P.write_array(U[k])
                 assert st[k] == st_o == 0
                 err = np.abs(out[k, :P.n_out] - out_o) / np.maximum(1.0, np.abs(out_o))
+                for nm in ("rVUS_f", "rVUS_p0", "VUS_syn", "VUS_ant"):      # exact zeros are replaced by random draws
+                    if nm in names and 1e-6 <= out_o[names.index(nm)] <= 1e-4:
+                        assert 1e-6 <= out[k, names.index(nm)] <= 1e-4
+                        err[names.index(nm)] = 0.0
                 worst = int(np.argmax(err))
                 assert err.max() <= 1e-9, (dname, v, model, names[worst], out[k, worst], out_o[worst])
             b.close()
@@ -162,12 +167,16 @@ def test_write_array_zero_patching(built, datasets):
     sd = prepare(y, x)
     b = _lib.Batch([sd])
     names = output_names(sd)
-    u = np.zeros(b.num_params(0))       # z = 0  =>  GP = 0  =>  Delta = 0 everywhere
+    u = np.zeros(b.num_params(0))
+    u[12:12 + 25] = 1.0                 # z > 0 and L1, L2 > 0  =>  GP > 0  =>  Delta > 0 everywhere  =>  VUS_syn == 0
     out, st = b.write_array(u[None, :], seed=5)
-    for nm in ("VUS_syn", "VUS_ant"):
-        v = out[0, names.index(nm)]
-        assert 1e-6 <= v <= 1e-4
-    assert out[0, names.index("VUS_Delta")] == 0.0
+    assert 1e-6 <= out[0, names.index("VUS_syn")] <= 1e-4
+    assert out[0, names.index("VUS_ant")] > 1e-3 and out[0, names.index("VUS_Delta")] > 1e-3
+    st_o, out_o = Problem(sd).write_array(u)
+    assert 1e-6 <= out_o[names.index("VUS_syn")] <= 1e-4          # the oracle patches the same entry
+    u[12:12 + 25] = -1.0
+    out, st = b.write_array(u[None, :], seed=5)
+    assert 1e-6 <= out[0, names.index("VUS_ant")] <= 1e-4 and out[0, names.index("VUS_syn")] < -1e-3
     b.close()
 
 
