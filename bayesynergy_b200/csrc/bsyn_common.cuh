@@ -46,27 +46,28 @@ struct ProbDesc {
 };
 
 template <int CPL> struct Cfg {
-    static constexpr int NM = (CPL == 1) ? 6 : (CPL == 2) ? 8 : (CPL == 4) ? 12 : 16;  // max n per axis
+    static constexpr int NM = (CPL <= 2) ? 8 : (CPL == 4) ? 12 : 16;   // max dose levels per axis (multiple of 4)
     static constexpr int NN = NM * NM;
+    static constexpr int NS = NM / 4;                   // 4-row strips per column
     static constexpr int GM = 32 * CPL;                 // max GP cells
-    static constexpr int MB = (GM > NN) ? GM : NN;      // size of one matrix scratch buffer
     static constexpr int PK = NM * (NM - 1);            // max off-diagonal pairs, both axes
     static constexpr int TR = NM * (NM + 1) / 2;        // packed lower-triangular entries of one matrix
-    // per-warp scratch, in doubles
+    // per-warp scratch, in doubles (every offset even: LDS.128 / STS.128 need 16-byte alignment).
+    // Grid-shaped buffers hold element (i, j) at i + j*NM (rows = drug-2 levels, padded to NM).
     static constexpr int OFF_TH = 0;                    // th[16] constrained scalars, ur[16] raw (unconstrained)
     static constexpr int OFF_UR = 16;
     static constexpr int OFF_PM = 32;                   // pm[32]: p01 then p02
-    static constexpr int OFF_PMB = 64;                  // 3*32 mono backward products
-    static constexpr int OFF_INVD = 160;                // 2*16 inverse Cholesky diagonals
-    static constexpr int OFF_L1R = 192;
-    static constexpr int OFF_L2R = OFF_L1R + NN;
-    static constexpr int OFF_L2C = OFF_L2R + NN;
-    static constexpr int OFF_M0 = OFF_L2C + NN;
-    static constexpr int OFF_M1 = OFF_M0 + MB;
-    static constexpr int OFF_M2 = OFF_M1 + MB;
-    static constexpr int OFF_M3 = OFF_M2 + MB;
-    static constexpr int OFF_LB1 = OFF_M3 + MB;
-    static constexpr int OFF_LB2 = OFF_LB1 + NN;
+    static constexpr int OFF_INVD = 64;                 // 2*16 inverse Cholesky diagonals
+    static constexpr int OFF_L1R = 96;                  // L1 row-major  [j*NM + l]
+    static constexpr int OFF_L2R = OFF_L1R + NN;        // L2 row-major  [i*NM + k]
+    static constexpr int OFF_L2C = OFF_L2R + NN;        // L2 col-major  [k*NM + i]
+    static constexpr int OFF_ZS = OFF_L2C + NN;         // Z           ; later S1 = L1^T L1bar
+    static constexpr int OFF_TS = OFF_ZS + NN;          // T = L2 Z    ; later S2 = L2^T L2bar
+    static constexpr int OFF_TT = OFF_TS + NN;          // T^T         ; later Y1 transpose
+    static constexpr int OFF_GS = OFF_TT + NN;          // G -> Gbar (in place) -> Zbar
+    static constexpr int OFF_WS = OFF_GS + NN;          // L1 col-major (Cholesky) ; p0bar ; W = Gbar L1 ; later Y2 transpose
+    static constexpr int OFF_LB1 = OFF_WS + NN;         // L1bar row-major [j*NM + l] ; later X1
+    static constexpr int OFF_LB2 = OFF_LB1 + NN;        // L2bar col-major [i + k*NM] ; later X2
     static constexpr int OFF_EX = OFF_LB2 + NN;         // exp table per pair
     static constexpr int WS_DOUBLES = OFF_EX + PK + (PK & 1);
 };
@@ -86,6 +87,34 @@ __device__ __forceinline__ double warp_sum(double v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
+}
+// Sum 8 per-lane values over the warp with 9 (instead of 40) 64-bit shuffles: three halving exchanges over
+// lane bits 0,1,2 leave lane L with the 8-lane partial sum of value (L & 7), two plain butterflies finish.
+// Returns on lane L the warp total of v[L & 7].
+__device__ __forceinline__ double warp_sum8(const double (&v)[8])
+{
+    const int lane = threadIdx.x & 31;
+    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
+    double w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {   // keep values with index bit0 == lane bit0
+        const double keep = b0 ? v[2 * k + 1] : v[2 * k], send = b0 ? v[2 * k] : v[2 * k + 1];
+        w[k] = keep + __shfl_xor_sync(FULL, send, 1);
+    }
+    double x[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {   // w[k] has index bit1 = k & 1: keep those matching lane bit1
+        const double keep = b1 ? w[2 * k + 1] : w[2 * k], send = b1 ? w[2 * k] : w[2 * k + 1];
+        x[k] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    double r;
+    {
+        const double keep = b2 ? x[1] : x[0], send = b2 ? x[0] : x[1];
+        r = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    r += __shfl_xor_sync(FULL, r, 8);
+    r += __shfl_xor_sync(FULL, r, 16);
+    return r;
 }
 __device__ __forceinline__ double half_sum(double v)   // sum within each half-warp
 {

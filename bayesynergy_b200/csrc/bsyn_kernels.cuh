@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const Pro
     const int s_pd = sl.pd_off + warp * sl.pd_stride;
     const int s_pi = 2 * (sl.pi_off + warp * sl.pi_stride);
     const int ws = sl.ws_off + warp * C::WS_DOUBLES;
+    for (int e = lane; e < C::WS_DOUBLES; e += 32) smem[ws + e] = 0.0;   // the factor's upper triangle must stay zero
+    __syncwarp();
     int loaded = -1;
     ProbS P;
     int cell[CPL];
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(32 * WPC) write_array_kernel(const Flags F, co
     const int s_pd = sl.pd_off + warp * sl.pd_stride;
     const int s_pi = 2 * (sl.pi_off + warp * sl.pi_stride);
     const int ws = sl.ws_off + warp * C::WS_DOUBLES;
+    for (int e = lane; e < C::WS_DOUBLES; e += 32) smem[ws + e] = 0.0;   // the factor's upper triangle must stay zero
+    __syncwarp();
     int loaded = -1;
     ProbS P;
     int cell[CPL];

@@ -77,10 +77,42 @@ __device__ __forceinline__ void kern_partials(const Flags &F, double d, double i
 }
 
 // ---------------------------------------------------------------------------------------------------
-// GP forward: kernel matrices -> two Cholesky factors (one per half-warp, rows in registers, pivots and
-// columns exchanged by shuffles) -> GP = L2 * Z * L1^T with the triangular structure.
-// Leaves in scratch: L1r, L2r (row-major), L2c (column-major), invd (1/diag), exv (exp table),
-// M0 = Z, M1 = T = L2*Z.  Returns GP values of this lane's cells in Gv.
+// Strip product: the one matrix-product shape every Kronecker / adjoint product is reduced to.
+//   Out[r0..r0+3, c] = sum_{m < nm} A[r0..r0+3 + m*NM] * B[c*SBC + m*SBM]        (c < C)
+// A lane owns a 4-row strip of one output column: per m it issues 2 LDS.128 (A) + 1 LDS.64 (B, shared by the
+// strip) for 4 DFMA; rows r0..r0+3 beyond the valid size only ever produce values in padding rows.
+template <int NM, int SBC, int SBM, class Epi>
+__device__ __forceinline__ void strip_product(const double *A, const double *B, const int C, const int nm, Epi &&epi)
+{
+    constexpr int NS = NM / 4;
+    const int lane = threadIdx.x & 31;
+    for (int s = lane; s < NS * C; s += 32) {
+        const int c = s / NS, r0 = 4 * (s - c * NS);
+        const double2 *Ap = reinterpret_cast<const double2 *>(A + r0);
+        const double *Bp = B + c * SBC;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+        for (int m = 0; m < nm; ++m) {
+            const double2 x = Ap[m * (NM / 2)], y = Ap[m * (NM / 2) + 1];
+            const double bv = Bp[m * SBM];
+            a0 = fma(x.x, bv, a0); a1 = fma(x.y, bv, a1); a2 = fma(y.x, bv, a2); a3 = fma(y.y, bv, a3);
+        }
+        epi(r0, c, a0, a1, a2, a3);
+    }
+}
+__device__ __forceinline__ void st2(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
+
+template <int CPL> __device__ __forceinline__ int zoff(const int cell)   // cell -> offset in a grid-shaped buffer
+{
+    return (cell & 255) + ((cell >> 8) & 255) * Cfg<CPL>::NM;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GP forward: kernel matrices -> two Cholesky factors -> GP = L2 * Z * L1^T.
+// Cholesky: half-warp h factorises matrix h, lane r of the half keeps row r in registers; the pivot travels by
+// shuffle, column k is published to the column-major factor in shared memory and read back (broadcast LDS.128)
+// for the trailing update.  Leaves in scratch: L1r, L2r (row-major), L2c (column-major), invd (1/diag), exv
+// (exp table), Zs = Z, Ts = T = L2*Z, Tt = T^T, Gs = GP.  Returns GP of this lane's cells in Gv.
 template <int CPL>
 __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const int ws, const int (&cell)[CPL],
                                            const double (&z)[CPL], double (&Gv)[CPL])
@@ -91,39 +123,40 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const
     const int n1 = P.n1, n2 = P.n2;
     double *const th = smem + ws + C::OFF_TH;
     double *const invd = smem + ws + C::OFF_INVD, *const L1r = smem + ws + C::OFF_L1R, *const L2r = smem + ws + C::OFF_L2R,
-                 *const L2c = smem + ws + C::OFF_L2C;
-    double *const M0 = smem + ws + C::OFF_M0, *const M1 = smem + ws + C::OFF_M1, *const exv = smem + ws + C::OFF_EX;
+                 *const L2c = smem + ws + C::OFF_L2C, *const L1c = smem + ws + C::OFF_WS;
+    double *const Zs = smem + ws + C::OFF_ZS, *const Ts = smem + ws + C::OFF_TS, *const Tt = smem + ws + C::OFF_TT,
+                 *const Gs = smem + ws + C::OFF_GS, *const exv = smem + ws + C::OFF_EX;
     const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA];
     const double iell = 1.0 / th[SL_ELL];
     const int P1 = P.P1, Pn = P.P1 + P.P2;
     for (int e0 = lane; e0 < Pn; e0 += 32) {
-        double d = smem[P.dist + e0];
-        int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
+        const double d = smem[P.dist + e0];
+        const int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
         double ev;
         if (F.kernel == 3) {
-            double w = d * d * iell * iell / (2.0 * alpha);
+            const double w = d * d * iell * iell / (2.0 * alpha);
             ev = exp(-alpha * log1p(w));
         } else {
             ev = exp(kern_arg(F, d, iell, alpha));
         }
         exv[e0] = ev;
-        double kv = kern_val(F, d, iell, ev);
-        if (e0 < P1) M0[a * NM + b] = sigf * kv; else M1[a * NM + b] = kv;
+        const double kv = kern_val(F, d, iell, ev);
+        if (e0 < P1) L1c[b * NM + a] = sigf * kv; else L2c[b * NM + a] = kv;   // lower triangle, column-major
     }
     __syncwarp();
-    // Cholesky: half-warp h factorises matrix h; lane r of the half holds row r.
     const int h = lane >> 4, r = lane & 15;
     const int n = h ? n2 : n1;
     bool ok = true;
     {
-        const double *A = h ? M1 : M0;
+        double *const Lc = h ? L2c : L1c;
         const double dg = h ? (1.0 + 1e-10) : (sigf + 1e-10);
         double a[NM];
         static_for<0, NM>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            const double lo = (r < n && k < r) ? A[r * NM + k] : 0.0;
+            const double lo = (r < n && k < r) ? Lc[k * NM + r] : 0.0;
             a[k] = (k == r) ? ((r < n) ? dg : 1.0) : lo;
         });
+        __syncwarp();
         static_for<0, NM>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             const double dkk = __shfl_sync(FULL, a[k], (lane & 16) + k);
@@ -131,51 +164,62 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const
             const double inv = rsqrt(dkk);
             a[k] *= inv;
             if (r == k) invd[h * 16 + k] = inv;
-            static_for<k + 1, NM>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                const double ljk = __shfl_sync(FULL, a[k], (lane & 16) + j);
-                a[j] = (r >= j) ? fma(-a[k], ljk, a[j]) : a[j];
+            if (r >= k && r < NM) Lc[k * NM + r] = a[k];   // publish column k
+            __syncwarp();
+            // trailing update a[j] -= L[r][k] * L[j][k], j > k.  Entries j > r (upper triangle) are updated too:
+            // they are never read (masked to zero when the row is stored).
+            constexpr int j0 = k + 1;
+            if constexpr (j0 < NM && (j0 & 1)) a[j0] = fma(-a[k], Lc[k * NM + j0], a[j0]);
+            constexpr int je = j0 + (j0 & 1);
+            static_for<je / 2, NM / 2>([&](auto pc) {
+                constexpr int j = 2 * decltype(pc)::value;
+                const double2 l = *reinterpret_cast<const double2 *>(Lc + k * NM + j);
+                a[j] = fma(-a[k], l.x, a[j]);
+                a[j + 1] = fma(-a[k], l.y, a[j + 1]);
             });
         });
-        __syncwarp();   // all reads of M0/M1 (A) are done before they are reused below
-        double *Lr = h ? L2r : L1r;
+        double *const Lr = h ? L2r : L1r;
         if (r < NM) {
-            static_for<0, NM>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                Lr[r * NM + k] = a[k];
-                if (h) L2c[k * NM + r] = a[k];
+            static_for<0, NM / 2>([&](auto pc) {
+                constexpr int k = 2 * decltype(pc)::value;
+                st2(Lr + r * NM + k, (k <= r) ? a[k] : 0.0, (k + 1 <= r) ? a[k + 1] : 0.0);
             });
         }
     }
-    // Z -> M0 ; T = L2*Z -> M1 ; G = T*L1^T
+    // Z -> Zs ; T = L2*Z -> Ts, Tt ; G = T*L1^T -> Gs
 #pragma unroll
     for (int t = 0; t < CPL; ++t)
-        if (cell[t] >> 16) M0[lane + 32 * t] = z[t];
+        if (cell[t] >> 16) Zs[zoff<CPL>(cell[t])] = z[t];
     __syncwarp();
-    double acc[CPL];
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) acc[t] = 0.0;
-    for (int k = 0; k < n2; ++k) {
-#pragma unroll
-        for (int t = 0; t < CPL; ++t) {
-            int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
-            if ((cell[t] >> 16) && k <= i) acc[t] = fma(L2c[k * NM + i], M0[k + j * n2], acc[t]);
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < CPL; ++t)
-        if (cell[t] >> 16) M1[lane + 32 * t] = acc[t];
+    strip_product<NM, NM, 1>(L2c, Zs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+        st2(Ts + r0 + c * NM, a0, a1); st2(Ts + r0 + c * NM + 2, a2, a3);
+        Tt[c + r0 * NM] = a0; Tt[c + (r0 + 1) * NM] = a1; Tt[c + (r0 + 2) * NM] = a2; Tt[c + (r0 + 3) * NM] = a3;
+    });
+    __syncwarp();
+    strip_product<NM, NM, 1>(Ts, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+        st2(Gs + r0 + c * NM, a0, a1); st2(Gs + r0 + c * NM + 2, a2, a3);
+    });
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < CPL; ++t) Gv[t] = 0.0;
-    for (int l = 0; l < n1; ++l) {
-#pragma unroll
-        for (int t = 0; t < CPL; ++t) {
-            int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
-            if ((cell[t] >> 16) && l <= j) Gv[t] = fma(M1[i + l * n2], L1r[j * NM + l], Gv[t]);
-        }
-    }
+    for (int t = 0; t < CPL; ++t) Gv[t] = (cell[t] >> 16) ? Gs[zoff<CPL>(cell[t])] : 0.0;
     return ok;
+}
+
+// Solve L^T y = s for one right-hand side held in registers (s is overwritten, y returned in s).
+// Right-looking form: once y[k] is known every remaining entry is updated independently, so the dependent
+// chain is NM steps long, not NM^2/2.  L row-major in shared memory, rows >= n are identity rows.
+template <int NM> __device__ __forceinline__ void solve_LT(const double *Lr, const double *idg, double (&s)[NM])
+{
+    static_for<0, NM>([&](auto kc) {
+        constexpr int k = NM - 1 - decltype(kc)::value;
+        s[k] *= idg[k];
+        static_for<0, (k + 1) / 2>([&](auto pc) {          // rr = 0 .. k-1 in pairs (rr = k itself is harmless: L[k][k]
+            constexpr int rr = 2 * decltype(pc)::value;     //  is only touched when rr+1 == k, handled below)
+            const double2 l = *reinterpret_cast<const double2 *>(Lr + k * NM + rr);
+            s[rr] = fma(-l.x, s[k], s[rr]);
+            if constexpr (rr + 1 < k) s[rr + 1] = fma(-l.y, s[k], s[rr + 1]);
+        });
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -265,18 +309,17 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
 // dbg (DBG only): global scratch for intermediate dumps (tests).
 template <int CPL, bool DBG>
 __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, const int ws, const int (&cell)[CPL],
-                                            const WVec<CPL> &q, const int jacobian, double &lp_out, WVec<CPL> &g,
-                                            double *dbg)
+                                               const WVec<CPL> &q, const int jacobian, double &lp_out, WVec<CPL> &g,
+                                               double *dbg)
 {
     using C = Cfg<CPL>;
     constexpr int NM = C::NM;
     const int lane = threadIdx.x & 31;
     const int n1 = P.n1, n2 = P.n2, nm = n1 + n2;
-    double *const th = smem + ws + C::OFF_TH, *const ur = smem + ws + C::OFF_UR, *const pm = smem + ws + C::OFF_PM,
-                 *const pmb = smem + ws + C::OFF_PMB;
+    double *const th = smem + ws + C::OFF_TH, *const ur = smem + ws + C::OFF_UR, *const pm = smem + ws + C::OFF_PM;
     double *const invd = smem + ws + C::OFF_INVD, *const L1r = smem + ws + C::OFF_L1R, *const L2r = smem + ws + C::OFF_L2R;
-    double *const M0 = smem + ws + C::OFF_M0, *const M1 = smem + ws + C::OFF_M1, *const M2 = smem + ws + C::OFF_M2,
-                 *const M3 = smem + ws + C::OFF_M3;
+    double *const Zs = smem + ws + C::OFF_ZS, *const Ts = smem + ws + C::OFF_TS, *const Tt = smem + ws + C::OFF_TT,
+                 *const Gs = smem + ws + C::OFF_GS, *const Ws = smem + ws + C::OFF_WS;
     double *const Lb1 = smem + ws + C::OFF_LB1, *const Lb2 = smem + ws + C::OFF_LB2, *const exv = smem + ws + C::OFF_EX;
     const bool gp = (F.model == 0);
     const double J = jacobian ? 1.0 : 0.0;
@@ -357,10 +400,8 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     const double is2 = 1.0 / (s * s);
     const double b1 = th[SL_B1], b2 = th[SL_B2];
     double b1bar = 0.0, b2bar = 0.0, slogbar = 0.0;
-    double Gbar[CPL];
 #pragma unroll
     for (int t = 0; t < CPL; ++t) {
-        Gbar[t] = 0.0;
         if (cell[t] >> 16) {
             const int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
             const double p0 = pm[j] * pm[n1 + i], q0 = 1.0 - p0;
@@ -383,10 +424,10 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
             }
             const int fc = (i + 1) + (j + 1) * (n2 + 1);
             const double fbar = lik_cell(F, P, fc, f, s, is2, lpl, slogbar, ok);
-            Gbar[t] = fbar * dfdG;
+            if (gp) Gs[zoff<CPL>(cell[t])] = fbar * dfdG;   // Gbar, in place of G
             b1bar = fma(fbar, dfdb1, b1bar);
             b2bar = fma(fbar, dfdb2, b2bar);
-            M2[lane + 32 * t] = fbar * dfdp0;   // p0bar
+            Ws[lane + 32 * t] = fbar * dfdp0;   // p0bar, packed cell index i + j*n2
         }
     }
     // boundary cells of f: f[0,a] = p01[a-1], f[b,0] = p02[b-1], f[0,0] = 1 (gp_grid.stan:170-172)
@@ -396,125 +437,107 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         pmbar = lik_cell(F, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, ok);
     }
     __syncwarp();
-    // ---- 7. adjoints of the monotherapy curves ------------------------------------------------------
-    if (lane < nm) {
-        if (lane < n1) { for (int i = 0; i < n2; ++i) pmbar = fma(M2[i + lane * n2], pm[n1 + i], pmbar); }
-        else { const int i = lane - n1; for (int j = 0; j < n1; ++j) pmbar = fma(M2[i + j * n2], pm[j], pmbar); }
-        const bool d1 = lane < n1;
-        const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
-        const double c = pmbar * (1.0 - lam) * BSYN_LN10 * (1.0 - om) * om;   // (1-la) E ln10/(1+E)^2
-        pmb[lane] = pmbar * (1.0 - om);            // d/d la = E/(1+E)
-        pmb[32 + lane] = -c * (smem[P.xs + lane] - mm);   // d/d slope
-        pmb[64 + lane] = c * sl;                   // d/d log10_ec50
-    }
-    __syncwarp();
+    // ---- 7. adjoints of the monotherapy curves: 6 sums delivered to their owner lanes by one butterfly ----
     {
-        int which = -1, lo = 0, hi = 0;
-        if (lane == SL_LA1) { which = 0; lo = 0; hi = n1; }
-        else if (lane == SL_LA2) { which = 0; lo = n1; hi = nm; }
-        else if (lane == SL_SL1) { which = 1; lo = 0; hi = n1; }
-        else if (lane == SL_SL2) { which = 1; lo = n1; hi = nm; }
-        else if (lane == SL_M1) { which = 2; lo = 0; hi = n1; }
-        else if (lane == SL_M2) { which = 2; lo = n1; hi = nm; }
-        if (which >= 0) {
-            double sacc = 0.0;
-            for (int m = lo; m < hi; ++m) sacc += pmb[which * 32 + m];
-            tb += sacc;
+        double v8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (lane < nm) {
+            const bool d1 = lane < n1;
+            if (d1) { for (int i = 0; i < n2; ++i) pmbar = fma(Ws[i + lane * n2], pm[n1 + i], pmbar); }
+            else { const int i = lane - n1; for (int j = 0; j < n1; ++j) pmbar = fma(Ws[i + j * n2], pm[j], pmbar); }
+            const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
+            const double c = pmbar * (1.0 - lam) * BSYN_LN10 * (1.0 - om) * om;   // (1-la) E ln10/(1+E)^2
+            const double dla = pmbar * (1.0 - om);            // d/d la = E/(1+E)
+            const double dsl = -c * (smem[P.xs + lane] - mm); // d/d slope
+            const double dm = c * sl;                         // d/d log10_ec50
+            // value index = owner lane & 7: la1 0, la2 1, m1 2, m2 3, slope_1 6, slope_2 7
+            v8[0] = d1 ? dla : 0.0; v8[1] = d1 ? 0.0 : dla;
+            v8[2] = d1 ? dm : 0.0;  v8[3] = d1 ? 0.0 : dm;
+            v8[6] = d1 ? dsl : 0.0; v8[7] = d1 ? 0.0 : dsl;
         }
+        const double rsum = warp_sum8(v8);
+        if (lane < 8) tb += rsum;   // lanes 4, 5 (theta_k) receive the zero sums of indices 4, 5
     }
     // ---- 8-10. adjoints of the Kronecker product, the Cholesky factors and the kernels --------------
     double ellbar = 0.0, sigfbar = 0.0, alphabar = 0.0;
     if (gp) {
-        const int T1 = P.T1, Tn = P.T1 + P.T2;
-#pragma unroll
-        for (int t = 0; t < CPL; ++t)
-            if (cell[t] >> 16) M3[lane + 32 * t] = Gbar[t];
+        __syncwarp();   // p0bar (in Ws) has been consumed
+        // W = Gbar * L1 -> Ws            W[i,l] = sum_j Gbar[i,j] L1[j,l]
+        strip_product<NM, 1, NM>(Gs, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Ws + r0 + c * NM, a0, a1); st2(Ws + r0 + c * NM + 2, a2, a3);
+        });
+        // L1bar = tril(Gbar^T T) -> Lb1 row-major: strip rows l of column j hold L1bar[j,l], kept for l <= j
+        strip_product<NM, NM, 1>(Tt, Gs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Lb1 + r0 + c * NM, (r0 <= c) ? a0 : 0.0, (r0 + 1 <= c) ? a1 : 0.0);
+            st2(Lb1 + r0 + c * NM + 2, (r0 + 2 <= c) ? a2 : 0.0, (r0 + 3 <= c) ? a3 : 0.0);
+        });
         __syncwarp();
-        // W = Gbar * L1 -> M2   (W[i,l] = sum_{j>=l} Gbar[i,j] L1[j,l])
-        double acc[CPL];
+        // L2bar = tril(W Z^T) -> Lb2 col-major [i + k*NM], kept for i >= k
+        strip_product<NM, 1, NM>(Ws, Zs, n2, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Lb2 + r0 + c * NM, (r0 >= c) ? a0 : 0.0, (r0 + 1 >= c) ? a1 : 0.0);
+            st2(Lb2 + r0 + c * NM + 2, (r0 + 2 >= c) ? a2 : 0.0, (r0 + 3 >= c) ? a3 : 0.0);
+        });
+        if (DBG) {
 #pragma unroll
-        for (int t = 0; t < CPL; ++t) acc[t] = 0.0;
-        for (int j = 0; j < n1; ++j) {
-#pragma unroll
-            for (int t = 0; t < CPL; ++t) {
-                const int i = cell[t] & 255, l = (cell[t] >> 8) & 255;
-                if ((cell[t] >> 16) && j >= l) acc[t] = fma(M3[i + j * n2], L1r[j * NM + l], acc[t]);
-            }
+            for (int t = 0; t < CPL; ++t)
+                if (cell[t] >> 16) dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gs[zoff<CPL>(cell[t])];
         }
-#pragma unroll
-        for (int t = 0; t < CPL; ++t)
-            if (cell[t] >> 16) M2[lane + 32 * t] = acc[t];
         __syncwarp();
-        // Zbar = L2^T * W   (Zbar[k,l] = sum_{i>=k} L2[i,k] W[i,l]);  + N(0,1) prior on z
-#pragma unroll
-        for (int t = 0; t < CPL; ++t) acc[t] = 0.0;
-        for (int i = 0; i < n2; ++i) {
-#pragma unroll
-            for (int t = 0; t < CPL; ++t) {
-                const int k = cell[t] & 255, l = (cell[t] >> 8) & 255;
-                if ((cell[t] >> 16) && i >= k) acc[t] = fma(L2r[i * NM + k], M2[i + l * n2], acc[t]);
-            }
-        }
+        // Zbar = L2^T W -> Gs            Zbar[k,l] = sum_i L2[i,k] W[i,l]
+        strip_product<NM, NM, 1>(L2r, Ws, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Gs + r0 + c * NM, a0, a1); st2(Gs + r0 + c * NM + 2, a2, a3);
+        });
+        // Cholesky adjoint (Murray 2016): Xfull = L^-T (Phi + Phi^T) L^-1, Phi = tril(L^T Lbar), diag halved.
+        // Stage A: P = L^T Lbar (only its lower triangle is used) -> S1 (over Zs), S2 (over Ts)
+        strip_product<NM, 1, NM>(L1r, Lb1, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Zs + r0 + c * NM, a0, a1); st2(Zs + r0 + c * NM + 2, a2, a3);
+        });
+        strip_product<NM, NM, 1>(L2r, Lb2, n2, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Ts + r0 + c * NM, a0, a1); st2(Ts + r0 + c * NM + 2, a2, a3);
+        });
+        __syncwarp();
+        // Zbar is complete: gradient wrt z (+ its N(0,1) prior)
 #pragma unroll
         for (int t = 0; t < CPL; ++t) {
             const bool v = cell[t] >> 16;
-            g.z[t] = v ? acc[t] - q.z[t] : 0.0;
+            const double zb = v ? Gs[zoff<CPL>(cell[t])] : 0.0;
+            g.z[t] = v ? zb - q.z[t] : 0.0;
             if (v) lpl = fma(-0.5 * q.z[t], q.z[t], lpl);
-            if (DBG && v) { dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gbar[t]; dbg[2 * C::NN + 3 * C::GM + lane + 32 * t] = acc[t]; }
+            if (DBG && v) dbg[2 * C::NN + 3 * C::GM + lane + 32 * t] = zb;
         }
-        // L1bar = tril(Gbar^T T), L2bar = tril(W Z^T): one packed lower-triangular entry per lane and round
-        for (int e0 = lane; e0 < Tn; e0 += 32) {
-            const bool m1 = e0 < T1;
-            const int rc = SMI(P.tri + (m1 ? e0 : e0 - T1)), rr = rc >> 8, cc = rc & 255;
-            double sacc = 0.0;
-            if (m1) { for (int i = 0; i < n2; ++i) sacc = fma(M3[i + rr * n2], M1[i + cc * n2], sacc); Lb1[rr * NM + cc] = sacc; }
-            else { for (int l = 0; l < n1; ++l) sacc = fma(M2[rr + l * n2], M0[cc + l * n2], sacc); Lb2[rr * NM + cc] = sacc; }
-        }
-        __syncwarp();
-        // Cholesky adjoint (Murray 2016): Xfull = L^-T (Phi + Phi^T) L^-1, Phi = tril(L^T Lbar), diag halved.
-        // Stage A: S = Phi + Phi^T -> M0 (matrix 1), M1 (matrix 2)
-        for (int e0 = lane; e0 < Tn; e0 += 32) {
-            const bool m1 = e0 < T1;
-            const int rc = SMI(P.tri + (m1 ? e0 : e0 - T1)), a = rc >> 8, b = rc & 255;
-            const double *L = m1 ? L1r : L2r, *Lb = m1 ? Lb1 : Lb2;
-            const int n = m1 ? n1 : n2;
-            double sacc = 0.0;
-            for (int i = a; i < n; ++i) sacc = fma(L[i * NM + a], Lb[i * NM + b], sacc);
-            double *S = m1 ? M0 : M1;
-            S[a * NM + b] = sacc;
-            S[b * NM + a] = sacc;
-        }
-        __syncwarp();
         {
             const int h = lane >> 4, r = lane & 15;
             const int n = h ? n2 : n1;
-            const double *L = h ? L2r : L1r;
-            double *S = h ? M1 : M0, *Y = h ? M3 : M2;
-            const double *idg = invd + h * 16;
-            // Stage B: Y = L^-T S (column r of Y on lane r)
-            if (r < n) {
-                for (int rr = n - 1; rr >= 0; --rr) {
-                    double sacc = S[rr * NM + r];
-                    for (int k = rr + 1; k < n; ++k) sacc = fma(-L[k * NM + rr], Y[k * NM + r], sacc);
-                    Y[rr * NM + r] = sacc * idg[rr];
-                }
-            }
+            const double *const Lr = h ? L2r : L1r;
+            const double *const Sm = h ? Ts : Zs;
+            double *const Yb = h ? Ws : Tt;
+            double *const Xb = h ? Lb2 : Lb1;
+            const double *const idg = invd + h * 16;
+            double sv[NM];
+            // Stage B: column r of Y = L^-T S;  S[rr, r] = P[max, min] (P stored [a + b*NM], lower part valid)
+            static_for<0, NM>([&](auto kc) {
+                constexpr int rr = decltype(kc)::value;
+                const int hi = rr > r ? rr : r, lo = rr > r ? r : rr;
+                sv[rr] = (rr < n && r < n) ? Sm[hi + lo * NM] : 0.0;
+            });
+            solve_LT<NM>(Lr, idg, sv);
+            __syncwarp();   // (Yb aliases buffers read by the strip products above)
+            if (r < NM) static_for<0, NM>([&](auto kc) { constexpr int rr = decltype(kc)::value; Yb[rr * NM + r] = sv[rr]; });
             __syncwarp();
-            // Stage C: X = Y L^-1 (row r of X on lane r), stored transposed over S: X[r,c] at S[c*NM + r]
-            if (r < n) {
-                for (int c = n - 1; c >= 0; --c) {
-                    double sacc = Y[r * NM + c];
-                    for (int k = c + 1; k < n; ++k) sacc = fma(-S[k * NM + r], L[k * NM + c], sacc);
-                    S[c * NM + r] = sacc * idg[c];
-                }
-            }
+            // Stage C: row r of X = Y L^-1  (same solve applied to row r of Y)
+            static_for<0, NM / 2>([&](auto pc) {
+                constexpr int c = 2 * decltype(pc)::value;
+                const double2 y2 = (r < NM) ? *reinterpret_cast<const double2 *>(Yb + r * NM + c) : make_double2(0.0, 0.0);
+                sv[c] = (r < n) ? y2.x : 0.0;
+                sv[c + 1] = (r < n) ? y2.y : 0.0;
+            });
+            solve_LT<NM>(Lr, idg, sv);
+            if (r < NM) static_for<0, NM / 2>([&](auto pc) { constexpr int c = 2 * decltype(pc)::value; st2(Xb + r * NM + c, sv[c], sv[c + 1]); });
             __syncwarp();
         }
         if (DBG) {
             for (int e0 = lane; e0 < C::NN; e0 += 32) {
                 dbg[e0] = L1r[e0]; dbg[C::NN + e0] = L2r[e0];
-                dbg[2 * C::NN + 4 * C::GM + e0] = Lb1[e0]; dbg[3 * C::NN + 4 * C::GM + e0] = Lb2[e0];
-                dbg[4 * C::NN + 4 * C::GM + e0] = M0[e0]; dbg[5 * C::NN + 4 * C::GM + e0] = M1[e0];
+                dbg[4 * C::NN + 4 * C::GM + e0] = Lb1[e0]; dbg[5 * C::NN + 4 * C::GM + e0] = Lb2[e0];
             }
         }
         // contraction with d cov / d(ell, sigma_f, alpha): sum over all (a,b) of Sbar_sym * dcov
@@ -524,7 +547,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         for (int e0 = lane; e0 < Pn; e0 += 32) {
             const bool m1 = e0 < P1;
             const int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
-            const double X = (m1 ? M0 : M1)[b * NM + a];
+            const double X = (m1 ? Lb1 : Lb2)[a * NM + b];
             double kv, dk, da;
             kern_partials(F, smem[P.dist + e0], iell, alpha, exv[e0], kv, dk, da);
             const double sc = m1 ? sigf : 1.0;
@@ -532,31 +555,29 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
             alphabar = fma(X * sc, da, alphabar);
             if (m1) sigfbar = fma(X, kv, sigfbar);
         }
-        if (lane < n1) sigfbar = fma(0.5, M0[lane * NM + lane], sigfbar);
+        if (lane < n1) sigfbar = fma(0.5, Lb1[lane * NM + lane], sigfbar);
     } else {
 #pragma unroll
         for (int t = 0; t < CPL; ++t) g.z[t] = 0.0;
     }
-    // ---- 11. reductions and chain rule through the constraining transforms ---------------------------
-    double tot;
-    tot = warp_sum(b1bar); if (lane == SL_B1) tb += tot;
-    tot = warp_sum(b2bar); if (lane == SL_B2) tb += tot;
-    if (gp) {
-        tot = warp_sum(ellbar); if (lane == SL_ELL) tb += tot;
-        tot = warp_sum(sigfbar); if (lane == SL_SIGF) tb += tot;
-        if (F.est_alpha) { tot = warp_sum(alphabar); if (lane == SL_ALPHA) tb += tot; }
+    // ---- 11. one butterfly for the 7 remaining sums; chain rule through the constraining transforms ------
+    // value index = owner lane & 7: b1 (lane 8) 0, b2 1, ell 2, sigma_f 3, alpha 4, s (lane 13) 5; 6 = lp
+    double lp;
+    {
+        const double v8[8] = {b1bar, b2bar, ellbar, sigfbar, alphabar, slogbar, lpl, 0.0};
+        const double rsum = warp_sum8(v8);
+        if (lane >= SL_B1 && lane <= SL_ALPHA) tb += rsum;
+        lp = __shfl_sync(FULL, rsum, 6);
+        lp += -(double)P.N * (BSYN_LOG_2PI_HALF + ur[SL_S]);
+        if (gp) lp += -(double)P.G * BSYN_LOG_2PI_HALF;
+        double gs;
+        if (is_la) gs = tb * thv * (1.0 - thv) + J * (1.0 - 2.0 * thv);
+        else if (is_lb) gs = tb * thv + J;
+        else gs = tb;
+        if (lane == SL_S) gs += rsum;
+        if (!act) gs = 0.0;
+        g.s = gs;
     }
-    const double slog = warp_sum(slogbar);
-    double lp = warp_sum(lpl);
-    lp += -(double)P.N * (BSYN_LOG_2PI_HALF + ur[SL_S]);
-    if (gp) lp += -(double)P.G * BSYN_LOG_2PI_HALF;
-    double gs;
-    if (is_la) gs = tb * thv * (1.0 - thv) + J * (1.0 - 2.0 * thv);
-    else if (is_lb) gs = tb * thv + J;
-    else gs = tb;
-    if (lane == SL_S) gs += slog;
-    if (!act) gs = 0.0;
-    g.s = gs;
     lp_out = lp;
     ok = ok && (lp == lp);
     return __all_sync(FULL, ok);
@@ -579,7 +600,7 @@ __device__ __forceinline__ bool warp_write_array(const Flags &F, const ProbS &P,
     const int lane = threadIdx.x & 31;
     const int n1 = P.n1, n2 = P.n2, nm = n1 + n2, G = P.G;
     double *const th = smem + ws + C::OFF_TH, *const pm = smem + ws + C::OFF_PM;
-    double *const M2 = smem + ws + C::OFF_M2;   // f grid (ncf <= (NM+1)^2 may exceed MB: f goes to M2..M3, contiguous)
+    double *const M2 = smem + ws + C::OFF_LB1;  // f grid: (n2+1)(n1+1) <= (NM+1)^2 <= 2 NN doubles, spans Lb1..Lb2
     const bool gp = (F.model == 0);
     __syncwarp();
     double e;

@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) nuts_kernel(const Flags F, con
     const int n_items = sp.n_problems * sp.groups;
     const int s_tri = 2 * sp.sl.tri_off, s_pd = sp.sl.pd_off, s_pi = 2 * sp.sl.pi_off;
     for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
+    for (int e = lane; e < C::WS_DOUBLES; e += 32) smem[sp.sl.ws_off + warp * C::WS_DOUBLES + e] = 0.0;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(sp.work_counter, 1);
