@@ -131,18 +131,19 @@ static const VariantOps *variant(int cpl);
 
 // shared memory layouts.  per_warp_problem: every warp has its own problem block (logp / write_array
 // kernels); otherwise one block per CTA (sampler).
-static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t *bytes)
+static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t *bytes, int warps = WPC)
 {
     SmemLayout sl;
     const int tr = variant(b->cpl)->tr;
+    auto even = [](int v) { return (v + 1) & ~1; };   // LDS.128 / STS.128 need 16-byte aligned double offsets
     sl.tri_off = 0;
-    sl.pd_off = (tr + 1) / 2 + 1;
-    sl.pd_stride = b->max_d_smem + (b->max_d_smem & 1);
-    sl.pi_stride = (b->max_i_smem + 1) / 2 + 1;   // in doubles
-    const int nblk = per_warp_problem ? WPC : 1;
+    sl.pd_off = even((tr + 1) / 2 + 1);
+    sl.pd_stride = even(b->max_d_smem);
+    sl.pi_stride = even((b->max_i_smem + 1) / 2 + 1);   // in doubles
+    const int nblk = per_warp_problem ? warps : 1;
     sl.pi_off = sl.pd_off + nblk * sl.pd_stride;
-    sl.ws_off = sl.pi_off + nblk * sl.pi_stride;
-    *bytes = sizeof(double) * (size_t)(sl.ws_off + WPC * variant(b->cpl)->ws_doubles);
+    sl.ws_off = even(sl.pi_off + nblk * sl.pi_stride);
+    *bytes = sizeof(double) * (size_t)(sl.ws_off + warps * variant(b->cpl)->ws_doubles);
     return sl;
 }
 
@@ -460,7 +461,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     if (a->metric != 0) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample: metric = dense_e is not implemented yet (diag_e only)");
     CK(cudaSetDevice(b->device));
     SamplerParams sp{};
-    sp.n_problems = b->n; sp.chains = a->chains; sp.groups = (a->chains + WPC - 1) / WPC;
+    sp.n_problems = b->n; sp.chains = a->chains; sp.groups = (a->chains + NWPC - 1) / NWPC;
     sp.iter = a->iter; sp.warmup = a->warmup; sp.thin = a->thin; sp.max_depth = a->max_treedepth; sp.save_warmup = a->save_warmup;
     const int ns_samp = (a->iter - a->warmup + a->thin - 1) / a->thin, ns_warm = a->save_warmup ? (a->warmup + a->thin - 1) / a->thin : 0;
     sp.n_save = ns_samp + ns_warm;
@@ -479,10 +480,10 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     sp.draws = ds.draws; sp.ld_draws = ds.ld_draws; sp.udraws = ds.udraws; sp.ld_u = ds.ld_u;
     sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im;
     size_t bytes;
-    sp.sl = make_layout(b, false, &bytes);
+    sp.sl = make_layout(b, false, &bytes, NWPC);
     // persistent grid: as many CTAs as fit, capped by the number of work items
     int per_sm = 1;
-    int minb = 3;
+    int minb = 12;
     if (const char *e = getenv("BSYN_NUTS_MINB")) minb = atoi(e);
     CK(variant(b->cpl)->nuts_occupancy(minb, bytes, &per_sm));
     if (per_sm < 1) return fail(BSYN_ERR_UNSUPPORTED, "sampler kernel does not fit on an SM");
@@ -490,7 +491,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     const int grid = std::max(1, std::min(n_items, per_sm * b->num_sms));
     const int VS = (b->cpl + 1) * 32;
     sp.arena_stride = (long long)arena_vectors(a->max_treedepth) * VS;
-    if ((rc = ensure(&b->d_arena, &b->arena_elems, (size_t)grid * WPC * sp.arena_stride))) return rc;
+    if ((rc = ensure(&b->d_arena, &b->arena_elems, (size_t)grid * NWPC * sp.arena_stride))) return rc;
     sp.arena = b->d_arena;
     sp.grad_counter = b->d_gradctr; sp.work_counter = b->d_workctr;
     CK(cudaMemsetAsync(b->d_gradctr, 0, sizeof(unsigned long long), b->stream));

@@ -136,20 +136,20 @@ template <int CPL> struct VariantImpl {
     static cudaError_t nuts(int minb, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                             const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
     {
-        if (minb >= 3) nuts_kernel<CPL, WPC, 3><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
-        else nuts_kernel<CPL, WPC, 2><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
+        if (minb >= 16) nuts_kernel<CPL, NWPC, 16><<<grid, 32 * NWPC, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
+        else nuts_kernel<CPL, NWPC, 12><<<grid, 32 * NWPC, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
         return cudaGetLastError();
     }
     static cudaError_t nuts_occupancy(int minb, size_t bytes, int *per_sm)
     {
-        if (minb >= 3) {
-            cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, WPC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (minb >= 16) {
+            cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NWPC, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
             if (e != cudaSuccess) return e;
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, WPC, 3>, 32 * WPC, bytes);
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NWPC, 16>, 32 * NWPC, bytes);
         }
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, WPC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NWPC, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, WPC, 2>, 32 * WPC, bytes);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NWPC, 12>, 32 * NWPC, bytes);
     }
     static const VariantOps *ops()
     {
