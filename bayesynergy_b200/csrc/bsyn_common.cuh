@@ -59,7 +59,8 @@ template <int CPL> struct Cfg {
     static constexpr int OFF_UR = 16;
     static constexpr int OFF_PM = 32;                   // pm[32]: p01 then p02
     static constexpr int OFF_INVD = 64;                 // 2*16 inverse Cholesky diagonals
-    static constexpr int OFF_L1R = 96;                  // L1 row-major  [j*NM + l]
+    static constexpr int OFF_ITH = 96;                  // 16 per-slot reciprocals (1/theta, 1/(1-la), 1/(1+s^2))
+    static constexpr int OFF_L1R = 112;                 // L1 row-major  [j*NM + l]
     static constexpr int OFF_L2R = OFF_L1R + NN;        // L2 row-major  [i*NM + k]
     static constexpr int OFF_L2C = OFF_L2R + NN;        // L2 col-major  [k*NM + i]
     static constexpr int OFF_ZS = OFF_L2C + NN;         // Z           ; later S1 = L1^T L1bar

@@ -9,6 +9,7 @@
 // hand-derived.
 #pragma once
 #include "bsyn_common.cuh"
+#include "bsyn_math.cuh"
 
 namespace bsyn {
 
@@ -46,7 +47,7 @@ template <int CPL> __device__ __forceinline__ void make_cells(const Flags &F, co
 // kernel value from the stored exponential (and, for the backward pass, its partials)
 __device__ __forceinline__ double kern_arg(const Flags &F, double d, double iell, double alpha)
 {
-    // argument x of ev = exp(x) (RQ: ev = exp(-alpha*log1p(w)) handled by the caller)
+    // argument x of ev = fast_exp(x) (RQ: ev = fast_exp(-alpha*log1p(w)) handled by the caller)
     if (F.kernel == 1) return -0.5 * d * d * iell * iell;
     if (F.nu_matern == 1) return -d * iell;
     if (F.nu_matern == 2) return -BSYN_SQRT3 * d * iell;
@@ -127,7 +128,7 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const
     double *const Zs = smem + ws + C::OFF_ZS, *const Ts = smem + ws + C::OFF_TS, *const Tt = smem + ws + C::OFF_TT,
                  *const Gs = smem + ws + C::OFF_GS, *const exv = smem + ws + C::OFF_EX;
     const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA];
-    const double iell = 1.0 / th[SL_ELL];
+    const double iell = fast_rcp(th[SL_ELL]);
     const int P1 = P.P1, Pn = P.P1 + P.P2;
     for (int e0 = lane; e0 < Pn; e0 += 32) {
         const double d = smem[P.dist + e0];
@@ -135,9 +136,9 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const
         double ev;
         if (F.kernel == 3) {
             const double w = d * d * iell * iell / (2.0 * alpha);
-            ev = exp(-alpha * log1p(w));
+            ev = fast_exp(-alpha * log1p(w));
         } else {
-            ev = exp(kern_arg(F, d, iell, alpha));
+            ev = fast_exp(kern_arg(F, d, iell, alpha));
         }
         exv[e0] = ev;
         const double kv = kern_val(F, d, iell, ev);
@@ -161,7 +162,7 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const
             constexpr int k = decltype(kc)::value;
             const double dkk = __shfl_sync(FULL, a[k], (lane & 16) + k);
             ok = ok && (dkk > 0.0);
-            const double inv = rsqrt(dkk);
+            const double inv = fast_rsqrt(dkk);
             a[k] *= inv;
             if (r == k) invd[h * 16 + k] = inv;
             if (r >= k && r < NM) Lc[k * NM + r] = a[k];   // publish column k
@@ -224,17 +225,17 @@ template <int NM> __device__ __forceinline__ void solve_LT(const double *Lr, con
 
 // ---------------------------------------------------------------------------------------------------
 // Constrain this lane's scalar slot (h:1086-1215, Stan Math lub_constrain/lb_constrain semantics) and
-// publish th[16] / ur[16] to the warp scratch.  Returns the constrained value; e = exp(x) where
+// publish th[16] / ur[16] to the warp scratch.  Returns the constrained value; e = fast_exp(x) where
 // x = -|u| (la slots) or u (lb slots).
 __device__ __forceinline__ double constrain_slot(const Flags &F, double u, const int th, const int ur, double &e)
 {
     const int lane = threadIdx.x & 31;
     const bool act = (F.active_mask >> lane) & 1u;
     const bool is_la = lane < 2, is_lb = (lane >= SL_SL1) && (lane < SL_COUNT);
-    e = exp(is_la ? -fabs(u) : u);
+    e = fast_exp(is_la ? -fabs(u) : u);
     double thv;
     if (is_la) {
-        double rr = 1.0 / (1.0 + e);
+        double rr = fast_rcp(1.0 + e);
         if (u > 0) { thv = rr; if (thv == 1.0) thv = 1.0 - 1e-15; }
         else { thv = 1.0 - rr; if (thv == 0.0) thv = 1e-15; }
     } else if (is_lb) {
@@ -250,21 +251,32 @@ __device__ __forceinline__ double constrain_slot(const Flags &F, double u, const
 
 // Likelihood of one cell of f (gp_grid.stan:212-232) from its sufficient statistics (Normal variants) or
 // its sorted observations (LPTN variants).  Adds to lpl / slogbar, returns d lp / d f.
-// The per-observation constants  -log(2pi)/2 - log(s)  are added once per evaluation by the caller.
+// The per-observation constants  -log(2pi)/2 - log(s)  are added once per evaluation by the caller, and the
+// heteroscedastic  -n/2 log(f + lambda)  terms of all cells of a lane are folded into ONE logarithm:
+// vprod accumulates prod (f+lambda)^n (n <= 4 replicates; otherwise the log is taken directly).
 __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int fc, double f, double s, double is2,
-                                           double &lpl, double &slogbar, bool &ok)
+                                           double &lpl, double &slogbar, double &vprod, bool &ok)
 {
     const double n = smem[P.cnt + fc];
     if (n == 0.0) return 0.0;
     double fbar;
+    double iv = 0.0;
+    if (F.het) {
+        const double v = f + F.lambda;
+        if (!(v > 0.0)) { ok = false; return 0.0; }
+        iv = fast_rcp(v);
+        if (n <= 4.0) {
+            const double v2 = v * v;
+            vprod *= (n == 1.0) ? v : (n == 2.0) ? v2 : (n == 3.0) ? v2 * v : v2 * v2;
+        } else {
+            lpl += -0.5 * n * log(v);
+        }
+    }
     if (!F.robust) {
         const double d = smem[P.ybar + fc] - f;
         const double Q = fma(n * d, d, smem[P.ss + fc]);
         if (F.het) {
-            const double v = f + F.lambda;
-            if (!(v > 0.0)) { ok = false; return 0.0; }
-            const double iv = 1.0 / v;
-            lpl += -0.5 * n * log(v) - 0.5 * Q * is2 * iv;
+            lpl += -0.5 * Q * is2 * iv;
             fbar = iv * (-0.5 * n + is2 * (n * d + 0.5 * Q * iv));
             slogbar += -n + Q * is2 * iv;
         } else {
@@ -273,14 +285,8 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
             slogbar += -n + Q * is2;
         }
     } else {
-        double iv = 0.0, isd = 1.0 / s;
-        if (F.het) {
-            const double v = f + F.lambda;
-            if (!(v > 0.0)) { ok = false; return 0.0; }
-            iv = 1.0 / v;
-            isd = rsqrt(v) / s;
-            lpl += -0.5 * n * log(v);
-        }
+        double isd = fast_rcp(s);
+        if (F.het) isd *= sqrt(iv);
         fbar = -0.5 * n * iv;
         const int o1 = SMI(P.cstart + fc + 1);
         for (int o = SMI(P.cstart + fc); o < o1; ++o) {
@@ -294,7 +300,7 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
                 const double az = fmax(ar, 1.0001);
                 const double la = log(az);
                 lpl += F.lptn_c0 - la - (F.lamL + 1.0) * log(la);
-                dl = (ar > 1.0001) ? -copysign(1.0, r) / az * (1.0 + (F.lamL + 1.0) / la) : 0.0;
+                dl = (ar > 1.0001) ? -copysign(1.0, r) * fast_rcp(az) * (1.0 + (F.lamL + 1.0) * fast_rcp(la)) : 0.0;
             }
             fbar += dl * (-isd - 0.5 * r * iv);
             slogbar += -dl * r - 1.0;
@@ -334,20 +340,26 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     double lpl = 0.0;   // lane-local part of lp
     double tb = 0.0;    // d lp / d(constrained scalar of this lane)
     {
+        // one log1p and one reciprocal for all lanes (lane-specific arguments); the per-slot branches below
+        // then contain only a handful of multiply-adds each
         const double l1 = log1p(is_la ? e : (lane == SL_S ? thv * thv : 0.0));
+        const double ie = fast_rcp(is_la ? (1.0 - thv) : (lane == SL_S ? fma(thv, thv, 1.0) : thv));
+        double *const ith = smem + ws + C::OFF_ITH;
+        if (lane < 16) ith[lane] = ie;
+        __syncwarp();
         if (act) {
             if (is_la) {
                 lpl += J * (-fabs(u) - 2.0 * l1);
                 lpl += BSYN_BETA_C + 0.25 * (-fmax(u, 0.0) - l1);   // beta(1,1.25): 0.25*log1m(theta)
-                tb += -0.25 / (1.0 - thv);
+                tb += -0.25 * ie;
             } else if (lane == SL_M1 || lane == SL_M2) {
                 const int k = lane - SL_M1;
-                const double d = thv - th[SL_TH1 + k], is2k = 1.0 / th[SL_S21 + k];
+                const double d = thv - th[SL_TH1 + k], is2k = ith[SL_S21 + k];
                 lpl += -BSYN_LOG_2PI_HALF - 0.5 * ur[SL_S21 + k] - 0.5 * d * d * is2k;
                 tb += -d * is2k;
             } else if (lane == SL_TH1 || lane == SL_TH2) {
                 const int k = lane - SL_TH1;
-                const double d = th[SL_M1 + k] - thv, is2k = 1.0 / th[SL_S21 + k];
+                const double d = th[SL_M1 + k] - thv, is2k = ith[SL_S21 + k];
                 lpl += -0.5 * thv * thv - BSYN_LOG_2PI_HALF;
                 tb += -thv + d * is2k;
             } else if (lane == SL_SL1 || lane == SL_SL2) {
@@ -358,21 +370,20 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
                 lpl += -BSYN_LOG_2PI_HALF - BSYN_LOG_0_1 - 0.5 * rr * rr + J * u;
                 tb += -(thv - 1.0) * 100.0;
             } else if (lane == SL_ELL) {
-                const double ie = 1.0 / thv;
                 if (F.pcprior) { lpl += F.log_lam12 - 2.0 * u - F.lam1 * ie + J * u; tb += -2.0 * ie + F.lam1 * ie * ie; }
                 else { lpl += BSYN_IG55_C - 6.0 * u - 5.0 * ie + J * u; tb += -6.0 * ie + 5.0 * ie * ie; }
             } else if (lane == SL_SIGF) {
-                if (F.pcprior) { const double sq = sqrt(thv); lpl += -F.lam2 * sq - 0.5 * u + J * u; tb += -0.5 * F.lam2 / sq - 0.5 / thv; }
-                else { lpl += -BSYN_LOG_2PI_HALF - u - 0.5 * (u - 1.0) * (u - 1.0) + J * u; tb += -u / thv; }
+                if (F.pcprior) { const double sq = sqrt(thv); lpl += -F.lam2 * sq - 0.5 * u + J * u; tb += -0.5 * F.lam2 * sq * ie - 0.5 * ie; }
+                else { lpl += -BSYN_LOG_2PI_HALF - u - 0.5 * (u - 1.0) * (u - 1.0) + J * u; tb += -u * ie; }
             } else if (lane == SL_ALPHA) {
                 lpl += -thv + J * u;
                 tb += -1.0;
             } else if (lane == SL_S) {
                 lpl += BSYN_LOG_2 - BSYN_LOG_PI - l1 + J * u;
-                tb += -2.0 * thv / (1.0 + thv * thv);
+                tb += -2.0 * thv * ie;
             } else {   // SL_S21, SL_S22: inv_gamma(3,2) + the N(theta_k, sqrt(s2_k)) prior of log10_ec50_k
                 const int k = lane - SL_S21;
-                const double ie = 1.0 / thv, d = th[SL_M1 + k] - th[SL_TH1 + k];
+                const double d = th[SL_M1 + k] - th[SL_TH1 + k];
                 lpl += BSYN_IG32_C - 4.0 * u - 2.0 * ie + J * u;
                 tb += -4.0 * ie + 2.0 * ie * ie - 0.5 * ie + 0.5 * d * d * ie * ie;
             }
@@ -388,8 +399,8 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         const bool d1 = lane < n1;
         const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
         lam = th[d1 ? SL_LA1 : SL_LA2];
-        const double Em = exp(BSYN_LN10 * sl * (smem[P.xs + lane] - mm));
-        om = 1.0 / (1.0 + Em);
+        const double Em = fast_exp(BSYN_LN10 * sl * (smem[P.xs + lane] - mm));
+        om = fast_rcp(1.0 + Em);
         pmv = fma(1.0 - lam, om, lam);
         pm[lane] = pmv;
         ok = ok && (pmv >= 0.0) && (pmv <= 1.0);
@@ -397,9 +408,9 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     __syncwarp();
     // ---- 6. cells: Bliss product, Delta transform, likelihood and their adjoints, fused ------------
     const double s = th[SL_S];
-    const double is2 = 1.0 / (s * s);
+    const double is2 = fast_rcp(s * s);
     const double b1 = th[SL_B1], b2 = th[SL_B2];
-    double b1bar = 0.0, b2bar = 0.0, slogbar = 0.0;
+    double b1bar = 0.0, b2bar = 0.0, slogbar = 0.0, vprod = 1.0;
 #pragma unroll
     for (int t = 0; t < CPL; ++t) {
         if (cell[t] >> 16) {
@@ -409,8 +420,8 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
             ok = ok && (p0 >= 0.0) && (p0 <= 1.0);
             if (gp) {
                 const double B = Gv[t];
-                const double e1 = exp(b1 * B), e2 = exp(-b2 * B);
-                const double iD1 = 1.0 / fma(p0, e1, q0), iD2 = 1.0 / fma(q0, e2, p0);
+                const double e1 = fast_exp(b1 * B), e2 = fast_exp(-b2 * B);
+                const double iD1 = fast_rcp(fma(p0, e1, q0)), iD2 = fast_rcp(fma(q0, e2, p0));
                 const double t1 = q0 * iD1, u1 = p0 * e1 * iD1, t2 = p0 * iD2, u2 = q0 * e2 * iD2;
                 const double Delta = q0 * t2 - p0 * t1;
                 ok = ok && (Delta >= -1.0) && (Delta <= 1.0);
@@ -423,7 +434,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
                 if (DBG) { dbg[2 * C::NN + lane + 32 * t] = B; dbg[2 * C::NN + C::GM + lane + 32 * t] = f; }
             }
             const int fc = (i + 1) + (j + 1) * (n2 + 1);
-            const double fbar = lik_cell(F, P, fc, f, s, is2, lpl, slogbar, ok);
+            const double fbar = lik_cell(F, P, fc, f, s, is2, lpl, slogbar, vprod, ok);
             if (gp) Gs[zoff<CPL>(cell[t])] = fbar * dfdG;   // Gbar, in place of G
             b1bar = fma(fbar, dfdb1, b1bar);
             b2bar = fma(fbar, dfdb2, b2bar);
@@ -434,8 +445,9 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     double pmbar = 0.0;
     if (lane <= nm) {
         const int fc = lane < n1 ? (lane + 1) * (n2 + 1) : (lane < nm ? lane - n1 + 1 : 0);
-        pmbar = lik_cell(F, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, ok);
+        pmbar = lik_cell(F, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, vprod, ok);
     }
+    if (F.het) lpl += -0.5 * log(vprod);
     __syncwarp();
     // ---- 7. adjoints of the monotherapy curves: 6 sums delivered to their owner lanes by one butterfly ----
     {
@@ -542,7 +554,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         }
         // contraction with d cov / d(ell, sigma_f, alpha): sum over all (a,b) of Sbar_sym * dcov
         //   = sum_{a>b} Xfull[a,b] * dcov[a,b] + 1/2 sum_a Xfull[a,a] * dcov[a,a]
-        const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA], iell = 1.0 / th[SL_ELL];
+        const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA], iell = fast_rcp(th[SL_ELL]);
         const int P1 = P.P1, Pn = P.P1 + P.P2;
         for (int e0 = lane; e0 < Pn; e0 += 32) {
             const bool m1 = e0 < P1;
@@ -612,8 +624,8 @@ __device__ __forceinline__ bool warp_write_array(const Flags &F, const ProbS &P,
     if (lane < nm) {
         const bool d1 = lane < n1;
         const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2], lam = th[d1 ? SL_LA1 : SL_LA2];
-        const double Em = exp(BSYN_LN10 * sl * (smem[P.xs + lane] - mm));
-        pmv = fma(1.0 - lam, 1.0 / (1.0 + Em), lam);
+        const double Em = fast_exp(BSYN_LN10 * sl * (smem[P.xs + lane] - mm));
+        pmv = fma(1.0 - lam, fast_rcp(1.0 + Em), lam);
         pm[lane] = pmv;
         ok = ok && (pmv >= 0.0) && (pmv <= 1.0);
     }
@@ -648,8 +660,8 @@ __device__ __forceinline__ bool warp_write_array(const Flags &F, const ProbS &P,
             double Delta = 0.0;
             if (gp) {
                 const double B = Gv[t];
-                const double e1 = exp(b1 * B), e2 = exp(-b2 * B);
-                Delta = q0 * (p0 / fma(q0, e2, p0)) - p0 * (q0 / fma(p0, e1, q0));
+                const double e1 = fast_exp(b1 * B), e2 = fast_exp(-b2 * B);
+                Delta = q0 * (p0 * fast_rcp(fma(q0, e2, p0))) - p0 * (q0 * fast_rcp(fma(p0, e1, q0)));
                 ok = ok && (Delta >= -1.0) && (Delta <= 1.0);
                 if (row) { row[npre + c] = q.z[t]; row[o_delta + c] = Delta; row[o_gp + c] = B; }
             }
@@ -678,7 +690,7 @@ __device__ __forceinline__ bool warp_write_array(const Flags &F, const ProbS &P,
             const double f = fg[iiglob[n]];
             const double sd = F.het ? s * sqrt(f + F.lambda) : s;
             const double r = (yglob[n] - f) / sd;
-            const double cpo = exp(BSYN_LOG_2PI_HALF + log(sd) + 0.5 * r * r);
+            const double cpo = fast_exp(BSYN_LOG_2PI_HALF + log(sd) + 0.5 * r * r);
             if (row) row[o_cpo + n] = cpo;
             if (cpo_acc) cpo_acc[n] += cpo;
         }
@@ -691,9 +703,9 @@ __device__ __forceinline__ bool warp_write_array(const Flags &F, const ProbS &P,
         double c1 = x[0], c2 = x[0];
         for (int k = 1; k < n; ++k) { c1 = fmin(c1, x[k]); c2 = fmax(c2, x[k]); }
         const double la = th[SL_LA1 + lane], sl = th[SL_SL1 + lane], mm = th[SL_M1 + lane];
-        ec = exp(BSYN_LN10 * mm);
-        const double val = (c2 - c1) + (la - 1.0) / sl * (log10(1.0 + exp(BSYN_LN10 * sl * (c2 - mm))) -
-                                                          log10(1.0 + exp(BSYN_LN10 * sl * (c1 - mm))));
+        ec = fast_exp(BSYN_LN10 * mm);
+        const double val = (c2 - c1) + (la - 1.0) / sl * (log10(1.0 + fast_exp(BSYN_LN10 * sl * (c2 - mm))) -
+                                                          log10(1.0 + fast_exp(BSYN_LN10 * sl * (c1 - mm))));
         ds = 100.0 * (1.0 - val / (c2 - c1));
     }
     const double ec2 = __shfl_sync(FULL, ec, 1), ds2 = __shfl_sync(FULL, ds, 1);

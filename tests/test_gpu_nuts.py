@@ -20,7 +20,10 @@ def _compare(res_q, outs, names, tag):
         a = res_q[:, :, Q.index(qn)]
         c = outs[:, :, names.index(qn)]
         se = np.hypot(mcse_mean(a), mcse_mean(c))
-        assert abs(a.mean() - c.mean()) <= 3.0 * se + 1e-6, (tag, qn, a.mean(), c.mean(), se)
+        # north_star: synergy / antagonism (VUS) scores within 3 MCSE; the nuisance scalars get 4 (16 comparisons
+        # per test at 3 sigma would fail spuriously every ~20 runs)
+        nsig = 3.0 if "VUS" in qn else 4.0
+        assert abs(a.mean() - c.mean()) <= nsig * se + 1e-6, (tag, qn, a.mean(), c.mean(), se)
 
 
 def test_nuts_matches_oracle_mathews(built, datasets):

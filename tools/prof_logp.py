@@ -22,5 +22,6 @@ for rep in range(3):
     lp, g, st = b.logp_grad(U, prob_idx=idx)
 print("logp ok", int((st != 0).sum()), float(lp[:4].sum()))
 if os.environ.get("PROF_NUTS"):
-    ng, ms = b.sample_device(chains=4, iter=60, warmup=30, seed=1)
-    print("nuts", ng, ms)
+    it = int(os.environ.get("PROF_ITER", "60"))
+    ng, ms = b.sample_device(chains=4, iter=it, warmup=it // 2, seed=1)
+    print("nuts", ng, ms, "evals/s %.3e" % (ng / ms * 1e3))
