@@ -461,7 +461,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     if (a->metric != 0) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample: metric = dense_e is not implemented yet (diag_e only)");
     CK(cudaSetDevice(b->device));
     SamplerParams sp{};
-    sp.n_problems = b->n; sp.chains = a->chains; sp.groups = (a->chains + NWPC - 1) / NWPC;
+    sp.n_problems = b->n; sp.chains = a->chains;
     sp.iter = a->iter; sp.warmup = a->warmup; sp.thin = a->thin; sp.max_depth = a->max_treedepth; sp.save_warmup = a->save_warmup;
     const int ns_samp = (a->iter - a->warmup + a->thin - 1) / a->thin, ns_warm = a->save_warmup ? (a->warmup + a->thin - 1) / a->thin : 0;
     sp.n_save = ns_samp + ns_warm;
@@ -479,19 +479,23 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     sp.qdraws = b->d_qdraws; sp.sp = b->d_sp; sp.chain_stats = b->d_chain_stats;
     sp.draws = ds.draws; sp.ld_draws = ds.ld_draws; sp.udraws = ds.udraws; sp.ld_u = ds.ld_u;
     sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im;
-    size_t bytes;
-    sp.sl = make_layout(b, false, &bytes, NWPC);
-    // persistent grid: as many CTAs as fit, capped by the number of work items
-    int per_sm = 1;
-    int minb = 12;
-    if (const char *e = getenv("BSYN_NUTS_MINB")) minb = atoi(e);
-    CK(variant(b->cpl)->nuts_occupancy(minb, bytes, &per_sm));
-    if (per_sm < 1) return fail(BSYN_ERR_UNSUPPORTED, "sampler kernel does not fit on an SM");
-    const int n_items = b->n * sp.groups;
-    const int grid = std::max(1, std::min(n_items, per_sm * b->num_sms));
+    // warps per CTA: the largest compiled variant (11, 5, 1) whose shared memory fits on an SM
+    size_t bytes = 0;
+    int nw = 0, per_sm = 0;
+    const int want = getenv("BSYN_NUTS_NW") ? atoi(getenv("BSYN_NUTS_NW")) : 0;
+    for (int cand : {11, 5, 1}) {
+        if (want && cand != want) continue;
+        sp.sl = make_layout(b, true, &bytes, cand);
+        if (bytes > 227 * 1024) continue;
+        if (variant(b->cpl)->nuts_occupancy(cand, bytes, &per_sm) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (per_sm >= 1) { nw = cand; break; }
+    }
+    if (!nw) return fail(BSYN_ERR_UNSUPPORTED, "sampler kernel does not fit on an SM");
+    const int n_items = b->n * a->chains;
+    const int grid = std::max(1, std::min((n_items + nw - 1) / nw, per_sm * b->num_sms));
     const int VS = (b->cpl + 1) * 32;
     sp.arena_stride = (long long)arena_vectors(a->max_treedepth) * VS;
-    if ((rc = ensure(&b->d_arena, &b->arena_elems, (size_t)grid * NWPC * sp.arena_stride))) return rc;
+    if ((rc = ensure(&b->d_arena, &b->arena_elems, (size_t)grid * nw * sp.arena_stride))) return rc;
     sp.arena = b->d_arena;
     sp.grad_counter = b->d_gradctr; sp.work_counter = b->d_workctr;
     CK(cudaMemsetAsync(b->d_gradctr, 0, sizeof(unsigned long long), b->stream));
@@ -502,7 +506,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, b->stream));
-    CK(variant(b->cpl)->nuts(minb, grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sp));
+    CK(variant(b->cpl)->nuts(nw, grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sp));
     ++g_launches;
     // per-problem posterior summaries (mean, sd over all chains and saved sampling draws)
     {

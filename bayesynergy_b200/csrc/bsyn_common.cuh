@@ -16,7 +16,6 @@ namespace bsyn {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WPC = 4;   // warps per CTA of the stand-alone lp+grad / write_array kernels
-constexpr int NWPC = 1;  // warps per CTA of the sampler: one chain per CTA, so no chain ever waits for a sibling
 
 // canonical scalar slots (lane index).  Order = the reference's parameter order with la_k / alpha
 // always given a slot (inactive slots carry 0 and never move).

@@ -44,7 +44,9 @@ __global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const Pro
         WVec<CPL> q, g;
         load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
         double lpv;
-        const bool ok = warp_logp_grad<CPL, DBG>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr);
+        GQ gq{};
+        gq.on = false;
+        const bool ok = warp_logp_grad<CPL, DBG>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr, gq);
         if (!ok) {
             lpv = -INFINITY;
 #pragma unroll
@@ -93,11 +95,17 @@ __global__ void __launch_bounds__(32 * WPC) write_array_kernel(const Flags F, co
         load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
         RngKey rk;
         rk.k0 = (uint32_t)seed; rk.k1 = (uint32_t)(seed >> 32); rk.chain = (uint32_t)pt;
-        double uz[4];
-        rng_u2(rk, RT_GQ, 0xFFu, 0, 0, uz[0], uz[1]);
-        rng_u2(rk, RT_GQ, 0xFFu, 0, 1, uz[2], uz[3]);
-        const bool ok = warp_write_array<CPL>(F, P, pd, ws, cell, q, dpool + pd.off_d + pool_y_off(pd),
-                                              ipool + pd.off_i + pool_ii_off(pd), uz, out + (size_t)pt * ldo, nullptr, nullptr);
+        GQ gq{};
+        gq.on = true;
+        gq.D = pd.D;
+        gq.yglob = dpool + pd.off_d + pool_y_off(pd);
+        gq.iiglob = ipool + pd.off_i + pool_ii_off(pd);
+        rng_u2(rk, RT_GQ, 0xFFu, 0, 0, gq.uz[0], gq.uz[1]);
+        rng_u2(rk, RT_GQ, 0xFFu, 0, 1, gq.uz[2], gq.uz[3]);
+        gq.row = out + (size_t)pt * ldo; gq.qout = nullptr; gq.cpo_acc = nullptr;
+        WVec<CPL> gtmp;
+        double lpv;
+        const bool ok = warp_logp_grad<CPL, false>(F, P, ws, cell, q, 1, lpv, gtmp, nullptr, gq);
         if (lane == 0) status[pt] = ok ? 0 : 1;
     }
 }
@@ -133,23 +141,32 @@ template <int CPL> struct VariantImpl {
         write_array_kernel<CPL><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, out, ldo, seed, status);
         return cudaGetLastError();
     }
-    static cudaError_t nuts(int minb, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
-                            const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
+    // sampler instantiations: (warps per CTA, min CTAs per SM): 11 x 1 (all warps of an SM in step), 5 x 2, 1 x 11
+    template <int NW, int MINB>
+    static cudaError_t nuts_launch(int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                                   const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
     {
-        if (minb >= 16) nuts_kernel<CPL, NWPC, 16><<<grid, 32 * NWPC, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
-        else nuts_kernel<CPL, NWPC, 12><<<grid, 32 * NWPC, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
+        nuts_kernel<CPL, NW, MINB><<<grid, 32 * NW, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
         return cudaGetLastError();
     }
-    static cudaError_t nuts_occupancy(int minb, size_t bytes, int *per_sm)
+    template <int NW, int MINB> static cudaError_t nuts_occ(size_t bytes, int *per_sm)
     {
-        if (minb >= 16) {
-            cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NWPC, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-            if (e != cudaSuccess) return e;
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NWPC, 16>, 32 * NWPC, bytes);
-        }
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NWPC, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NWPC, 12>, 32 * NWPC, bytes);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NW, MINB>, 32 * NW, bytes);
+    }
+    static cudaError_t nuts(int nw, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                            const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
+    {
+        if (nw == 11) return nuts_launch<11, 1>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        if (nw == 5) return nuts_launch<5, 2>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        return nuts_launch<1, 11>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+    }
+    static cudaError_t nuts_occupancy(int nw, size_t bytes, int *per_sm)
+    {
+        if (nw == 11) return nuts_occ<11, 1>(bytes, per_sm);
+        if (nw == 5) return nuts_occ<5, 2>(bytes, per_sm);
+        return nuts_occ<1, 11>(bytes, per_sm);
     }
     static const VariantOps *ops()
     {

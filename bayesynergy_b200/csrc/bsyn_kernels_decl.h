@@ -14,9 +14,9 @@ struct VariantOps {
                                const double *dpool, const int *ipool, const int *tri, SmemLayout sl, int B,
                                const int *idx, const double *u, int ldu, double *out, int ldo, unsigned long long seed,
                                int *status);
-    cudaError_t (*nuts)(int minb, int grid, size_t smem_bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+    cudaError_t (*nuts)(int nw, int grid, size_t smem_bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                         const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp);
-    cudaError_t (*nuts_occupancy)(int minb, size_t smem_bytes, int *per_sm);
+    cudaError_t (*nuts_occupancy)(int nw, size_t smem_bytes, int *per_sm);
 };
 
 }  // namespace bsyn

@@ -130,6 +130,7 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const
     const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA];
     const double iell = fast_rcp(th[SL_ELL]);
     const int P1 = P.P1, Pn = P.P1 + P.P2;
+#pragma unroll 3
     for (int e0 = lane; e0 < Pn; e0 += 32) {
         const double d = smem[P.dist + e0];
         const int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
@@ -232,7 +233,7 @@ __device__ __forceinline__ double constrain_slot(const Flags &F, double u, const
     const int lane = threadIdx.x & 31;
     const bool act = (F.active_mask >> lane) & 1u;
     const bool is_la = lane < 2, is_lb = (lane >= SL_SL1) && (lane < SL_COUNT);
-    e = fast_exp(is_la ? -fabs(u) : u);
+    e = exp(is_la ? -fabs(u) : u);   // exact exp here: exp(u) = inf must propagate (the reference rejects it)
     double thv;
     if (is_la) {
         double rr = fast_rcp(1.0 + e);
@@ -309,6 +310,48 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
     return fbar;
 }
 
+// Branch-free version for the Normal likelihoods: an unobserved (or masked: live = false) cell has n = 0 and
+// every term vanishes, so the four cells of a lane are straight-line code the scheduler can interleave.
+__device__ __forceinline__ double lik_cell_normal(const Flags &F, const ProbS &P, int fc, double f, double is2, bool live,
+                                                  double &lpl, double &slogbar, double &vprod, bool &ok)
+{
+    const double n = live ? smem[P.cnt + fc] : 0.0;
+    const double d = smem[P.ybar + fc] - f;
+    const double Q = fma(n * d, d, (n > 0.0) ? smem[P.ss + fc] : 0.0);
+    if (F.het) {
+        const double v = f + F.lambda;
+        ok = ok && ((v > 0.0) || (n == 0.0));
+        const double iv = fast_rcp(v);
+        const double v2 = v * v;
+        vprod *= (n == 0.0) ? 1.0 : (n == 1.0) ? v : (n == 2.0) ? v2 : (n == 3.0) ? v2 * v : (n == 4.0) ? v2 * v2 : 1.0;
+        if (n > 4.0) lpl += -0.5 * n * log(v);
+        const double qi = Q * is2 * iv;
+        lpl = fma(-0.5, qi, lpl);
+        slogbar += qi - n;
+        return iv * (-0.5 * n + is2 * (n * d + 0.5 * Q * iv));
+    }
+    const double qi = Q * is2;
+    lpl = fma(-0.5, qi, lpl);
+    slogbar += qi - n;
+    return n * d * is2;
+}
+
+// Optional generated-quantities sink of an evaluation = write_array (h:1705-2235; gp_grid.stan:234-299).
+// When on, the evaluation also emits one output row
+//   [constrained params | p0 | p01 | p02 | Delta | GP | ec50_1 ec50_2 | CPO[N] | dss_1 dss_2 |
+//    rVUS_f rVUS_p0 VUS_Delta VUS_syn VUS_ant]            (nointeraction: without Delta, GP, last three)
+// and/or the generated scalars (qout) and the per-chain CPO accumulator.  Keeping this inside the ONE
+// evaluation function (instead of a second forward pass) keeps a single copy of the model code in the
+// sampler kernel -- its instruction footprint is what bounds the sampler (profiles/).
+struct GQ {
+    bool on;
+    int D;                    // number of unconstrained parameters of this problem
+    const double *yglob;      // y[N] in original order (global memory)
+    const int *iiglob;        // 0-based f index of every observation, original order
+    double uz[4];             // U(0,1) draws for the zero-VUS replacement (gp_grid.stan:294-297)
+    double *row, *qout, *cpo_acc;
+};
+
 // ---------------------------------------------------------------------------------------------------
 // lp(u) and d lp / d u for one (problem, point), cooperatively on one warp.
 // q / g are in lane layout.  Returns false where the reference would throw (reject): lp/g undefined.
@@ -316,7 +359,7 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
 template <int CPL, bool DBG>
 __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, const int ws, const int (&cell)[CPL],
                                                const WVec<CPL> &q, const int jacobian, double &lp_out, WVec<CPL> &g,
-                                               double *dbg)
+                                               double *dbg, const GQ &gq)
 {
     using C = Cfg<CPL>;
     constexpr int NM = C::NM;
@@ -337,6 +380,11 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     const double u = q.s;
     double e;
     const double thv = constrain_slot(F, u, ws + C::OFF_TH, ws + C::OFF_UR, e);
+    const int npre = 2 * F.est_la + 6 + (gp ? 4 + F.est_alpha : 0);
+    if (gq.on && gq.row && act) {   // constrained parameters in declaration order
+        const int pos = (lane < SL_M1) ? lane : (lane <= SL_ALPHA) ? lane - (F.est_la ? 0 : 2) : gq.D - 3 + (lane - SL_S);
+        gq.row[pos] = thv;
+    }
     double lpl = 0.0;   // lane-local part of lp
     double tb = 0.0;    // d lp / d(constrained scalar of this lane)
     {
@@ -411,43 +459,115 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     const double is2 = fast_rcp(s * s);
     const double b1 = th[SL_B1], b2 = th[SL_B2];
     double b1bar = 0.0, b2bar = 0.0, slogbar = 0.0, vprod = 1.0;
+    // generated quantities (only when gq.on): output offsets, VUS accumulators, f on its (n2+1) x (n1+1) grid
+    const int G = P.G;
+    const int o_p0 = gq.D, o_p01 = o_p0 + G, o_delta = o_p01 + nm, o_gp = o_delta + G;
+    const int o_ec = gp ? o_gp + G : o_delta, o_cpo = o_ec + 2, o_dss = o_cpo + P.N, o_vus = o_dss + 2;
+    double *const fg = Lb1;   // (n2+1)(n1+1) <= 2 NN doubles: spans Lb1..Lb2, both free until the adjoint products
+    double vus[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int t = 0; t < CPL; ++t) {
-        if (cell[t] >> 16) {
-            const int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
-            const double p0 = pm[j] * pm[n1 + i], q0 = 1.0 - p0;
-            double f = p0, dfdG = 0.0, dfdb1 = 0.0, dfdb2 = 0.0, dfdp0 = 1.0;
-            ok = ok && (p0 >= 0.0) && (p0 <= 1.0);
-            if (gp) {
-                const double B = Gv[t];
-                const double e1 = fast_exp(b1 * B), e2 = fast_exp(-b2 * B);
-                const double iD1 = fast_rcp(fma(p0, e1, q0)), iD2 = fast_rcp(fma(q0, e2, p0));
-                const double t1 = q0 * iD1, u1 = p0 * e1 * iD1, t2 = p0 * iD2, u2 = q0 * e2 * iD2;
-                const double Delta = q0 * t2 - p0 * t1;
-                ok = ok && (Delta >= -1.0) && (Delta <= 1.0);
-                f = p0 + Delta;
-                const double w1 = p0 * t1 * u1, w2 = q0 * t2 * u2;
-                dfdG = w1 * b1 + w2 * b2;
-                dfdb1 = w1 * B;
-                dfdb2 = w2 * B;
-                dfdp0 = 1.0 - t1 - t2 + iD1 * u1 + iD2 * u2;
-                if (DBG) { dbg[2 * C::NN + lane + 32 * t] = B; dbg[2 * C::NN + C::GM + lane + 32 * t] = f; }
+        // no branch on cell validity: masked cells decode to (i, j) = (0, 0) and contribute exact zeros
+        const bool live = (cell[t] >> 16) & 1;
+        const int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
+        const double p0 = pm[j] * pm[n1 + i], q0 = 1.0 - p0;
+        double f = p0, dfdG = 0.0, dfdb1 = 0.0, dfdb2 = 0.0, dfdp0 = 1.0;
+        ok = ok && (p0 >= 0.0) && (p0 <= 1.0);
+        if (gp) {
+            const double B = Gv[t];
+            const double e1 = fast_exp(b1 * B), e2 = fast_exp(-b2 * B);
+            const double iD1 = fast_rcp(fma(p0, e1, q0)), iD2 = fast_rcp(fma(q0, e2, p0));
+            const double t1 = q0 * iD1, u1 = p0 * e1 * iD1, t2 = p0 * iD2, u2 = q0 * e2 * iD2;
+            const double Delta = q0 * t2 - p0 * t1;
+            ok = ok && (Delta >= -1.0) && (Delta <= 1.0);
+            f = p0 + Delta;
+            const double w1 = p0 * t1 * u1, w2 = q0 * t2 * u2;
+            dfdG = w1 * b1 + w2 * b2;
+            dfdb1 = w1 * B;
+            dfdb2 = w2 * B;
+            dfdp0 = 1.0 - t1 - t2 + iD1 * u1 + iD2 * u2;
+            if (DBG && live) { dbg[2 * C::NN + lane + 32 * t] = B; dbg[2 * C::NN + C::GM + lane + 32 * t] = f; }
+            if (gq.on && live) {
+                const double w = smem[P.vw + j] * smem[P.vw + n1 + i];
+                vus[2] = fma(w, Delta, vus[2]); vus[3] = fma(w, fmin(Delta, 0.0), vus[3]); vus[4] = fma(w, fmax(Delta, 0.0), vus[4]);
+                if (gq.row) { const int c = lane + 32 * t; gq.row[npre + c] = q.z[t]; gq.row[o_delta + c] = Delta; gq.row[o_gp + c] = B; }
             }
-            const int fc = (i + 1) + (j + 1) * (n2 + 1);
-            const double fbar = lik_cell(F, P, fc, f, s, is2, lpl, slogbar, vprod, ok);
-            if (gp) Gs[zoff<CPL>(cell[t])] = fbar * dfdG;   // Gbar, in place of G
-            b1bar = fma(fbar, dfdb1, b1bar);
-            b2bar = fma(fbar, dfdb2, b2bar);
-            Ws[lane + 32 * t] = fbar * dfdp0;   // p0bar, packed cell index i + j*n2
         }
+        const int fc = (i + 1) + (j + 1) * (n2 + 1);
+        if (gq.on && live) {
+            const double w = smem[P.vw + j] * smem[P.vw + n1 + i];
+            vus[0] = fma(w, 1.0 - f, vus[0]); vus[1] = fma(w, 1.0 - p0, vus[1]);
+            fg[fc] = f;
+            if (gq.row) gq.row[o_p0 + lane + 32 * t] = p0;
+        }
+        double fbar;
+        if (!F.robust) fbar = lik_cell_normal(F, P, fc, f, is2, live, lpl, slogbar, vprod, ok);
+        else fbar = live ? lik_cell(F, P, fc, f, s, is2, lpl, slogbar, vprod, ok) : 0.0;
+        if (gp && live) Gs[zoff<CPL>(cell[t])] = fbar * dfdG;   // Gbar, in place of G
+        b1bar = fma(fbar, dfdb1, b1bar);
+        b2bar = fma(fbar, dfdb2, b2bar);
+        if (live) Ws[lane + 32 * t] = fbar * dfdp0;   // p0bar, packed cell index i + j*n2
     }
     // boundary cells of f: f[0,a] = p01[a-1], f[b,0] = p02[b-1], f[0,0] = 1 (gp_grid.stan:170-172)
     double pmbar = 0.0;
     if (lane <= nm) {
         const int fc = lane < n1 ? (lane + 1) * (n2 + 1) : (lane < nm ? lane - n1 + 1 : 0);
         pmbar = lik_cell(F, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, vprod, ok);
+        if (gq.on) {
+            fg[fc] = lane < nm ? pmv : 1.0;
+            if (gq.row && lane < nm) gq.row[o_p01 + lane] = pmv;   // p01 then p02 are contiguous
+        }
     }
     if (F.het) lpl += -0.5 * log(vprod);
+    if (gq.on) {
+        __syncwarp();
+        const double vr = warp_sum8(vus);                       // lane L holds the total of vus[L & 7]
+        double v_f = __shfl_sync(FULL, vr, 0), v_p0 = __shfl_sync(FULL, vr, 1), v_d = __shfl_sync(FULL, vr, 2);
+        double v_syn = __shfl_sync(FULL, vr, 3), v_ant = __shfl_sync(FULL, vr, 4);
+        // CPO (always the Normal density, even when robust: gp_grid.stan:264-270)
+        if (gq.row || gq.cpo_acc) {
+            for (int n = lane; n < P.N; n += 32) {
+                const double fv = fg[gq.iiglob[n]];
+                const double sd = F.het ? s * sqrt(fv + F.lambda) : s;
+                const double r = (gq.yglob[n] - fv) / sd;
+                const double cpo = exp(BSYN_LOG_2PI_HALF + log(sd) + 0.5 * r * r);
+                if (gq.row) gq.row[o_cpo + n] = cpo;
+                if (gq.cpo_acc) gq.cpo_acc[n] += cpo;
+            }
+        }
+        // ec50, dss (include/dss.stan) on lanes 0 / 1
+        double ec = 0.0, ds = 0.0;
+        if (lane < 2) {
+            const int nn = lane ? n2 : n1;
+            const double *xx = smem + P.xs + (lane ? n1 : 0);
+            double c1 = xx[0], c2 = xx[0];
+            for (int k = 1; k < nn; ++k) { c1 = fmin(c1, xx[k]); c2 = fmax(c2, xx[k]); }
+            const double la = th[SL_LA1 + lane], sl = th[SL_SL1 + lane], mm = th[SL_M1 + lane];
+            ec = exp(BSYN_LN10 * mm);
+            const double val = (c2 - c1) + (la - 1.0) / sl * (log10(1.0 + exp(BSYN_LN10 * sl * (c2 - mm))) -
+                                                              log10(1.0 + exp(BSYN_LN10 * sl * (c1 - mm))));
+            ds = 100.0 * (1.0 - val / (c2 - c1));
+        }
+        const double ec2 = __shfl_sync(FULL, ec, 1), ds2 = __shfl_sync(FULL, ds, 1);
+        // zero-valued integrals are replaced by U(1e-6,1e-4) draws (gp_grid.stan:294-297)
+        if (v_f == 0.0) v_f = 1e-6 + (1e-4 - 1e-6) * gq.uz[0];
+        if (v_p0 == 0.0) v_p0 = 1e-6 + (1e-4 - 1e-6) * gq.uz[1];
+        if (gp) {
+            if (v_syn == 0.0) v_syn = 1e-6 + (1e-4 - 1e-6) * gq.uz[2];
+            if (v_ant == 0.0) v_ant = 1e-6 + (1e-4 - 1e-6) * gq.uz[3];
+        }
+        if (lane == 0) {
+            if (gq.row) {
+                gq.row[o_ec] = ec; gq.row[o_ec + 1] = ec2; gq.row[o_dss] = ds; gq.row[o_dss + 1] = ds2;
+                gq.row[o_vus] = v_f; gq.row[o_vus + 1] = v_p0;
+                if (gp) { gq.row[o_vus + 2] = v_d; gq.row[o_vus + 3] = v_syn; gq.row[o_vus + 4] = v_ant; }
+            }
+            if (gq.qout) {
+                gq.qout[0] = ec; gq.qout[1] = ec2; gq.qout[2] = ds; gq.qout[3] = ds2; gq.qout[4] = s;
+                gq.qout[5] = v_f; gq.qout[6] = v_p0; gq.qout[7] = v_d; gq.qout[8] = v_syn; gq.qout[9] = v_ant;
+            }
+        }
+    }
     __syncwarp();
     // ---- 7. adjoints of the monotherapy curves: 6 sums delivered to their owner lanes by one butterfly ----
     {
@@ -556,6 +676,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         //   = sum_{a>b} Xfull[a,b] * dcov[a,b] + 1/2 sum_a Xfull[a,a] * dcov[a,a]
         const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA], iell = fast_rcp(th[SL_ELL]);
         const int P1 = P.P1, Pn = P.P1 + P.P2;
+#pragma unroll 3
         for (int e0 = lane; e0 < Pn; e0 += 32) {
             const bool m1 = e0 < P1;
             const int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
@@ -592,141 +713,6 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     }
     lp_out = lp;
     ok = ok && (lp == lp);
-    return __all_sync(FULL, ok);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// write_array (h:1705-2235; gp_grid.stan:234-299): one warp writes one output row
-//   [constrained params | p0 | p01 | p02 | Delta | GP | ec50_1 ec50_2 | CPO[N] | dss_1 dss_2 |
-//    rVUS_f rVUS_p0 VUS_Delta VUS_syn VUS_ant]            (nointeraction: without Delta, GP, last three)
-// `row` may be NULL (screen path); qout[BSYN_NQ-ish] receives the generated scalars (lane 0 writes);
-// cpo_acc (may be NULL): per-chain accumulator of CPO_n, added to.
-// yglob/iiglob: this problem's y[N], ii0[N] in original order (global memory).
-template <int CPL>
-__device__ __forceinline__ bool warp_write_array(const Flags &F, const ProbS &P, const ProbDesc &pd, const int ws,
-                                              const int (&cell)[CPL], const WVec<CPL> &q, const double *yglob,
-                                              const int *iiglob, double u_zero_fix[4], double *row, double *qout,
-                                              double *cpo_acc)
-{
-    using C = Cfg<CPL>;
-    const int lane = threadIdx.x & 31;
-    const int n1 = P.n1, n2 = P.n2, nm = n1 + n2, G = P.G;
-    double *const th = smem + ws + C::OFF_TH, *const pm = smem + ws + C::OFF_PM;
-    double *const M2 = smem + ws + C::OFF_LB1;  // f grid: (n2+1)(n1+1) <= (NM+1)^2 <= 2 NN doubles, spans Lb1..Lb2
-    const bool gp = (F.model == 0);
-    __syncwarp();
-    double e;
-    const double thv = constrain_slot(F, q.s, ws + C::OFF_TH, ws + C::OFF_UR, e);
-    double Gv[CPL];
-    bool ok = true;
-    if (gp) ok = gp_forward<CPL>(F, P, ws, cell, q.z, Gv);
-    double pmv = 0.0;
-    if (lane < nm) {
-        const bool d1 = lane < n1;
-        const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2], lam = th[d1 ? SL_LA1 : SL_LA2];
-        const double Em = fast_exp(BSYN_LN10 * sl * (smem[P.xs + lane] - mm));
-        pmv = fma(1.0 - lam, fast_rcp(1.0 + Em), lam);
-        pm[lane] = pmv;
-        ok = ok && (pmv >= 0.0) && (pmv <= 1.0);
-    }
-    __syncwarp();
-    // output offsets
-    const int npre = 2 * F.est_la + 6 + (gp ? 4 + F.est_alpha : 0);
-    const int D = pd.D;
-    const int o_p0 = D, o_p01 = o_p0 + G, o_p02 = o_p01 + n1;
-    const int o_delta = o_p02 + n2, o_gp = o_delta + G;
-    const int o_ec = gp ? o_gp + G : o_p02 + n2;
-    const int o_cpo = o_ec + 2, o_dss = o_cpo + P.N, o_vus = o_dss + 2;
-    // constrained parameters in declaration order
-    if (row && lane < 16 && ((F.active_mask >> lane) & 1u)) {
-        int pos;
-        if (lane < SL_M1) pos = lane;
-        else if (lane <= SL_ALPHA) pos = lane - (F.est_la ? 0 : 2);
-        else pos = D - 3 + (lane - SL_S);
-        if (!gp && lane >= SL_B1 && lane <= SL_ALPHA) pos = -1;
-        if (pos >= 0) row[pos] = thv;
-    }
-    const double b1 = th[SL_B1], b2 = th[SL_B2], s = th[SL_S];
-    double v_f = 0.0, v_p0 = 0.0, v_d = 0.0, v_syn = 0.0, v_ant = 0.0;
-    const int ld = n2 + 1;
-    double *fg = M2;   // f on the (n2+1) x (n1+1) grid, column-major
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) {
-        if (cell[t] >> 16) {
-            const int c = lane + 32 * t;
-            const int i = cell[t] & 255, j = (cell[t] >> 8) & 255;
-            const double p0 = pm[j] * pm[n1 + i], q0 = 1.0 - p0;
-            ok = ok && (p0 >= 0.0) && (p0 <= 1.0);
-            double Delta = 0.0;
-            if (gp) {
-                const double B = Gv[t];
-                const double e1 = fast_exp(b1 * B), e2 = fast_exp(-b2 * B);
-                Delta = q0 * (p0 * fast_rcp(fma(q0, e2, p0))) - p0 * (q0 * fast_rcp(fma(p0, e1, q0)));
-                ok = ok && (Delta >= -1.0) && (Delta <= 1.0);
-                if (row) { row[npre + c] = q.z[t]; row[o_delta + c] = Delta; row[o_gp + c] = B; }
-            }
-            if (row) row[o_p0 + c] = p0;
-            const double f = p0 + Delta;
-            fg[(i + 1) + (j + 1) * ld] = f;
-            const double w = smem[P.vw + j] * smem[P.vw + n1 + i];
-            v_f = fma(w, 1.0 - f, v_f);
-            v_p0 = fma(w, 1.0 - p0, v_p0);
-            v_d = fma(w, Delta, v_d);
-            v_syn = fma(w, fmin(Delta, 0.0), v_syn);
-            v_ant = fma(w, fmax(Delta, 0.0), v_ant);
-        }
-    }
-    if (lane <= nm) {
-        const int fc = lane < n1 ? (lane + 1) * ld : (lane < nm ? lane - n1 + 1 : 0);
-        fg[fc] = lane < nm ? pmv : 1.0;
-        if (row && lane < nm) row[o_p01 + lane] = pmv;   // p01 then p02 are contiguous
-    }
-    __syncwarp();
-    v_f = warp_sum(v_f); v_p0 = warp_sum(v_p0);
-    if (gp) { v_d = warp_sum(v_d); v_syn = warp_sum(v_syn); v_ant = warp_sum(v_ant); }
-    // CPO (always the Normal density, even when robust: gp_grid.stan:264-270)
-    if (row || cpo_acc) {
-        for (int n = lane; n < P.N; n += 32) {
-            const double f = fg[iiglob[n]];
-            const double sd = F.het ? s * sqrt(f + F.lambda) : s;
-            const double r = (yglob[n] - f) / sd;
-            const double cpo = fast_exp(BSYN_LOG_2PI_HALF + log(sd) + 0.5 * r * r);
-            if (row) row[o_cpo + n] = cpo;
-            if (cpo_acc) cpo_acc[n] += cpo;
-        }
-    }
-    // ec50, dss (include/dss.stan) on lanes 0/1
-    double ec = 0.0, ds = 0.0;
-    if (lane < 2) {
-        const int n = lane ? n2 : n1;
-        const double *x = smem + P.xs + (lane ? n1 : 0);
-        double c1 = x[0], c2 = x[0];
-        for (int k = 1; k < n; ++k) { c1 = fmin(c1, x[k]); c2 = fmax(c2, x[k]); }
-        const double la = th[SL_LA1 + lane], sl = th[SL_SL1 + lane], mm = th[SL_M1 + lane];
-        ec = fast_exp(BSYN_LN10 * mm);
-        const double val = (c2 - c1) + (la - 1.0) / sl * (log10(1.0 + fast_exp(BSYN_LN10 * sl * (c2 - mm))) -
-                                                          log10(1.0 + fast_exp(BSYN_LN10 * sl * (c1 - mm))));
-        ds = 100.0 * (1.0 - val / (c2 - c1));
-    }
-    const double ec2 = __shfl_sync(FULL, ec, 1), ds2 = __shfl_sync(FULL, ds, 1);
-    // zero-valued integrals are replaced by U(1e-6,1e-4) draws (gp_grid.stan:294-297)
-    if (v_f == 0.0) v_f = 1e-6 + (1e-4 - 1e-6) * u_zero_fix[0];
-    if (v_p0 == 0.0) v_p0 = 1e-6 + (1e-4 - 1e-6) * u_zero_fix[1];
-    if (gp) {
-        if (v_syn == 0.0) v_syn = 1e-6 + (1e-4 - 1e-6) * u_zero_fix[2];
-        if (v_ant == 0.0) v_ant = 1e-6 + (1e-4 - 1e-6) * u_zero_fix[3];
-    }
-    if (lane == 0) {
-        if (row) {
-            row[o_ec] = ec; row[o_ec + 1] = ec2; row[o_dss] = ds; row[o_dss + 1] = ds2;
-            row[o_vus] = v_f; row[o_vus + 1] = v_p0;
-            if (gp) { row[o_vus + 2] = v_d; row[o_vus + 3] = v_syn; row[o_vus + 4] = v_ant; }
-        }
-        if (qout) {
-            qout[0] = ec; qout[1] = ec2; qout[2] = ds; qout[3] = ds2; qout[4] = s;
-            qout[5] = v_f; qout[6] = v_p0; qout[7] = v_d; qout[8] = v_syn; qout[9] = v_ant;
-        }
-    }
     return __all_sync(FULL, ok);
 }
 
