@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbsyn.so")
+LIB_PATH = os.environ.get("BSYN_LIB", os.path.join(_HERE, "lib", "libbsyn.so"))   # BSYN_LIB: A/B builds
 
 BSYN_NQ = 12
 BSYN_NSP = 7

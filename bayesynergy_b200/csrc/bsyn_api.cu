@@ -479,11 +479,11 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     sp.qdraws = b->d_qdraws; sp.sp = b->d_sp; sp.chain_stats = b->d_chain_stats;
     sp.draws = ds.draws; sp.ld_draws = ds.ld_draws; sp.udraws = ds.udraws; sp.ld_u = ds.ld_u;
     sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im;
-    // warps per CTA: the largest compiled variant (11, 5, 1) whose shared memory fits on an SM
+    // warps per CTA: the largest compiled variant (12, 6, 4, 1) whose shared memory fits on an SM
     size_t bytes = 0;
     int nw = 0, per_sm = 0;
     const int want = getenv("BSYN_NUTS_NW") ? atoi(getenv("BSYN_NUTS_NW")) : 0;
-    for (int cand : {11, 5, 1}) {
+    for (int cand : {12, 6, 4, 1}) {
         if (want && cand != want) continue;
         sp.sl = make_layout(b, true, &bytes, cand);
         if (bytes > 227 * 1024) continue;

@@ -141,7 +141,7 @@ template <int CPL> struct VariantImpl {
         write_array_kernel<CPL><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, out, ldo, seed, status);
         return cudaGetLastError();
     }
-    // sampler instantiations: (warps per CTA, min CTAs per SM): 11 x 1 (all warps of an SM in step), 5 x 2, 1 x 11
+    // sampler instantiations <warps per CTA, register cap>: 12 warps per SM as 1 x 12, 2 x 6, 3 x 4 or 12 x 1 CTAs
     template <int NW, int MINB>
     static cudaError_t nuts_launch(int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                                    const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
@@ -158,15 +158,17 @@ template <int CPL> struct VariantImpl {
     static cudaError_t nuts(int nw, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                             const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
     {
-        if (nw == 11) return nuts_launch<11, 1>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        if (nw == 5) return nuts_launch<5, 2>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        return nuts_launch<1, 11>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        if (nw == 12) return nuts_launch<12, 168>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        if (nw == 6) return nuts_launch<6, 168>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        if (nw == 4) return nuts_launch<4, 168>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        return nuts_launch<1, 168>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
     }
     static cudaError_t nuts_occupancy(int nw, size_t bytes, int *per_sm)
     {
-        if (nw == 11) return nuts_occ<11, 1>(bytes, per_sm);
-        if (nw == 5) return nuts_occ<5, 2>(bytes, per_sm);
-        return nuts_occ<1, 11>(bytes, per_sm);
+        if (nw == 12) return nuts_occ<12, 168>(bytes, per_sm);
+        if (nw == 6) return nuts_occ<6, 168>(bytes, per_sm);
+        if (nw == 4) return nuts_occ<4, 168>(bytes, per_sm);
+        return nuts_occ<1, 168>(bytes, per_sm);
     }
     static const VariantOps *ops()
     {

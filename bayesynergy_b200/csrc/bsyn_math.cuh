@@ -12,6 +12,53 @@
 
 namespace bsyn {
 
+// Polynomial coefficients and range-reduction constants live in constant memory so that they are DFMA
+// operands (c[bank][off]) instead of 64-bit immediates, each of which costs two UMOVs at every use.
+static __constant__ double c_exp[16] = {
+    2.51100376175620502e-08, 2.76326396541237579e-07, 2.75572409185476252e-06, 2.48014854822877313e-05,
+    1.98412698900471429e-04, 1.38888889523148119e-03, 8.33333333331960115e-03, 4.16666666664880919e-02,
+    1.66666666666666796e-01, 5.00000000000001887e-01,
+    1.4426950408889634074,          // [10] log2(e)
+    6755399441055744.0,             // [11] 1.5 * 2^52
+    -6.93147180369123816490e-01,    // [12] -ln2 hi
+    -1.90821492927058770002e-10,    // [13] -ln2 lo
+    709.0, -708.0};
+
+// Library log / exp / log10 for rarely executed paths (LPTN tails, > 4 replicates per cell, generated
+// quantities): out of line, so that their ~100-instruction bodies are not replicated at every inlined site.
+static __device__ __noinline__ double cold_log(double x) { return log(x); }
+static __device__ __noinline__ double cold_exp(double x) { return exp(x); }
+
+// log(x) for normal positive x (the algorithm of fdlibm's e_log.c: x = 2^k (1+f), s = f/(2+f),
+// log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)), R = degree-7 Remez polynomial; Lg1..Lg7 are its published
+// coefficients).  No denormal / zero / negative handling: callers pass products of (f + lambda) >= lambda^n
+// or 1 + positive.  Error < 1 ulp.
+static __constant__ double c_log[10] = {
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
+    6.93147180369123816490e-01,   // [7] ln2 hi
+    1.90821492927058770002e-10,   // [8] ln2 lo
+    1.41421356237309504880};      // [9] sqrt(2)
+
+__device__ __forceinline__ double fast_rcp(double d);   // below
+
+__device__ __forceinline__ double fast_log(double x)
+{
+    int hi = __double2hiint(x);
+    int k = (hi >> 20) - 1023;
+    double mnt = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
+    if (mnt > c_log[9]) { mnt *= 0.5; ++k; }
+    const double f = mnt - 1.0;
+    const double s = f * fast_rcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, c_log[5], c_log[3]), c_log[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, c_log[6], c_log[4]), c_log[2]), c_log[0]);
+    const double R = t1 + t2;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return fma(dk, c_log[7], f - (hfsq - fma(s, hfsq + R, dk * c_log[8])));
+}
+
 __device__ __forceinline__ double fast_rcp(double d)
 {
     double x;
@@ -44,22 +91,15 @@ __device__ __forceinline__ double fast_rsqrt(double d)
 // 8e307 for inf -- both only feed 1/(1+E)-type expressions here); NaN propagates.
 __device__ __forceinline__ double fast_exp(double x)
 {
-    const double xc = fmax(fmin(x, 709.0), -708.0);
-    const double magic = 6755399441055744.0;   // 1.5 * 2^52: (t + magic) - magic rounds t to an integer
-    const double tm = fma(xc, 1.4426950408889634074, magic);
+    const double xc = fmax(fmin(x, c_exp[14]), c_exp[15]);
+    const double magic = c_exp[11];            // (t + magic) - magic rounds t to an integer
+    const double tm = fma(xc, c_exp[10], magic);
     const double t = tm - magic;
-    double r = fma(t, -6.93147180369123816490e-01, xc);   // ln2 hi
-    r = fma(t, -1.90821492927058770002e-10, r);           // ln2 lo
-    double p = 2.51100376175620502e-08;
-    p = fma(p, r, 2.76326396541237579e-07);
-    p = fma(p, r, 2.75572409185476252e-06);
-    p = fma(p, r, 2.48014854822877313e-05);
-    p = fma(p, r, 1.98412698900471429e-04);
-    p = fma(p, r, 1.38888889523148119e-03);
-    p = fma(p, r, 8.33333333331960115e-03);
-    p = fma(p, r, 4.16666666664880919e-02);
-    p = fma(p, r, 1.66666666666666796e-01);
-    p = fma(p, r, 5.00000000000001887e-01);
+    double r = fma(t, c_exp[12], xc);
+    r = fma(t, c_exp[13], r);
+    double p = c_exp[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) p = fma(p, r, c_exp[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const int k = __double2loint(tm);           // the integer t (low word of t + magic)

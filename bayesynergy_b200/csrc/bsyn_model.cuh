@@ -270,7 +270,7 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
             const double v2 = v * v;
             vprod *= (n == 1.0) ? v : (n == 2.0) ? v2 : (n == 3.0) ? v2 * v : v2 * v2;
         } else {
-            lpl += -0.5 * n * log(v);
+            lpl += -0.5 * n * cold_log(v);
         }
     }
     if (!F.robust) {
@@ -299,8 +299,8 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
                 dl = -r;
             } else {
                 const double az = fmax(ar, 1.0001);
-                const double la = log(az);
-                lpl += F.lptn_c0 - la - (F.lamL + 1.0) * log(la);
+                const double la = cold_log(az);
+                lpl += F.lptn_c0 - la - (F.lamL + 1.0) * cold_log(la);
                 dl = (ar > 1.0001) ? -copysign(1.0, r) * fast_rcp(az) * (1.0 + (F.lamL + 1.0) * fast_rcp(la)) : 0.0;
             }
             fbar += dl * (-isd - 0.5 * r * iv);
@@ -324,7 +324,7 @@ __device__ __forceinline__ double lik_cell_normal(const Flags &F, const ProbS &P
         const double iv = fast_rcp(v);
         const double v2 = v * v;
         vprod *= (n == 0.0) ? 1.0 : (n == 1.0) ? v : (n == 2.0) ? v2 : (n == 3.0) ? v2 * v : (n == 4.0) ? v2 * v2 : 1.0;
-        if (n > 4.0) lpl += -0.5 * n * log(v);
+        if (n > 4.0) lpl += -0.5 * n * cold_log(v);
         const double qi = Q * is2 * iv;
         lpl = fma(-0.5, qi, lpl);
         slogbar += qi - n;
@@ -390,7 +390,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     {
         // one log1p and one reciprocal for all lanes (lane-specific arguments); the per-slot branches below
         // then contain only a handful of multiply-adds each
-        const double l1 = log1p(is_la ? e : (lane == SL_S ? thv * thv : 0.0));
+        const double l1 = fast_log(1.0 + (is_la ? e : (lane == SL_S ? thv * thv : 0.0)));   // log1p, abs err 1e-16
         const double ie = fast_rcp(is_la ? (1.0 - thv) : (lane == SL_S ? fma(thv, thv, 1.0) : thv));
         double *const ith = smem + ws + C::OFF_ITH;
         if (lane < 16) ith[lane] = ie;
@@ -518,7 +518,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
             if (gq.row && lane < nm) gq.row[o_p01 + lane] = pmv;   // p01 then p02 are contiguous
         }
     }
-    if (F.het) lpl += -0.5 * log(vprod);
+    if (F.het) lpl += -0.5 * fast_log(vprod);
     if (gq.on) {
         __syncwarp();
         const double vr = warp_sum8(vus);                       // lane L holds the total of vus[L & 7]
@@ -530,7 +530,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
                 const double fv = fg[gq.iiglob[n]];
                 const double sd = F.het ? s * sqrt(fv + F.lambda) : s;
                 const double r = (gq.yglob[n] - fv) / sd;
-                const double cpo = exp(BSYN_LOG_2PI_HALF + log(sd) + 0.5 * r * r);
+                const double cpo = cold_exp(BSYN_LOG_2PI_HALF + cold_log(sd) + 0.5 * r * r);
                 if (gq.row) gq.row[o_cpo + n] = cpo;
                 if (gq.cpo_acc) gq.cpo_acc[n] += cpo;
             }
@@ -543,9 +543,9 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
             double c1 = xx[0], c2 = xx[0];
             for (int k = 1; k < nn; ++k) { c1 = fmin(c1, xx[k]); c2 = fmax(c2, xx[k]); }
             const double la = th[SL_LA1 + lane], sl = th[SL_SL1 + lane], mm = th[SL_M1 + lane];
-            ec = exp(BSYN_LN10 * mm);
-            const double val = (c2 - c1) + (la - 1.0) / sl * (log10(1.0 + exp(BSYN_LN10 * sl * (c2 - mm))) -
-                                                              log10(1.0 + exp(BSYN_LN10 * sl * (c1 - mm))));
+            ec = cold_exp(BSYN_LN10 * mm);
+            const double val = (c2 - c1) + (la - 1.0) / sl * (cold_log(1.0 + cold_exp(BSYN_LN10 * sl * (c2 - mm))) -
+                                                              cold_log(1.0 + cold_exp(BSYN_LN10 * sl * (c1 - mm)))) * (1.0 / BSYN_LN10);
             ds = 100.0 * (1.0 - val / (c2 - c1));
         }
         const double ec2 = __shfl_sync(FULL, ec, 1), ds2 = __shfl_sync(FULL, ds, 1);

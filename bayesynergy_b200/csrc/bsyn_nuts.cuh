@@ -181,7 +181,7 @@ enum Phase { PH_FETCH = 0, PH_INIT, PH_ISTEP, PH_TREE, PH_GQ, PH_DONE };
 enum Next { N_NONE = 0, N_ENDTRANS, N_ITER, N_TRANS, N_DOUBLE };
 
 template <int CPL, int NW, int MINB>
-__global__ void __launch_bounds__(32 * NW, MINB) nuts_kernel(const Flags F, const ProbDesc *__restrict__ descs,
+__global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const Flags F, const ProbDesc *__restrict__ descs,
                                                          const double *__restrict__ dpool, const int *__restrict__ ipool,
                                                          const int *__restrict__ tri_tab, const SamplerParams sp)
 {

@@ -22,6 +22,12 @@ def main():
     sds = [prepare(*synthetic_experiment(k)) for k in range(n_prob)]
     b = _lib.Batch(sds)
     D = b.max_params
+    if os.environ.get("QB_NUTS_ONLY"):
+        for (it, wu) in ((int(os.environ.get("QB_ITER", "200")), int(os.environ.get("QB_ITER", "200")) // 2),):
+            ng, ms = b.sample_device(chains=4, iter=it, warmup=wu, seed=1)
+            print(f"NUTS {n_prob} combos x 4 chains, iter={it} warmup={wu}: {ng} grad evals, kernel {ms:.1f} ms, "
+                  f"{ng/ms*1e3:.3e} evals/s ({ng/ms*1e3*27824/pk.value:.3f} of FP64 peak)", flush=True)
+        return
     rng = np.random.default_rng(0)
     B = 400_000
     U = rng.uniform(-1, 1, size=(B, D))
