@@ -100,7 +100,8 @@ __device__ __forceinline__ double log_add_exp(double a, double b)
 {
     if (a == -INFINITY) return b;
     if (b == -INFINITY) return a;
-    return a > b ? a + log1p(exp(b - a)) : b + log1p(exp(a - b));
+    const double hi = fmax(a, b), d = -fabs(a - b);
+    return hi + fast_log(1.0 + fast_exp(d));   // fast_exp clamps d at -708: exp(d) = 3e-308 ~ 0
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     double lsw = 0.0, summetro = 0.0, lsw_sub = 0.0;
     int curdir = 1, depth = 0, nleap = 0, k = 0, nleaf = 1;
     bool divergent = false;
-    uint32_t rctr = 0;
+    double u_leaf = 0.5;
     TransInfo info{};
     const double *yglob = nullptr;
     const int *iiglob = nullptr;
@@ -403,12 +404,18 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             const double w = H0 - h;
             if (h - H0 > 1000.0) divergent = true;
             lsw_sub = log_add_exp(lsw_sub, w);
-            summetro += (w > 0.0) ? 1.0 : exp(w);
+            summetro += (w > 0.0) ? 1.0 : fast_exp(w);
             bool valid = !divergent;
             if (valid) {
-                // uniform progressive sampling of the subtree's proposal
+                // uniform progressive sampling of the subtree's proposal.  ONE uniform per subtree is recycled:
+                // after a Bernoulli(pr) decision taken as (u < pr), u/pr resp. (u-pr)/(1-pr) is again U(0,1).
                 bool take = (k == 0);
-                if (!take) take = rng_warp_uniform(rk, RT_LEAF, it, rctr++) < exp(w - lsw_sub);
+                if (!take) {
+                    const double pr = fast_exp(w - lsw_sub);
+                    take = u_leaf < pr;
+                    u_leaf = take ? u_leaf * fast_rcp(pr) : (u_leaf - pr) * fast_rcp(1.0 - pr);
+                    u_leaf = fmin(fmax(u_leaf, 0.0), 1.0);
+                }
                 if (take) {
                     vstore<CPL>(A + A_PQ * VS, q); vstore<CPL>(A + A_PG * VS, g);
                     proposeV = V; proposeH = h;
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 // ---- subtree complete: multinomial sample across subtrees (biased progressive sampling) ----
                 ++depth;
                 bool take = lsw_sub > lsw;
-                if (!take) take = rng_warp_uniform(rk, RT_TOP, it, depth) < exp(lsw_sub - lsw);
+                if (!take) take = rng_warp_uniform(rk, RT_TOP, it, depth) < fast_exp(lsw_sub - lsw);
                 if (take) {
                     vcopy<CPL>(A + A_SQ * VS, A + A_PQ * VS); vcopy<CPL>(A + A_SG * VS, A + A_PG * VS);
                     sampleV = proposeV; sampleH = proposeH;
@@ -632,12 +639,14 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             vstore<CPL>(A + A_SQ * VS, q); vstore<CPL>(A + A_SG * VS, g);
             vstore<CPL>(A + A_RHO_OLD * VS, p);
             otherV = V; sampleV = V; sampleH = H0; proposeV = V; proposeH = H0;
-            curdir = 1; lsw = 0.0; summetro = 0.0; depth = 0; nleap = 0; divergent = false; rctr = 0;
+            curdir = 1; lsw = 0.0; summetro = 0.0; depth = 0; nleap = 0; divergent = false;
             next = N_DOUBLE;
         }
         if (next == N_DOUBLE) {
             // ---- extend the trajectory by a subtree of 2^depth leapfrogs in a random direction ----
-            const int dir = rng_warp_uniform(rk, RT_DIR, it, depth) > 0.5 ? 1 : -1;
+            double u_dir;
+            rng_u2(rk, RT_DIR, 0xFFu, it, depth, u_dir, u_leaf);   // direction + this subtree's sampling uniform
+            const int dir = u_dir > 0.5 ? 1 : -1;
             if (dir != curdir) {   // make the end being extended the register-resident one
                 WVec<CPL> tv;
                 vload<CPL>(A + A_OQ * VS, tv); vstore<CPL>(A + A_OQ * VS, q); q = tv;
