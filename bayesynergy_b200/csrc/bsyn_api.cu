@@ -267,8 +267,16 @@ extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const 
     CK(cudaMalloc(&b->d_gradctr, sizeof(unsigned long long)));
     CK(cudaMalloc(&b->d_workctr, sizeof(int)));
     CK(cudaMemcpy(b->d_descs, b->descs.data(), sizeof(ProbDesc) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(b->d_dpool, dpool.data(), sizeof(double) * dpool.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(b->d_ipool, ipool.data(), sizeof(int) * ipool.size(), cudaMemcpyHostToDevice));
+    // the packed pools are pinned for the upload (page-locked DMA straight from the staging vectors)
+    const bool pin_d = cudaHostRegister(dpool.data(), sizeof(double) * dpool.size(), cudaHostRegisterDefault) == cudaSuccess;
+    const bool pin_i = cudaHostRegister(ipool.data(), sizeof(int) * ipool.size(), cudaHostRegisterDefault) == cudaSuccess;
+    cudaGetLastError();
+    cudaError_t ce = cudaMemcpyAsync(b->d_dpool, dpool.data(), sizeof(double) * dpool.size(), cudaMemcpyHostToDevice, b->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(b->d_ipool, ipool.data(), sizeof(int) * ipool.size(), cudaMemcpyHostToDevice, b->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
+    if (pin_d) cudaHostUnregister(dpool.data());
+    if (pin_i) cudaHostUnregister(ipool.data());
+    if (ce != cudaSuccess) { g_err = std::string("upload of the problem pools: ") + cudaGetErrorString(ce); return BSYN_ERR_CUDA; }
     CK(cudaMemcpy(b->d_tri, tri.data(), sizeof(int) * tri.size(), cudaMemcpyHostToDevice));
     *out = b;
     return BSYN_OK;
