@@ -45,9 +45,10 @@ def _sampler_kwargs(control, chains, iter, warmup, thin, seed):
              adapt_t0="adapt_t0", adapt_init_buffer="adapt_init_buffer", adapt_term_buffer="adapt_term_buffer",
              adapt_window="adapt_window")
     for k, v in control.items():
-        if k == "metric":
-            # dense_e is what the reference asks for when robust=TRUE; the device sampler currently adapts a
-            # diagonal metric only (DESIGN.md "out of scope / next"), so dense_e is mapped to diag_e.
+        if k == "metric":       # "diag_e" (default) or "dense_e" (the reference's choice when robust=TRUE)
+            if v not in ("diag_e", "dense_e"):
+                raise ValueError("control$metric must be 'diag_e' or 'dense_e'")
+            kw["metric"] = 1 if v == "dense_e" else 0
             continue
         if k not in m:
             raise ValueError(f"unknown control argument {k!r}")

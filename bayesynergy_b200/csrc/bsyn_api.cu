@@ -53,7 +53,8 @@ struct bsyn_batch {
     int num_sms = 0;
     // buffers of the last sampling call (device)
     double *d_qdraws = nullptr, *d_sp = nullptr, *d_summary = nullptr, *d_chain_stats = nullptr;
-    double *d_arena = nullptr;
+    double *d_arena = nullptr, *d_dense_L = nullptr, *d_dense_m2 = nullptr, *d_dense_mf = nullptr;
+    size_t dense_L_elems = 0, dense_m2_elems = 0, dense_mf_elems = 0;
     size_t qdraws_elems = 0, sp_elems = 0, arena_elems = 0, summary_elems = 0, cs_elems = 0;
     int last_chains = 0, last_nsave = 0, last_nskip = 0;
     unsigned long long *d_gradctr = nullptr;
@@ -287,7 +288,7 @@ extern "C" void bsyn_batch_destroy(bsyn_batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaFree(b->d_descs); cudaFree(b->d_dpool); cudaFree(b->d_ipool); cudaFree(b->d_tri);
-    cudaFree(b->d_qdraws); cudaFree(b->d_sp); cudaFree(b->d_summary); cudaFree(b->d_chain_stats); cudaFree(b->d_arena);
+    cudaFree(b->d_qdraws); cudaFree(b->d_sp); cudaFree(b->d_summary); cudaFree(b->d_chain_stats); cudaFree(b->d_arena); cudaFree(b->d_dense_L); cudaFree(b->d_dense_m2); cudaFree(b->d_dense_mf);
     cudaFree(b->d_gradctr); cudaFree(b->d_workctr);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -466,7 +467,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
 {
     if (a->chains < 1 || a->iter < 1 || a->warmup < 0 || a->warmup > a->iter || a->thin < 1 || a->max_treedepth < 1 || a->max_treedepth > 20)
         return fail(BSYN_ERR_ARG, "bsyn_sample: bad sampler arguments");
-    if (a->metric != 0) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample: metric = dense_e is not implemented yet (diag_e only)");
+    if (a->metric != 0 && a->metric != 1) return fail(BSYN_ERR_ARG, "bsyn_sample: metric must be 0 (diag_e) or 1 (dense_e)");
     CK(cudaSetDevice(b->device));
     SamplerParams sp{};
     sp.n_problems = b->n; sp.chains = a->chains;
@@ -476,7 +477,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     sp.init_r = a->init_r; sp.delta = a->adapt_delta; sp.stepsize0 = a->stepsize; sp.jitter = a->stepsize_jitter;
     sp.gamma = a->adapt_gamma; sp.kappa = a->adapt_kappa; sp.t0 = a->adapt_t0;
     sp.init_buffer = a->adapt_init_buffer; sp.term_buffer = a->adapt_term_buffer; sp.window = a->adapt_window;
-    sp.seed = a->seed; sp.jacobian = 1;
+    sp.seed = a->seed; sp.jacobian = 1; sp.metric = a->metric;
     const size_t nrows = (size_t)b->n * a->chains * sp.n_save;
     int rc;
     if ((rc = ensure(&b->d_qdraws, &b->qdraws_elems, nrows * BSYN_NQ))) return rc;
@@ -493,17 +494,26 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     const int want = getenv("BSYN_NUTS_NW") ? atoi(getenv("BSYN_NUTS_NW")) : 0;
     for (int cand : {12, 6, 4, 1}) {
         if (want && cand != want) continue;
+        if (a->metric == 1 && cand != 12 && cand != 4) continue;
         sp.sl = make_layout(b, true, &bytes, cand);
         if (bytes > 227 * 1024) continue;
-        if (variant(b->cpl)->nuts_occupancy(cand, bytes, &per_sm) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (variant(b->cpl)->nuts_occupancy(cand, a->metric, bytes, &per_sm) != cudaSuccess) { cudaGetLastError(); continue; }
         if (per_sm >= 1) { nw = cand; break; }
     }
     if (!nw) return fail(BSYN_ERR_UNSUPPORTED, "sampler kernel does not fit on an SM");
     const int n_items = b->n * a->chains;
     const int grid = std::max(1, std::min((n_items + nw - 1) / nw, per_sm * b->num_sms));
     const int VS = (b->cpl + 1) * 32;
-    sp.arena_stride = (long long)arena_vectors(a->max_treedepth) * VS;
+    sp.arena_stride = (long long)arena_vectors(a->max_treedepth) * VS * (a->metric == 1 ? 2 : 1);
     if ((rc = ensure(&b->d_arena, &b->arena_elems, (size_t)grid * nw * sp.arena_stride))) return rc;
+    if (a->metric == 1) {   // per resident warp: M^-1 (float), its Cholesky factor and the Welford accumulator (double)
+        const size_t DI = (size_t)VS, per = DI * DI, slots = (size_t)grid * nw;
+        sp.dense_stride = (long long)per;
+        if ((rc = ensure(&b->d_dense_L, &b->dense_L_elems, slots * per))) return rc;
+        if ((rc = ensure(&b->d_dense_m2, &b->dense_m2_elems, slots * per))) return rc;
+        if ((rc = ensure(&b->d_dense_mf, &b->dense_mf_elems, (slots * per + 1) / 2))) return rc;
+        sp.dense_L = b->d_dense_L; sp.dense_m2 = b->d_dense_m2; sp.dense_minv = reinterpret_cast<float *>(b->d_dense_mf);
+    }
     sp.arena = b->d_arena;
     sp.grad_counter = b->d_gradctr; sp.work_counter = b->d_workctr;
     CK(cudaMemsetAsync(b->d_gradctr, 0, sizeof(unsigned long long), b->stream));

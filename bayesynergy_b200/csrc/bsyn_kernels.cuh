@@ -141,34 +141,43 @@ template <int CPL> struct VariantImpl {
         write_array_kernel<CPL><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, out, ldo, seed, status);
         return cudaGetLastError();
     }
-    // sampler instantiations <warps per CTA, register cap>: 12 warps per SM as 1 x 12, 2 x 6, 3 x 4 or 12 x 1 CTAs
-    template <int NW, int MINB>
+    // sampler instantiations <warps per CTA, register cap, dense metric>: 12 warps per SM as 1 x 12, 2 x 6, 3 x 4 or
+    // 12 x 1 CTAs for diag_e; dense_e (robust models, R/bayesynergy.R:112-115) as 1 x 12
+    template <int NW, int MINB, bool DENSE>
     static cudaError_t nuts_launch(int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                                    const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
     {
-        nuts_kernel<CPL, NW, MINB><<<grid, 32 * NW, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
+        nuts_kernel<CPL, NW, MINB, DENSE><<<grid, 32 * NW, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
         return cudaGetLastError();
     }
-    template <int NW, int MINB> static cudaError_t nuts_occ(size_t bytes, int *per_sm)
+    template <int NW, int MINB, bool DENSE> static cudaError_t nuts_occ(size_t bytes, int *per_sm)
     {
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NW, MINB, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NW, MINB>, 32 * NW, bytes);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NW, MINB, DENSE>, 32 * NW, bytes);
     }
     static cudaError_t nuts(int nw, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                             const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
     {
-        if (nw == 12) return nuts_launch<12, 168>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        if (nw == 6) return nuts_launch<6, 168>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        if (nw == 4) return nuts_launch<4, 168>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        return nuts_launch<1, 168>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        if (sp.metric == 1) {
+            if (nw == 12) return nuts_launch<12, 168, true>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+            return nuts_launch<4, 168, true>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        }
+        if (nw == 12) return nuts_launch<12, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        if (nw == 6) return nuts_launch<6, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        if (nw == 4) return nuts_launch<4, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        return nuts_launch<1, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
     }
-    static cudaError_t nuts_occupancy(int nw, size_t bytes, int *per_sm)
+    static cudaError_t nuts_occupancy(int nw, int metric, size_t bytes, int *per_sm)
     {
-        if (nw == 12) return nuts_occ<12, 168>(bytes, per_sm);
-        if (nw == 6) return nuts_occ<6, 168>(bytes, per_sm);
-        if (nw == 4) return nuts_occ<4, 168>(bytes, per_sm);
-        return nuts_occ<1, 168>(bytes, per_sm);
+        if (metric == 1) {
+            if (nw == 12) return nuts_occ<12, 168, true>(bytes, per_sm);
+            return nuts_occ<4, 168, true>(bytes, per_sm);
+        }
+        if (nw == 12) return nuts_occ<12, 168, false>(bytes, per_sm);
+        if (nw == 6) return nuts_occ<6, 168, false>(bytes, per_sm);
+        if (nw == 4) return nuts_occ<4, 168, false>(bytes, per_sm);
+        return nuts_occ<1, 168, false>(bytes, per_sm);
     }
     static const VariantOps *ops()
     {

@@ -16,7 +16,7 @@ struct VariantOps {
                                int *status);
     cudaError_t (*nuts)(int nw, int grid, size_t smem_bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                         const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp);
-    cudaError_t (*nuts_occupancy)(int nw, size_t smem_bytes, int *per_sm);
+    cudaError_t (*nuts_occupancy)(int nw, int metric, size_t smem_bytes, int *per_sm);
 };
 
 }  // namespace bsyn

@@ -38,6 +38,10 @@ struct SamplerParams {
     double *chain_stats;
     double *inv_metric; int ld_im;
     double *cpo_acc; int ld_cpo;     // [n_problems][chains][ld_cpo]
+    // dense_e metric (metric == 1): per resident warp  M^-1 (float, column-major DI x DI),  its Cholesky factor
+    // (double, column-major lower) and the Welford cross-product accumulator (double)
+    int metric;
+    float *dense_minv; double *dense_L, *dense_m2; long long dense_stride;
     // work
     double *arena; long long arena_stride;
     unsigned long long *grad_counter;
@@ -46,7 +50,7 @@ struct SamplerParams {
 };
 
 enum ArenaSlot {
-    A_OQ = 0, A_OP, A_OG, A_SQ, A_SG, A_PQ, A_PG, A_RHO_OLD, A_P_OLD_NEAR, A_P_NEW_NEAR, A_WM, A_WM2, A_LVL
+    A_OQ = 0, A_OP, A_OG, A_SQ, A_SG, A_PQ, A_PG, A_RHO_OLD, A_P_OLD_NEAR, A_P_NEW_NEAR, A_WM, A_WM2, A_PREV, A_LVL
 };
 __host__ __device__ inline int arena_vectors(int max_depth) { return A_LVL + 3 * (max_depth > 2 ? max_depth - 1 : 1); }
 
@@ -95,6 +99,30 @@ __device__ __forceinline__ bool uturn_ok(const WVec<CPL> &m, const WVec<CPL> &a,
         sb += __shfl_xor_sync(FULL, sb, o);
     }
     return sa > 0.0 && sb > 0.0;
+}
+// compute_criterion with the sharp momenta given explicitly (p_sharp = M^-1 p): a_sharp . rho > 0 && b_sharp . rho > 0
+template <int CPL>
+__device__ __forceinline__ bool uturn_sharp_ok(const WVec<CPL> &as, const WVec<CPL> &bs, const WVec<CPL> &r)
+{
+    double sa = as.s * r.s, sb = bs.s * r.s;
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+        sa = fma(as.z[t], r.z[t], sa);
+        sb = fma(bs.z[t], r.z[t], sb);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(FULL, sa, o);
+        sb += __shfl_xor_sync(FULL, sb, o);
+    }
+    return sa > 0.0 && sb > 0.0;
+}
+template <int CPL> __device__ __forceinline__ double vdot2(const WVec<CPL> &a, const WVec<CPL> &b)
+{
+    double s = a.s * b.s;
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) s = fma(a.z[t], b.z[t], s);
+    return warp_sum(s);
 }
 __device__ __forceinline__ double log_add_exp(double a, double b)
 {
@@ -181,7 +209,7 @@ struct TransInfo {
 enum Phase { PH_FETCH = 0, PH_INIT, PH_ISTEP, PH_TREE, PH_GQ, PH_DONE };
 enum Next { N_NONE = 0, N_ENDTRANS, N_ITER, N_TRANS, N_DOUBLE };
 
-template <int CPL, int NW, int MINB>
+template <int CPL, int NW, int MINB, bool DENSE>
 __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const Flags F, const ProbDesc *__restrict__ descs,
                                                          const double *__restrict__ dpool, const int *__restrict__ ipool,
                                                          const int *__restrict__ tri_tab, const SamplerParams sp)
@@ -197,6 +225,13 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
     for (int e = lane; e < C::WS_DOUBLES; e += 32) smem[ws + e] = 0.0;   // the factor's upper triangle must stay zero
     double *const A = sp.arena + (long long)(blockIdx.x * NW + warp) * sp.arena_stride;
+    // dense_e: sharp momenta (M^-1 p) cannot be recomputed cheaply, so every stored p has a mirror slot for it
+    constexpr int DI = (CPL + 1) * 32;                 // internal slots of a D-vector: cell c at c, scalar s at 32 CPL + s
+    const int SOFF = arena_vectors(sp.max_depth);
+    float *const Mf = DENSE ? sp.dense_minv + (long long)(blockIdx.x * NW + warp) * sp.dense_stride : nullptr;
+    double *const Lc = DENSE ? sp.dense_L + (long long)(blockIdx.x * NW + warp) * sp.dense_stride : nullptr;
+    double *const M2 = DENSE ? sp.dense_m2 + (long long)(blockIdx.x * NW + warp) * sp.dense_stride : nullptr;
+    double *const pv = smem + ws + C::OFF_ZS;           // DI <= 2 NN doubles: spans Zs..Ts, free outside the evaluation
     const bool lane_active = (F.active_mask >> lane) & 1u;
     const double l08 = -0.22314355131420976;   // log(0.8)
     // warm-up schedule (windowed_adaptation), identical for every chain
@@ -237,18 +272,95 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     const int *iiglob = nullptr;
     double *cpo_acc = nullptr, *cs = nullptr;
 
-    auto kinetic = [&]() { return 0.5 * vdot3<CPL>(minv, p, p); };
+    // y = M^-1 x.  diag_e: elementwise; dense_e: column sweep over the active slots, x broadcast from shared memory,
+    // M^-1 read coalesced (column g, 32 consecutive rows per load) from the per-warp float matrix.
+    auto sharp = [&](const WVec<CPL> &x, WVec<CPL> &y) {
+        if constexpr (!DENSE) {
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) y.z[t] = minv.z[t] * x.z[t];
+            y.s = minv.s * x.s;
+        } else {
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) pv[t * 32 + lane] = x.z[t];
+            pv[CPL * 32 + lane] = x.s;
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) y.z[t] = 0.0;
+            y.s = 0.0;
+            const int nz = (F.model == 0) ? P.G : 0;
+#pragma unroll 4
+            for (int gg = 0; gg < nz; ++gg) {
+                const double xg = pv[gg];
+                const float *col = Mf + (size_t)gg * DI + lane;
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) y.z[t] = fma((double)col[t * 32], xg, y.z[t]);
+                y.s = fma((double)col[CPL * 32], xg, y.s);
+            }
+            for (int sidx = 0; sidx < SL_COUNT; ++sidx) {
+                if (!((F.active_mask >> sidx) & 1u)) continue;
+                const double xg = pv[CPL * 32 + sidx];
+                const float *col = Mf + (size_t)(CPL * 32 + sidx) * DI + lane;
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) y.z[t] = fma((double)col[t * 32], xg, y.z[t]);
+                y.s = fma((double)col[CPL * 32], xg, y.s);
+            }
+            __syncwarp();
+        }
+    };
+    // sharp momentum of a stored p: mirror slot (dense) or recomputed (diag)
+    auto sh_load = [&](int slot, const WVec<CPL> &pvec, WVec<CPL> &out) {
+        if constexpr (DENSE) vload<CPL>(A + (long long)(slot + SOFF) * VS, out);
+        else sharp(pvec, out);
+    };
+    auto sh_store = [&](int slot, const WVec<CPL> &psv) {
+        if constexpr (DENSE) vstore<CPL>(A + (long long)(slot + SOFF) * VS, psv);
+    };
+    auto slot_active = [&](int f) -> bool {   // is internal slot f a parameter?
+        return f < CPL * 32 ? (F.model == 0 && f < P.G) : ((f - CPL * 32) < SL_COUNT && ((F.active_mask >> (f - CPL * 32)) & 1u));
+    };
     auto sample_momentum = [&](uint32_t tag, uint32_t iter, uint32_t idx0) {
-        // p_i = N(0,1) / sqrt(minv_i)  (diag_e_metric::sample_p)
+        // diag_e_metric::sample_p: p_i = N(0,1) / sqrt(minv_i);  dense_e_metric::sample_p: p = L^-T z, M^-1 = L L^T
         double n0, n1;
 #pragma unroll
         for (int t = 0; t < CPL; t += 2) {
             rng_lane_normal2(rk, tag, iter, idx0 + t, n0, n1);
-            p.z[t] = ((cell[t] >> 17) & 1) ? n0 * rsqrt(minv.z[t]) : 0.0;
-            if (t + 1 < CPL) p.z[t + 1] = ((cell[t + 1] >> 17) & 1) ? n1 * rsqrt(minv.z[t + 1]) : 0.0;
+            const double s0 = DENSE ? 1.0 : rsqrt(minv.z[t]);
+            p.z[t] = ((cell[t] >> 17) & 1) ? n0 * s0 : 0.0;
+            if (t + 1 < CPL) {
+                const double s1 = DENSE ? 1.0 : rsqrt(minv.z[t + 1]);
+                p.z[t + 1] = ((cell[t + 1] >> 17) & 1) ? n1 * s1 : 0.0;
+            }
         }
         rng_lane_normal2(rk, tag, iter, idx0 + CPL + 1, n0, n1);
-        p.s = lane_active ? n0 * rsqrt(minv.s) : 0.0;
+        p.s = lane_active ? n0 * (DENSE ? 1.0 : rsqrt(minv.s)) : 0.0;
+        if constexpr (DENSE) {
+            // back substitution on L^T (left-looking, L column-major lower): p_g = (z_g - sum_{f>g} L[f][g] p_f) / L[g][g]
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) pv[t * 32 + lane] = p.z[t];
+            pv[CPL * 32 + lane] = p.s;
+            __syncwarp();
+            for (int gg = DI - 1; gg >= 0; --gg) {
+                if (!slot_active(gg)) continue;
+                const double *col = Lc + (size_t)gg * DI;
+                double part = 0.0;
+#pragma unroll
+                for (int t = 0; t <= CPL; ++t) {
+                    const int f = t * 32 + lane;
+                    if (f > gg) part = fma(col[f], pv[f], part);
+                }
+                const double tot = warp_sum(part);
+                const double pg = (pv[gg] - tot) / col[gg];
+                __syncwarp();
+                if (lane == 0) pv[gg] = pg;
+                __syncwarp();
+            }
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) p.z[t] = pv[t * 32 + lane];
+            p.s = pv[CPL * 32 + lane];
+            __syncwarp();
+        }
     };
     auto draw_init = [&](uint32_t tr) {
         double ua, ub;
@@ -268,7 +380,9 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     auto istep_probe = [&]() {   // restore the starting point, draw a fresh momentum, aim one leapfrog of eps_try
         vload<CPL>(A + A_SQ * VS, q); vload<CPL>(A + A_SG * VS, g); V = is_V0;
         sample_momentum(RT_ISTEP, istep_tag, (uint32_t)is_it * (CPL + 4));
-        is_H0 = V + kinetic();
+        WVec<CPL> ts;
+        sharp(p, ts);
+        is_H0 = V + 0.5 * vdot2<CPL>(p, ts);
         step = eps_try;
     };
 
@@ -295,6 +409,20 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) minv.z[t] = ((cell[t] >> 17) & 1) ? 1.0 : 0.0;
                 minv.s = lane_active ? 1.0 : 0.0;
+                if constexpr (DENSE) {   // M^-1 = L = I on the parameter slots, Welford accumulator = 0
+                    for (int gg = 0; gg < DI; ++gg) {
+                        const bool ag = slot_active(gg);
+#pragma unroll
+                        for (int t = 0; t <= CPL; ++t) {
+                            const int f = t * 32 + lane;
+                            const double v = (f == gg && ag) ? 1.0 : 0.0;
+                            Mf[(size_t)gg * DI + f] = (float)v;
+                            Lc[(size_t)gg * DI + f] = (f == gg) ? 1.0 : 0.0;
+                            M2[(size_t)gg * DI + f] = 0.0;
+                        }
+                    }
+                    __syncwarp();
+                }
                 cs = sp.chain_stats ? sp.chain_stats + cg * 8 : nullptr;
                 yglob = dpool + pd.off_d + pool_y_off(pd);
                 iiglob = ipool + pd.off_i + pool_ii_off(pd);
@@ -310,12 +438,15 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
         {
             const double he = 0.5 * step;
 #pragma unroll
-            for (int t = 0; t < CPL; ++t) {
-                p.z[t] = fma(he, g.z[t], p.z[t]);
-                q.z[t] = fma(step * minv.z[t], p.z[t], q.z[t]);
-            }
+            for (int t = 0; t < CPL; ++t) p.z[t] = fma(he, g.z[t], p.z[t]);
             p.s = fma(he, g.s, p.s);
-            q.s = fma(step * minv.s, p.s, q.s);
+            {
+                WVec<CPL> yv;
+                sharp(p, yv);   // dtau/dp = M^-1 p
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) q.z[t] = fma(step, yv.z[t], q.z[t]);
+                q.s = fma(step, yv.s, q.s);
+            }
             GQ gq;
             gq.on = (phase == PH_GQ);
             gq.D = pd.D; gq.yglob = yglob; gq.iiglob = iiglob;
@@ -344,6 +475,9 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             for (int t = 0; t < CPL; ++t) p.z[t] = fma(he, g.z[t], p.z[t]);
             p.s = fma(he, g.s, p.s);
         }
+        WVec<CPL> ps;   // sharp momentum of the state just reached; lives only until the next evaluation
+        sharp(p, ps);
+        auto kinetic = [&]() { return 0.5 * vdot2<CPL>(p, ps); };
         // ---- bookkeeping of this chain ---------------------------------------------------------------
         int next = N_NONE;
         if (phase == PH_INIT) {
@@ -423,11 +557,13 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) S.z[t] += p.z[t];
                 S.s += p.s;
-                if (k == 0) vstore<CPL>(A + A_P_NEW_NEAR * VS, p);
+                if (k == 0) { vstore<CPL>(A + A_P_NEW_NEAR * VS, p); sh_store(A_P_NEW_NEAR, ps); }
                 // leaf k opens blocks at every level l >= 2 with k % 2^l == 0
                 if ((k & 3) == 0) {
-                    for (int l = 2; l <= depth && (k & ((1 << l) - 1)) == 0; ++l)
+                    for (int l = 2; l <= depth && (k & ((1 << l) - 1)) == 0; ++l) {
                         vstore<CPL>(A + (A_LVL + 3 * (l - 2)) * VS, p);
+                        sh_store(A_LVL + 3 * (l - 2), ps);
+                    }
                 }
                 if (k & 1) {
                     // level 1: left = leaf k-1, right = leaf k (the three tests coincide)
@@ -435,7 +571,9 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
 #pragma unroll
                     for (int t = 0; t < CPL; ++t) car.z[t] = pprev.z[t] + p.z[t];
                     car.s = pprev.s + p.s;
-                    valid = uturn_ok<CPL>(minv, pprev, p, car);
+                    WVec<CPL> pprev_s;
+                    sh_load(A_PREV, pprev, pprev_s);
+                    valid = uturn_sharp_ok<CPL>(pprev_s, ps, car);
                     int l = 2;
                     const int kk = k + 1;
                     while (valid && l <= depth && (kk & ((1 << l) - 1)) == 0) {
@@ -445,22 +583,26 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
 #pragma unroll
                         for (int t = 0; t < CPL; ++t) ext.z[t] = rhoL.z[t] + car.z[t];
                         ext.s = rhoL.s + car.s;
-                        bool okm = uturn_ok<CPL>(minv, pbegL, p, ext);           // rho_L + rho_R around the block
+                        WVec<CPL> pbegL_s;
+                        sh_load(A_LVL + 3 * (l - 2), pbegL, pbegL_s);
+                        bool okm = uturn_sharp_ok<CPL>(pbegL_s, ps, ext);        // rho_L + rho_R around the block
                         {
-                            WVec<CPL> pbegR, e2;
-                            if (l == 2) pbegR = pprev; else vload<CPL>(A + (A_LVL + 3 * (l - 3)) * VS, pbegR);
+                            WVec<CPL> pbegR, pbegR_s, e2;
+                            if (l == 2) { pbegR = pprev; pbegR_s = pprev_s; }
+                            else { vload<CPL>(A + (A_LVL + 3 * (l - 3)) * VS, pbegR); sh_load(A_LVL + 3 * (l - 3), pbegR, pbegR_s); }
 #pragma unroll
                             for (int t = 0; t < CPL; ++t) e2.z[t] = rhoL.z[t] + pbegR.z[t];
                             e2.s = rhoL.s + pbegR.s;
-                            okm = okm && uturn_ok<CPL>(minv, pbegL, pbegR, e2);   // rho_L + p(first leaf of R)
+                            okm = okm && uturn_sharp_ok<CPL>(pbegL_s, pbegR_s, e2);   // rho_L + p(first leaf of R)
                         }
                         {
-                            WVec<CPL> pendL, e3;
+                            WVec<CPL> pendL, pendL_s, e3;
                             vload<CPL>(Lv + VS, pendL);
+                            sh_load(A_LVL + 3 * (l - 2) + 1, pendL, pendL_s);
 #pragma unroll
                             for (int t = 0; t < CPL; ++t) e3.z[t] = car.z[t] + pendL.z[t];
                             e3.s = car.s + pendL.s;
-                            okm = okm && uturn_ok<CPL>(minv, pendL, p, e3);       // rho_R + p(last leaf of L)
+                            okm = okm && uturn_sharp_ok<CPL>(pendL_s, ps, e3);     // rho_R + p(last leaf of L)
                         }
                         valid = okm;
                         car = ext;
@@ -469,6 +611,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                     if (valid && l <= depth) {   // the completed block is the left half of a level-l block
                         double *Lv = A + (A_LVL + 3 * (l - 2)) * VS;
                         vstore<CPL>(Lv + VS, p);
+                        sh_store(A_LVL + 3 * (l - 2) + 1, ps);
                         vstore<CPL>(Lv + 2 * VS, car);
                     }
                 }
@@ -478,6 +621,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             } else if (k + 1 < nleaf) {
                 ++k;
                 pprev = p;
+                sh_store(A_PREV, ps);
             } else {
                 // ---- subtree complete: multinomial sample across subtrees (biased progressive sampling) ----
                 ++depth;
@@ -495,23 +639,27 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) rho.z[t] = rho_old.z[t] + S.z[t];
                 rho.s = rho_old.s + S.s;
-                bool persist = uturn_ok<CPL>(minv, pfar, p, rho);
+                WVec<CPL> pfar_s;
+                sh_load(A_OP, pfar, pfar_s);
+                bool persist = uturn_sharp_ok<CPL>(pfar_s, ps, rho);
                 vstore<CPL>(A + A_RHO_OLD * VS, rho);
                 {
-                    WVec<CPL> pnn, e2;
-                    if (nleaf == 1) pnn = p; else vload<CPL>(A + A_P_NEW_NEAR * VS, pnn);
+                    WVec<CPL> pnn, pnn_s, e2;
+                    if (nleaf == 1) { pnn = p; pnn_s = ps; }
+                    else { vload<CPL>(A + A_P_NEW_NEAR * VS, pnn); sh_load(A_P_NEW_NEAR, pnn, pnn_s); }
 #pragma unroll
                     for (int t = 0; t < CPL; ++t) e2.z[t] = rho_old.z[t] + pnn.z[t];
                     e2.s = rho_old.s + pnn.s;
-                    persist = persist && uturn_ok<CPL>(minv, pfar, pnn, e2);
+                    persist = persist && uturn_sharp_ok<CPL>(pfar_s, pnn_s, e2);
                 }
                 {
-                    WVec<CPL> pon, e3;
+                    WVec<CPL> pon, pon_s, e3;
                     vload<CPL>(A + A_P_OLD_NEAR * VS, pon);
+                    sh_load(A_P_OLD_NEAR, pon, pon_s);
 #pragma unroll
                     for (int t = 0; t < CPL; ++t) e3.z[t] = S.z[t] + pon.z[t];
                     e3.s = S.s + pon.s;
-                    persist = persist && uturn_ok<CPL>(minv, pon, p, e3);
+                    persist = persist && uturn_sharp_ok<CPL>(pon_s, ps, e3);
                 }
                 next = (persist && depth < sp.max_depth) ? N_DOUBLE : N_ENDTRANS;
             }
@@ -543,28 +691,97 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 // windowed variance adaptation (var_adaptation::learn_variance, Welford)
                 if ((it >= init_buffer) && (it < nw - term_buffer)) {
                     wn += 1.0;
-                    WVec<CPL> m, m2;
+                    WVec<CPL> m, m2, dold;
                     vload<CPL>(A + A_WM * VS, m); vload<CPL>(A + A_WM2 * VS, m2);
                     const double iw = 1.0 / wn;
 #pragma unroll
                     for (int t = 0; t < CPL; ++t) {
                         const double d = q.z[t] - m.z[t];
+                        dold.z[t] = d;
                         m.z[t] = fma(d, iw, m.z[t]);
                         m2.z[t] = fma(q.z[t] - m.z[t], d, m2.z[t]);
                     }
                     {
                         const double d = q.s - m.s;
+                        dold.s = d;
                         m.s = fma(d, iw, m.s);
                         m2.s = fma(q.s - m.s, d, m2.s);
                     }
+                    if constexpr (DENSE) {
+                        // covar_adaptation::learn_covariance (Welford): M2 += (q - mean_new) (q - mean_old)^T
+                        __syncwarp();
+#pragma unroll
+                        for (int t = 0; t < CPL; ++t) pv[t * 32 + lane] = q.z[t] - m.z[t];
+                        pv[CPL * 32 + lane] = q.s - m.s;
+                        __syncwarp();
+                        for (int gg = 0; gg < DI; ++gg) {
+                            if (!slot_active(gg)) continue;
+                            const double dn = pv[gg];
+                            double *col = M2 + (size_t)gg * DI + lane;
+#pragma unroll
+                            for (int t = 0; t < CPL; ++t) col[t * 32] = fma(dn, dold.z[t], col[t * 32]);
+                            col[CPL * 32] = fma(dn, dold.s, col[CPL * 32]);
+                        }
+                        __syncwarp();
+                    }
                     if (it == win_end) {
                         const double aa = wn / (wn + 5.0), bb = 1e-3 * (5.0 / (wn + 5.0)), inm1 = 1.0 / (wn - 1.0);
+                        if constexpr (!DENSE) {
 #pragma unroll
-                        for (int t = 0; t < CPL; ++t) {
-                            if ((cell[t] >> 17) & 1) minv.z[t] = fma(aa, m2.z[t] * inm1, bb);
-                            m.z[t] = 0.0; m2.z[t] = 0.0;
+                            for (int t = 0; t < CPL; ++t)
+                                if ((cell[t] >> 17) & 1) minv.z[t] = fma(aa, m2.z[t] * inm1, bb);
+                            if (lane_active) minv.s = fma(aa, m2.s * inm1, bb);
+                        } else {
+                            // M^-1 = n/(n+5) cov + 1e-3 5/(n+5) I, symmetrised from the lower triangle, rounded to float;
+                            // L = chol(M^-1) of exactly that rounded matrix (column-major lower, right-looking, in place)
+                            for (int gg = 0; gg < DI; ++gg) {
+                                const bool ag = slot_active(gg);
+#pragma unroll
+                                for (int t = 0; t <= CPL; ++t) {
+                                    const int f = t * 32 + lane;
+                                    double v = (f == gg) ? 1.0 : 0.0;
+                                    if (ag && slot_active(f)) {
+                                        const int hi = f > gg ? f : gg, lo = f > gg ? gg : f;
+                                        v = aa * M2[(size_t)hi * DI + lo] * inm1 + ((f == gg) ? bb : 0.0);
+                                    }
+                                    const float vf = (float)v;
+                                    Mf[(size_t)gg * DI + f] = vf;
+                                    Lc[(size_t)gg * DI + f] = (double)vf;
+                                }
+                            }
+                            __syncwarp();
+                            for (int gg = 0; gg < DI; ++gg) {
+#pragma unroll
+                                for (int t = 0; t <= CPL; ++t) M2[(size_t)gg * DI + t * 32 + lane] = 0.0;
+                            }
+                            for (int kk = 0; kk < DI; ++kk) {
+                                if (!slot_active(kk)) continue;
+                                double *colk = Lc + (size_t)kk * DI;
+                                const double inv = rsqrt(fmax(colk[kk], 1e-300));
+                                double ck[CPL + 1];
+                                __syncwarp();
+#pragma unroll
+                                for (int t = 0; t <= CPL; ++t) {
+                                    const int f = t * 32 + lane;
+                                    ck[t] = (f >= kk) ? colk[f] * inv : 0.0;
+                                    if (f >= kk) colk[f] = ck[t];
+                                }
+                                __syncwarp();
+                                for (int jj = kk + 1; jj < DI; ++jj) {
+                                    if (!slot_active(jj)) continue;
+                                    const double ljk = colk[jj];
+                                    double *colj = Lc + (size_t)jj * DI;
+#pragma unroll
+                                    for (int t = 0; t <= CPL; ++t) {
+                                        const int f = t * 32 + lane;
+                                        if (f >= jj) colj[f] = fma(-ck[t], ljk, colj[f]);
+                                    }
+                                }
+                            }
+                            __syncwarp();
                         }
-                        if (lane_active) minv.s = fma(aa, m2.s * inm1, bb);
+#pragma unroll
+                        for (int t = 0; t < CPL; ++t) { m.z[t] = 0.0; m2.z[t] = 0.0; }
                         m.s = 0.0; m2.s = 0.0;
                         wn = 0.0;
                         if (win_end != nw - term_buffer - 1) {   // compute_next_window
@@ -634,8 +851,10 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             e_used = eps;
             if (sp.jitter > 0.0) e_used = eps * (1.0 + sp.jitter * (2.0 * rng_warp_uniform(rk, RT_JIT, it, 0) - 1.0));
             sample_momentum(RT_MOM, (uint32_t)it, 0);
+            sharp(p, ps);
             H0 = V + kinetic();
             vstore<CPL>(A + A_OQ * VS, q); vstore<CPL>(A + A_OP * VS, p); vstore<CPL>(A + A_OG * VS, g);
+            sh_store(A_OP, ps);
             vstore<CPL>(A + A_SQ * VS, q); vstore<CPL>(A + A_SG * VS, g);
             vstore<CPL>(A + A_RHO_OLD * VS, p);
             otherV = V; sampleV = V; sampleH = H0; proposeV = V; proposeH = H0;
@@ -651,11 +870,15 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 WVec<CPL> tv;
                 vload<CPL>(A + A_OQ * VS, tv); vstore<CPL>(A + A_OQ * VS, q); q = tv;
                 vload<CPL>(A + A_OP * VS, tv); vstore<CPL>(A + A_OP * VS, p); p = tv;
+                if constexpr (DENSE) { vload<CPL>(A + (long long)(A_OP + SOFF) * VS, tv); vstore<CPL>(A + (long long)(A_OP + SOFF) * VS, ps); ps = tv; }
+                else sharp(p, ps);
                 vload<CPL>(A + A_OG * VS, tv); vstore<CPL>(A + A_OG * VS, g); g = tv;
                 const double t2 = otherV; otherV = V; V = t2;
                 curdir = dir;
             }
             vstore<CPL>(A + A_P_OLD_NEAR * VS, p);
+            sh_store(A_P_OLD_NEAR, ps);
+            sh_store(A_PREV, ps);
 #pragma unroll
             for (int t = 0; t < CPL; ++t) S.z[t] = 0.0;
             S.s = 0.0;

@@ -110,3 +110,25 @@ def test_tree_statistics_match_oracle(built, datasets):
     assert abs(dep_g.mean() - dep_o.mean()) < 4 * se_dep + 0.1, (dep_g.mean(), dep_o.mean(), se_dep)
     assert abs(sp[..., 0].mean() - spo[..., 0].mean()) < 0.03          # accept_stat ~ adapt_delta on both sides
     b.close()
+
+
+def test_dense_metric_agrees_with_diag(built, datasets):
+    """dense_e (what bayesynergy() selects for robust = TRUE, R/bayesynergy.R:112-115, with stepsize_jitter 0.5):
+    same posterior as diag_e within Monte Carlo error, sane adaptation, and a non-trivial adapted metric."""
+    y, x = datasets["mathews:ispinesib + ibrutinib"]
+    for v in (dict(), dict(robust=True)):
+        sd = prepare(y, x, **v)
+        b = _lib.Batch([sd, sd])
+        jit = 0.5 if v else 0.0
+        rd = b.sample(chains=4, iter=1200, warmup=600, seed=31, metric=1, stepsize_jitter=jit)
+        r0 = b.sample(chains=4, iter=1200, warmup=600, seed=32, metric=0, stepsize_jitter=jit)
+        assert (rd["chain_stats"][:, :, 6] == 0).all()
+        assert 0.7 < rd["chain_stats"][:, :, 5].mean() < 0.99
+        for qn in ("rVUS_f", "rVUS_p0", "VUS_syn", "VUS_ant", "s", "dss_1"):
+            a = rd["qdraws"][:, :, :, Q.index(qn)].reshape(8, -1)
+            c = r0["qdraws"][:, :, :, Q.index(qn)].reshape(8, -1)
+            se = np.hypot(mcse_mean(a), mcse_mean(c))
+            assert abs(a.mean() - c.mean()) <= 4.0 * se + 1e-6, (v, qn, a.mean(), c.mean(), se)
+        # the dense sampler should not need more leapfrogs per iteration than the diagonal one
+        assert rd["sampler_params"][..., 3].mean() < 1.5 * r0["sampler_params"][..., 3].mean()
+        b.close()
