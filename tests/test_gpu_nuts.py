@@ -132,3 +132,30 @@ def test_dense_metric_agrees_with_diag(built, datasets):
         # the dense sampler should not need more leapfrogs per iteration than the diagonal one
         assert rd["sampler_params"][..., 3].mean() < 1.5 * r0["sampler_params"][..., 3].mean()
         b.close()
+
+
+def test_oneil_shaped_screen(built, datasets):
+    """cfg2-shaped problems (11x11 grid, 32 of 144 cells observed, 9-12 replicates; the two raw experiments shipped in
+    ONeil_A375$failed) through synergyscreen(): two-pass strip products, unobserved cells, > 4 replicates per cell."""
+    from bayesynergy_b200.api import synergyscreen, SCREEN_COLUMNS
+    exps = []
+    for k in (0, 1):
+        y, x = datasets[f"oneil_failed:{k}"]
+        exps.append(dict(y=y, x=x, drug_names=[f"A{k}", f"B{k}"], experiment_ID="A375"))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = synergyscreen(exps, bayesynergy_params=dict(iter=600, chains=4, seed=3), max_retries=1)
+    rows = out["screenSummary"] + [None] * len(out.get("failed", []))
+    assert len(rows) == 2
+    for r in out["screenSummary"]:
+        assert list(r.keys()) == SCREEN_COLUMNS
+        assert 0 < r["Efficacy (mean)"] < 100 and r["Synergy (mean)"] <= 1e-3 and r["Antagonism (mean)"] >= 0
+        assert np.isfinite(r["Synergy Score"]) and r["s"] > 0
+    # statistical agreement with the oracle on the first experiment
+    sd = prepare(*datasets["oneil_failed:0"])
+    b = _lib.Batch([sd])
+    res = b.sample(chains=4, iter=1000, warmup=500, seed=8)
+    ng, outs, spo = nuts_screen([Problem(sd)], n_chains=4, num_warmup=500, num_samples=500, seed=12)
+    _compare(res["qdraws"][0], outs[0], output_names(sd), "oneil_failed:0")
+    b.close()
