@@ -101,37 +101,6 @@ __device__ __forceinline__ void strip_product(const double *A, const double *B, 
         epi(r0, c, a0, a1, a2, a3);
     }
 }
-// Two independent strip products in one loop (8 accumulators per lane): halves the number of dependent phases
-// of the backward pass and doubles the FMA-level parallelism the latency-bound warp can expose.
-template <int NM, int SBC1, int SBM1, int SBC2, int SBM2, class Epi1, class Epi2>
-__device__ __forceinline__ void strip_product2(const double *A1, const double *B1, const int C1, const int nm1, Epi1 &&epi1,
-                                               const double *A2, const double *B2, const int C2, const int nm2, Epi2 &&epi2)
-{
-    constexpr int NS = NM / 4;
-    const int lane = threadIdx.x & 31;
-    const int S1 = NS * C1, S2 = NS * C2, Smax = S1 > S2 ? S1 : S2, nm = nm1 > nm2 ? nm1 : nm2;
-    for (int s = lane; s < Smax; s += 32) {
-        const int c = s / NS, r0 = 4 * (s - c * NS);
-        const double2 *Ap1 = reinterpret_cast<const double2 *>(A1 + r0), *Ap2 = reinterpret_cast<const double2 *>(A2 + r0);
-        const double *Bp1 = B1 + c * SBC1, *Bp2 = B2 + c * SBC2;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-#pragma unroll 2
-        for (int m = 0; m < nm; ++m) {
-            if (m < nm1) {
-                const double2 x = Ap1[m * (NM / 2)], y = Ap1[m * (NM / 2) + 1];
-                const double bv = Bp1[m * SBM1];
-                a0 = fma(x.x, bv, a0); a1 = fma(x.y, bv, a1); a2 = fma(y.x, bv, a2); a3 = fma(y.y, bv, a3);
-            }
-            if (m < nm2) {
-                const double2 x = Ap2[m * (NM / 2)], y = Ap2[m * (NM / 2) + 1];
-                const double bv = Bp2[m * SBM2];
-                b0 = fma(x.x, bv, b0); b1 = fma(x.y, bv, b1); b2 = fma(y.x, bv, b2); b3 = fma(y.y, bv, b3);
-            }
-        }
-        if (s < S1) epi1(r0, c, a0, a1, a2, a3);
-        if (s < S2) epi2(r0, c, b0, b1, b2, b3);
-    }
-}
 __device__ __forceinline__ void st2(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
 
 template <int CPL> __device__ __forceinline__ int zoff(const int cell)   // cell -> offset in a grid-shaped buffer
@@ -624,42 +593,39 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     double ellbar = 0.0, sigfbar = 0.0, alphabar = 0.0;
     if (gp) {
         __syncwarp();   // p0bar (in Ws) has been consumed
-        // W = Gbar * L1 -> Ws   (W[i,l] = sum_j Gbar[i,j] L1[j,l])   fused with
+        // W = Gbar * L1 -> Ws            W[i,l] = sum_j Gbar[i,j] L1[j,l]
+        strip_product<NM, 1, NM>(Gs, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Ws + r0 + c * NM, a0, a1); st2(Ws + r0 + c * NM + 2, a2, a3);
+        });
         // L1bar = tril(Gbar^T T) -> Lb1 row-major: strip rows l of column j hold L1bar[j,l], kept for l <= j
-        strip_product2<NM, 1, NM, NM, 1>(
-            Gs, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-                st2(Ws + r0 + c * NM, a0, a1); st2(Ws + r0 + c * NM + 2, a2, a3);
-            },
-            Tt, Gs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-                st2(Lb1 + r0 + c * NM, (r0 <= c) ? a0 : 0.0, (r0 + 1 <= c) ? a1 : 0.0);
-                st2(Lb1 + r0 + c * NM + 2, (r0 + 2 <= c) ? a2 : 0.0, (r0 + 3 <= c) ? a3 : 0.0);
-            });
+        strip_product<NM, NM, 1>(Tt, Gs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Lb1 + r0 + c * NM, (r0 <= c) ? a0 : 0.0, (r0 + 1 <= c) ? a1 : 0.0);
+            st2(Lb1 + r0 + c * NM + 2, (r0 + 2 <= c) ? a2 : 0.0, (r0 + 3 <= c) ? a3 : 0.0);
+        });
+        __syncwarp();
+        // L2bar = tril(W Z^T) -> Lb2 col-major [i + k*NM], kept for i >= k
+        strip_product<NM, 1, NM>(Ws, Zs, n2, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Lb2 + r0 + c * NM, (r0 >= c) ? a0 : 0.0, (r0 + 1 >= c) ? a1 : 0.0);
+            st2(Lb2 + r0 + c * NM + 2, (r0 + 2 >= c) ? a2 : 0.0, (r0 + 3 >= c) ? a3 : 0.0);
+        });
         if (DBG) {
 #pragma unroll
             for (int t = 0; t < CPL; ++t)
                 if (cell[t] >> 16) dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gs[zoff<CPL>(cell[t])];
         }
         __syncwarp();
-        // L2bar = tril(W Z^T) -> Lb2 col-major [i + k*NM], kept for i >= k   fused with
-        // Zbar = L2^T W -> Gs   (Zbar[k,l] = sum_i L2[i,k] W[i,l])
-        strip_product2<NM, 1, NM, NM, 1>(
-            Ws, Zs, n2, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-                st2(Lb2 + r0 + c * NM, (r0 >= c) ? a0 : 0.0, (r0 + 1 >= c) ? a1 : 0.0);
-                st2(Lb2 + r0 + c * NM + 2, (r0 + 2 >= c) ? a2 : 0.0, (r0 + 3 >= c) ? a3 : 0.0);
-            },
-            L2r, Ws, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-                st2(Gs + r0 + c * NM, a0, a1); st2(Gs + r0 + c * NM + 2, a2, a3);
-            });
-        __syncwarp();
+        // Zbar = L2^T W -> Gs            Zbar[k,l] = sum_i L2[i,k] W[i,l]
+        strip_product<NM, NM, 1>(L2r, Ws, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Gs + r0 + c * NM, a0, a1); st2(Gs + r0 + c * NM + 2, a2, a3);
+        });
         // Cholesky adjoint (Murray 2016): Xfull = L^-T (Phi + Phi^T) L^-1, Phi = tril(L^T Lbar), diag halved.
-        // Stage A: P = L^T Lbar (only its lower triangle is used) -> S1 (over Zs), S2 (over Ts), fused
-        strip_product2<NM, 1, NM, NM, 1>(
-            L1r, Lb1, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-                st2(Zs + r0 + c * NM, a0, a1); st2(Zs + r0 + c * NM + 2, a2, a3);
-            },
-            L2r, Lb2, n2, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-                st2(Ts + r0 + c * NM, a0, a1); st2(Ts + r0 + c * NM + 2, a2, a3);
-            });
+        // Stage A: P = L^T Lbar (only its lower triangle is used) -> S1 (over Zs), S2 (over Ts)
+        strip_product<NM, 1, NM>(L1r, Lb1, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Zs + r0 + c * NM, a0, a1); st2(Zs + r0 + c * NM + 2, a2, a3);
+        });
+        strip_product<NM, NM, 1>(L2r, Lb2, n2, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st2(Ts + r0 + c * NM, a0, a1); st2(Ts + r0 + c * NM + 2, a2, a3);
+        });
         __syncwarp();
         // Zbar is complete: gradient wrt z (+ its N(0,1) prior)
 #pragma unroll
