@@ -235,3 +235,54 @@ def synthetic_experiment(combo_id: int, n=10, nrep=3, seed0=20261019):
     fvec = f[b_idx.reshape(-1), a_idx.reshape(-1)]
     y = fvec[:, None] + rng.normal(size=(fvec.shape[0], nrep)) * (0.1 * np.sqrt(fvec + 0.005))[:, None]
     return y, x
+
+
+def synthetic_oneil_experiment(combo_id: int, seed0=20261019 + 10_000_000, mono_reps=12):
+    """cfg2/cfg3 generator: one synthetic combination on the exact dose layout of the shipped raw
+    experiment `ONeil_A375$failed[[1]]`: 8 monotherapy doses per drug x `mono_reps` replicates on dose levels that
+    do not align with the 4 x 4 combination block (x 4 replicates), no (0, 0) well  =>  11 distinct non-zero levels
+    per axis (top dose shared), N = 256, 16 of 121 interior cells observed.  Returns (y[N], x[N, 2])."""
+    rng = np.random.default_rng(seed0 + combo_id)
+    m1 = np.array([0.0022, 0.0065, 0.02, 0.06, 0.19, 0.55, 1.7, 5.0])
+    m2 = np.array([0.0045, 0.014, 0.04, 0.12, 0.37, 1.1, 3.4, 10.0])
+    c1 = np.array([0.325, 0.8, 2.0, 5.0])
+    c2 = np.array([0.223, 0.775, 2.75, 10.0])
+    scale = 10.0 ** rng.uniform(-0.3, 0.3, size=2)          # per-combination dose scale
+    m1, c1, m2, c2 = m1 * scale[0], c1 * scale[0], m2 * scale[1], c2 * scale[1]
+    la = rng.beta(1.0, 1.25, size=2) * 0.5
+    slope = rng.gamma(2.0, 1.0, size=2) + 0.3
+    mid = np.array([np.log10(np.median(m1)), np.log10(np.median(m2))]) + rng.normal(0, 0.5, size=2)
+    strength = rng.choice([0.0, 0.0, 0.5, 1.5])
+    u1 = np.unique(np.concatenate([m1, c1]))
+    u2 = np.unique(np.concatenate([m2, c2]))
+    lx1, lx2 = np.log10(u1), np.log10(u2)
+
+    def chol_k(lx):
+        d = np.abs(lx[:, None] - lx[None, :])
+        K = (1 + math.sqrt(3) * d) * np.exp(-math.sqrt(3) * d) + 1e-10 * np.eye(len(lx))
+        return np.linalg.cholesky(K)
+
+    z = rng.normal(size=(len(u2), len(u1))) * strength
+    GP = chol_k(lx2) @ z @ chol_k(lx1).T
+    p01 = la[0] + (1 - la[0]) / (1 + 10 ** (slope[0] * (lx1 - mid[0])))
+    p02 = la[1] + (1 - la[1]) / (1 + 10 ** (slope[1] * (lx2 - mid[1])))
+    p0 = p02[:, None] * p01[None, :]
+    lg = np.log(p0 / (1 - p0))
+    f = p0 + (-p0 / (1 + np.exp(GP + lg)) + (1 - p0) / (1 + np.exp(-GP - lg)))
+    rows, vals = [], []
+    for a, d in enumerate(u1):
+        if d in m1:
+            for _ in range(mono_reps):
+                rows.append((d, 0.0)); vals.append(p01[a])
+    for b, d in enumerate(u2):
+        if d in m2:
+            for _ in range(mono_reps):
+                rows.append((0.0, d)); vals.append(p02[b])
+    for d1 in c1:
+        for d2 in c2:
+            a, b = int(np.where(u1 == d1)[0][0]), int(np.where(u2 == d2)[0][0])
+            for _ in range(4):
+                rows.append((d1, d2)); vals.append(f[b, a])
+    vals = np.array(vals)
+    y = vals + rng.normal(size=vals.shape[0]) * 0.1 * np.sqrt(vals + 0.005)
+    return y, np.array(rows)

@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Measured rates for every BASELINE.json config (the bench line is cfg5; these are documentation).
+
+cfg1  bayesynergy() on mathews_DLBCL[[1]], 4 chains x 2000 iter: a batch of identical copies (different seeds)
+cfg1' same with the RBF kernel (type = 2)
+cfg2  O'Neil-shaped screen (11x11 grid, 32 observed cells, N = 256), default options
+cfg3  robust + PC-prior Matern + lower asymptotes, dense_e + stepsize_jitter 0.5 (what bayesynergy() selects)
+cfg4  heteroscedastic gp_grid + the nointeraction model (Bayes-factor pair) on the cfg5 data
+cfg5  synthetic 10x10x3 screen (the bench line)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bayesynergy_b200 import _lib  # noqa: E402
+from bayesynergy_b200.dataprep import prepare, synthetic_experiment, synthetic_oneil_experiment  # noqa: E402
+
+
+def run(name, sds, model="gp_grid", iters=2000, **kw):
+    b = _lib.Batch(sds, model=model)
+    b.sample_device(chains=4, iter=200, warmup=100, seed=9, **kw)     # warm-up launch
+    ng, ms = b.sample_device(chains=4, iter=iters, warmup=iters // 2, seed=1, **kw)
+    ess_syn, _ = b.ess("VUS_syn") if model == "gp_grid" else b.ess("rVUS_f")
+    ess_ant, rhat = b.ess("VUS_ant") if model == "gp_grid" else b.ess("rVUS_p0")
+    ess = np.fmin(ess_syn, ess_ant)
+    out = dict(config=name, model=model, combos=len(sds), D=b.max_params, n_grad=ng, kernel_s=ms * 1e-3,
+               grad_evals_per_s=ng / ms * 1e3, leapfrogs_per_iter=ng / (len(sds) * 4 * iters),
+               ess_min_mean=float(np.nanmean(ess)), total_ess_per_s=float(np.nansum(ess) / (ms * 1e-3)),
+               rhat_max=float(np.nanmax(rhat)), sampler=kw)
+    b.close()
+    print(json.dumps(out), flush=True)
+    return out
+
+
+def main():
+    nb = int(os.environ.get("CB_COMBOS", "888"))
+    m = json.load(open(os.path.join(ROOT, "tests/golden/mathews_DLBCL.json")))
+    e = m["ispinesib + ibrutinib"]
+    x = np.array(e["x"]).reshape(2, -1).T
+    y = np.array(e["y"])
+    res = []
+    res.append(run("cfg1 mathews_DLBCL[[1]] Matern 3/2 (package default)", [prepare(y, x)] * nb))
+    res.append(run("cfg1' mathews_DLBCL[[1]] RBF (type=2)", [prepare(y, x, type=2)] * nb))
+    on = [prepare(*synthetic_oneil_experiment(k)) for k in range(min(nb, 583))]
+    res.append(run("cfg2 O'Neil-shaped screen, default options", on))
+    onr = [prepare(*synthetic_oneil_experiment(k), robust=True, pcprior=True) for k in range(min(nb, 583))]
+    res.append(run("cfg3 O'Neil-shaped, robust + PC prior, dense_e + jitter 0.5", onr, metric=1, stepsize_jitter=0.5))
+    res.append(run("cfg3-diag same model with diag_e (for comparison)", onr, metric=0, stepsize_jitter=0.5))
+    syn = [prepare(*synthetic_experiment(k)) for k in range(nb)]
+    res.append(run("cfg4 nointeraction (H0 of the Bayes factor) on cfg5 data", syn, model="nointeraction"))
+    res.append(run("cfg5 synthetic 10x10x3 (bench line)", syn))
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "config_bench.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
