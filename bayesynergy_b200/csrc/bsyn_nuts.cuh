@@ -117,6 +117,24 @@ __device__ __forceinline__ bool uturn_sharp_ok(const WVec<CPL> &as, const WVec<C
     }
     return sa > 0.0 && sb > 0.0;
 }
+// Three compute_criterion tests at once: (a1, b1 | r1), (a2, b2 | r2), (a3, b3 | r3) -> 6 dot products reduced with ONE
+// 8-value butterfly (9 shuffles, one latency chain) instead of three pairs of reductions.
+template <int CPL>
+__device__ __forceinline__ bool uturn3_ok(const WVec<CPL> &a1, const WVec<CPL> &b1, const WVec<CPL> &r1,
+                                          const WVec<CPL> &a2, const WVec<CPL> &b2, const WVec<CPL> &r2,
+                                          const WVec<CPL> &a3, const WVec<CPL> &b3, const WVec<CPL> &r3)
+{
+    double v[8] = {a1.s * r1.s, b1.s * r1.s, a2.s * r2.s, b2.s * r2.s, a3.s * r3.s, b3.s * r3.s, 0.0, 0.0};
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+        v[0] = fma(a1.z[t], r1.z[t], v[0]); v[1] = fma(b1.z[t], r1.z[t], v[1]);
+        v[2] = fma(a2.z[t], r2.z[t], v[2]); v[3] = fma(b2.z[t], r2.z[t], v[3]);
+        v[4] = fma(a3.z[t], r3.z[t], v[4]); v[5] = fma(b3.z[t], r3.z[t], v[5]);
+    }
+    const double tot = warp_sum8(v);                       // lane L holds the total of v[L & 7]
+    const bool mine = ((threadIdx.x & 7) >= 6) || (tot > 0.0);
+    return __all_sync(FULL, mine);
+}
 template <int CPL> __device__ __forceinline__ double vdot2(const WVec<CPL> &a, const WVec<CPL> &b)
 {
     double s = a.s * b.s;
@@ -578,32 +596,21 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                     const int kk = k + 1;
                     while (valid && l <= depth && (kk & ((1 << l) - 1)) == 0) {
                         double *Lv = A + (A_LVL + 3 * (l - 2)) * VS;
-                        WVec<CPL> pbegL, rhoL, ext;
-                        vload<CPL>(Lv, pbegL); vload<CPL>(Lv + 2 * VS, rhoL);
-#pragma unroll
-                        for (int t = 0; t < CPL; ++t) ext.z[t] = rhoL.z[t] + car.z[t];
-                        ext.s = rhoL.s + car.s;
-                        WVec<CPL> pbegL_s;
+                        WVec<CPL> pbegL, rhoL, pendL, pbegR, ext, e2, e3, pbegL_s, pbegR_s, pendL_s;
+                        // issue all loads of this merge together: L's first / last leaf and rho, R's first leaf
+                        vload<CPL>(Lv, pbegL); vload<CPL>(Lv + 2 * VS, rhoL); vload<CPL>(Lv + VS, pendL);
+                        if (l == 2) pbegR = pprev; else vload<CPL>(A + (A_LVL + 3 * (l - 3)) * VS, pbegR);
                         sh_load(A_LVL + 3 * (l - 2), pbegL, pbegL_s);
-                        bool okm = uturn_sharp_ok<CPL>(pbegL_s, ps, ext);        // rho_L + rho_R around the block
-                        {
-                            WVec<CPL> pbegR, pbegR_s, e2;
-                            if (l == 2) { pbegR = pprev; pbegR_s = pprev_s; }
-                            else { vload<CPL>(A + (A_LVL + 3 * (l - 3)) * VS, pbegR); sh_load(A_LVL + 3 * (l - 3), pbegR, pbegR_s); }
+                        sh_load(A_LVL + 3 * (l - 2) + 1, pendL, pendL_s);
+                        if (l == 2) pbegR_s = pprev_s; else sh_load(A_LVL + 3 * (l - 3), pbegR, pbegR_s);
 #pragma unroll
-                            for (int t = 0; t < CPL; ++t) e2.z[t] = rhoL.z[t] + pbegR.z[t];
-                            e2.s = rhoL.s + pbegR.s;
-                            okm = okm && uturn_sharp_ok<CPL>(pbegL_s, pbegR_s, e2);   // rho_L + p(first leaf of R)
+                        for (int t = 0; t < CPL; ++t) {
+                            ext.z[t] = rhoL.z[t] + car.z[t];      // rho_L + rho_R around the merged block
+                            e2.z[t] = rhoL.z[t] + pbegR.z[t];     // rho_L + p(first leaf of R)
+                            e3.z[t] = car.z[t] + pendL.z[t];      // rho_R + p(last leaf of L)
                         }
-                        {
-                            WVec<CPL> pendL, pendL_s, e3;
-                            vload<CPL>(Lv + VS, pendL);
-                            sh_load(A_LVL + 3 * (l - 2) + 1, pendL, pendL_s);
-#pragma unroll
-                            for (int t = 0; t < CPL; ++t) e3.z[t] = car.z[t] + pendL.z[t];
-                            e3.s = car.s + pendL.s;
-                            okm = okm && uturn_sharp_ok<CPL>(pendL_s, ps, e3);     // rho_R + p(last leaf of L)
-                        }
+                        ext.s = rhoL.s + car.s; e2.s = rhoL.s + pbegR.s; e3.s = car.s + pendL.s;
+                        const bool okm = uturn3_ok<CPL>(pbegL_s, ps, ext, pbegL_s, pbegR_s, e2, pendL_s, ps, e3);
                         valid = okm;
                         car = ext;
                         ++l;
@@ -639,28 +646,20 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) rho.z[t] = rho_old.z[t] + S.z[t];
                 rho.s = rho_old.s + S.s;
-                WVec<CPL> pfar_s;
+                WVec<CPL> pfar_s, pnn, pnn_s, pon, pon_s, e2, e3;
                 sh_load(A_OP, pfar, pfar_s);
-                bool persist = uturn_sharp_ok<CPL>(pfar_s, ps, rho);
+                if (nleaf == 1) { pnn = p; pnn_s = ps; }
+                else { vload<CPL>(A + A_P_NEW_NEAR * VS, pnn); sh_load(A_P_NEW_NEAR, pnn, pnn_s); }
+                vload<CPL>(A + A_P_OLD_NEAR * VS, pon);
+                sh_load(A_P_OLD_NEAR, pon, pon_s);
                 vstore<CPL>(A + A_RHO_OLD * VS, rho);
-                {
-                    WVec<CPL> pnn, pnn_s, e2;
-                    if (nleaf == 1) { pnn = p; pnn_s = ps; }
-                    else { vload<CPL>(A + A_P_NEW_NEAR * VS, pnn); sh_load(A_P_NEW_NEAR, pnn, pnn_s); }
 #pragma unroll
-                    for (int t = 0; t < CPL; ++t) e2.z[t] = rho_old.z[t] + pnn.z[t];
-                    e2.s = rho_old.s + pnn.s;
-                    persist = persist && uturn_sharp_ok<CPL>(pfar_s, pnn_s, e2);
+                for (int t = 0; t < CPL; ++t) {
+                    e2.z[t] = rho_old.z[t] + pnn.z[t];
+                    e3.z[t] = S.z[t] + pon.z[t];
                 }
-                {
-                    WVec<CPL> pon, pon_s, e3;
-                    vload<CPL>(A + A_P_OLD_NEAR * VS, pon);
-                    sh_load(A_P_OLD_NEAR, pon, pon_s);
-#pragma unroll
-                    for (int t = 0; t < CPL; ++t) e3.z[t] = S.z[t] + pon.z[t];
-                    e3.s = S.s + pon.s;
-                    persist = persist && uturn_sharp_ok<CPL>(pon_s, ps, e3);
-                }
+                e2.s = rho_old.s + pnn.s; e3.s = S.s + pon.s;
+                const bool persist = uturn3_ok<CPL>(pfar_s, ps, rho, pfar_s, pnn_s, e2, pon_s, ps, e3);
                 next = (persist && depth < sp.max_depth) ? N_DOUBLE : N_ENDTRANS;
             }
         } else if (phase == PH_GQ) {
