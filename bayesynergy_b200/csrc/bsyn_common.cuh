@@ -127,6 +127,9 @@ __device__ __forceinline__ double half_sum(double v)   // sum within each half-w
 // All shared memory is addressed through ONE dynamic array and 32-bit element offsets, so every access
 // compiles to LDS/STS (a pointer smuggled through a struct decays to a generic LD with 64-bit address math).
 extern __shared__ double smem[];
+// A warp-uniform, loop-invariant value (a shared-memory offset) the compiler must KEEP: without this ptxas
+// rematerialises the whole S2R / LDC / IMAD chain at every use (12 % of the sampler's issue slots in r01 profiles).
+__device__ __forceinline__ int pin_uniform(const int v) { return __shfl_sync(0xffffffffu, v, 0); }
 #define SMI(off) (reinterpret_cast<int *>(smem)[(off)])
 
 // Problem view in shared memory (one per CTA, shared by its warps).  Members are offsets into smem

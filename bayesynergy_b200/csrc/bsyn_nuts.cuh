@@ -237,9 +237,9 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = sp.n_problems * sp.chains;
     const int s_tri = 2 * sp.sl.tri_off;
-    const int s_pd = sp.sl.pd_off + warp * sp.sl.pd_stride;
-    const int s_pi = 2 * (sp.sl.pi_off + warp * sp.sl.pi_stride);
-    const int ws = sp.sl.ws_off + warp * C::WS_DOUBLES;
+    const int s_pd = pin_uniform(sp.sl.pd_off + warp * sp.sl.pd_stride);
+    const int s_pi = pin_uniform(2 * (sp.sl.pi_off + warp * sp.sl.pi_stride));
+    const int ws = pin_uniform(sp.sl.ws_off + warp * C::WS_DOUBLES);
     for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
     for (int e = lane; e < C::WS_DOUBLES; e += 32) smem[ws + e] = 0.0;   // the factor's upper triangle must stay zero
     double *const A = sp.arena + (long long)(blockIdx.x * NW + warp) * sp.arena_stride;
