@@ -23,8 +23,9 @@ EXPORTS = [
     "bsyn_batch_create", "bsyn_batch_destroy", "bsyn_last_error", "bsyn_version", "bsyn_num_params",
     "bsyn_num_outputs", "bsyn_max_params", "bsyn_max_outputs", "bsyn_num_problems", "bsyn_logp_grad",
     "bsyn_logp_grad_device", "bsyn_write_array", "bsyn_unconstrain", "bsyn_sampler_defaults", "bsyn_sample",
-    "bsyn_sample_device", "bsyn_ess", "bsyn_launch_count",
+    "bsyn_sample_device", "bsyn_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi",
 ]
+VI_NAMES = ["status", "eta", "iterations", "elbo", "converged", "n_grad", "n_lp", "_reserved"]
 
 
 class BsynProblem(C.Structure):
@@ -55,6 +56,21 @@ class BsynSinks(C.Structure):
                 ("qdraws", C.POINTER(C.c_double)), ("sampler_params", C.POINTER(C.c_double)),
                 ("summary", C.POINTER(C.c_double)), ("cpo_mean", C.POINTER(C.c_double)), ("ld_cpo", C.c_int64),
                 ("chain_stats", C.POINTER(C.c_double)), ("inv_metric", C.POINTER(C.c_double))]
+
+
+class BsynAdviArgs(C.Structure):
+    _fields_ = [("iter", C.c_int32), ("grad_samples", C.c_int32), ("elbo_samples", C.c_int32),
+                ("eval_elbo", C.c_int32), ("eta", C.c_double), ("adapt_engaged", C.c_int32),
+                ("adapt_iter", C.c_int32), ("tol_rel_obj", C.c_double), ("output_samples", C.c_int32),
+                ("init_r", C.c_double), ("seed", C.c_uint64)]
+
+
+class BsynAdviSinks(C.Structure):
+    _fields_ = [("mean", C.POINTER(C.c_double)), ("ld_mean", C.c_int64), ("info", C.POINTER(C.c_double)),
+                ("draws", C.POINTER(C.c_double)), ("ld_draws", C.c_int64),
+                ("udraws", C.POINTER(C.c_double)), ("ld_udraws", C.c_int64),
+                ("qdraws", C.POINTER(C.c_double)), ("summary", C.POINTER(C.c_double)),
+                ("cpo_mean", C.POINTER(C.c_double)), ("ld_cpo", C.c_int64)]
 
 
 class BsynError(RuntimeError):
@@ -95,6 +111,10 @@ def load():
     L.bsyn_sample_device.argtypes = [vp, C.POINTER(BsynSamplerArgs), C.POINTER(C.c_int64), C.POINTER(C.c_float),
                                      C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.bsyn_ess.argtypes = [vp, C.c_int32, dp, dp]
+    L.bsyn_advi_defaults.argtypes = [C.POINTER(BsynAdviArgs)]
+    L.bsyn_advi_defaults.restype = None
+    L.bsyn_advi.argtypes = [vp, C.POINTER(BsynAdviArgs), C.POINTER(BsynAdviSinks), C.POINTER(C.c_int64),
+                            C.POINTER(C.c_float)]
     L.bsyn_launch_count.restype = C.c_int64
     _LIB = L
     return L
@@ -267,6 +287,37 @@ class Batch:
         _check(load().bsyn_sample(self.h, C.byref(a), C.byref(s), C.byref(ng)), "bsyn_sample")
         res["n_grad"] = ng.value
         res["n_save"] = ns
+        return res
+
+    def advi(self, want_draws=False, want_udraws=False, want_qdraws=True, want_cpo=False, **kw):
+        """Full-rank ADVI (rstan::vb(algorithm="fullrank") defaults unless overridden in kw) for every experiment in
+        one launch.  Returns a dict of numpy arrays; `info[:, 0]` != 0 where the reference would have thrown."""
+        a = BsynAdviArgs()
+        load().bsyn_advi_defaults(C.byref(a))
+        for k, v in kw.items():
+            if not hasattr(a, k):
+                raise TypeError(f"unknown ADVI argument {k!r}")
+            setattr(a, k, v)
+        n, ns = self.n, a.output_samples
+        s = BsynAdviSinks()
+        res = {"mean": np.zeros((n, self.max_params)), "info": np.zeros((n, 8)), "summary": np.zeros((n, BSYN_NQ, 2))}
+        s.mean, s.ld_mean, s.info, s.summary = _dp(res["mean"]), self.max_params, _dp(res["info"]), _dp(res["summary"])
+        if want_draws:
+            res["draws"] = np.zeros((n, 1, ns, self.max_outputs))
+            s.draws, s.ld_draws = _dp(res["draws"]), self.max_outputs
+        if want_udraws:
+            res["udraws"] = np.zeros((n, 1, ns, self.max_params))
+            s.udraws, s.ld_udraws = _dp(res["udraws"]), self.max_params
+        if want_qdraws:
+            res["qdraws"] = np.zeros((n, 1, ns, BSYN_NQ))
+            s.qdraws = _dp(res["qdraws"])
+        if want_cpo:
+            ldc = max(self.n_obs)
+            res["cpo_mean"] = np.zeros((n, ldc))
+            s.cpo_mean, s.ld_cpo = _dp(res["cpo_mean"]), ldc
+        ne, ms = C.c_int64(), C.c_float()
+        _check(load().bsyn_advi(self.h, C.byref(a), C.byref(s), C.byref(ne), C.byref(ms)), "bsyn_advi")
+        res["n_evals"], res["kernel_ms"], res["n_save"] = ne.value, ms.value, ns
         return res
 
     def sample_device(self, **kw):

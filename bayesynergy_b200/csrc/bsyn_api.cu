@@ -623,6 +623,118 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
     return rc;
 }
 
+extern "C" void bsyn_advi_defaults(bsyn_advi_args *a)
+{
+    a->iter = 10000; a->grad_samples = 1; a->elbo_samples = 100; a->eval_elbo = 100;
+    a->eta = 1.0; a->adapt_engaged = 1; a->adapt_iter = 50; a->tol_rel_obj = 0.01;
+    a->output_samples = 1000; a->init_r = 2.0; a->seed = 1;
+}
+
+extern "C" int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *a, const bsyn_advi_sinks *sinks, int64_t *total_evals,
+                         float *elapsed_ms)
+{
+    if (!b || !a || !sinks) return fail(BSYN_ERR_ARG, "bsyn_advi: null argument");
+    if (a->iter < 1 || a->elbo_samples < 1 || a->eval_elbo < 1 || a->adapt_iter < 1 || a->output_samples < 0 ||
+        !(a->tol_rel_obj > 0) || !(a->eta > 0))
+        return fail(BSYN_ERR_ARG, "bsyn_advi: bad arguments");
+    if (a->grad_samples != 1) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_advi: grad_samples must be 1");
+    const int cb_size = (int)std::max(0.1 * a->iter / a->eval_elbo, 2.0);
+    if (cb_size > 32) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_advi: iter / eval_elbo > 320 is not supported");
+    CK(cudaSetDevice(b->device));
+    AdviParams vp{};
+    vp.n_problems = b->n;
+    vp.max_iter = a->iter; vp.elbo_samples = a->elbo_samples; vp.eval_elbo = a->eval_elbo;
+    vp.adapt_engaged = a->adapt_engaged; vp.adapt_iter = a->adapt_iter; vp.output_samples = a->output_samples;
+    vp.cb_size = cb_size; vp.eta = a->eta; vp.tol_rel_obj = a->tol_rel_obj; vp.init_r = a->init_r; vp.seed = a->seed;
+    size_t bytes = 0;
+    vp.sl = make_layout(b, true, &bytes, WPC);
+    int per_sm = 0;
+    if (bytes > 227 * 1024 || variant(b->cpl)->advi_occupancy(bytes, &per_sm) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return fail(BSYN_ERR_UNSUPPORTED, "ADVI kernel does not fit on an SM");
+    }
+    const int grid = std::max(1, std::min((b->n + WPC - 1) / WPC, per_sm * b->num_sms));
+    vp.DP = (b->maxD + 31) / 32 * 32;
+    vp.state_stride = 6LL * vp.DP + 2LL * vp.DP * vp.DP;
+    const size_t ns = (size_t)a->output_samples, nrows = (size_t)b->n * ns;
+    double *d_state = nullptr, *d_mean = nullptr, *d_info = nullptr, *d_draws = nullptr, *d_u = nullptr, *d_cpo = nullptr;
+    int rc = BSYN_OK;
+    auto cleanup = [&]() { cudaFree(d_state); cudaFree(d_mean); cudaFree(d_info); cudaFree(d_draws); cudaFree(d_u); cudaFree(d_cpo); };
+    auto alloc0 = [&](double **p, size_t n) {
+        if (cudaMalloc(p, sizeof(double) * std::max<size_t>(n, 1)) != cudaSuccess) return false;
+        return cudaMemsetAsync(*p, 0, sizeof(double) * std::max<size_t>(n, 1), b->stream) == cudaSuccess;
+    };
+    if (!alloc0(&d_state, (size_t)grid * WPC * vp.state_stride) || !alloc0(&d_mean, (size_t)b->n * b->maxD) ||
+        !alloc0(&d_info, (size_t)b->n * BSYN_NVI)) { cleanup(); return fail(BSYN_ERR_ALLOC, "bsyn_advi: device allocation failed"); }
+    if (sinks->draws) {
+        if (sinks->ld_draws < b->maxOut) { cleanup(); return fail(BSYN_ERR_ARG, "bsyn_advi: ld_draws < bsyn_max_outputs"); }
+        if (!alloc0(&d_draws, nrows * sinks->ld_draws)) { cleanup(); return fail(BSYN_ERR_ALLOC, "bsyn_advi: draws buffer does not fit on the device"); }
+        vp.draws = d_draws; vp.ld_draws = sinks->ld_draws;
+    }
+    if (sinks->udraws) {
+        if (sinks->ld_udraws < b->maxD) { cleanup(); return fail(BSYN_ERR_ARG, "bsyn_advi: ld_udraws < bsyn_max_params"); }
+        if (!alloc0(&d_u, nrows * sinks->ld_udraws)) { cleanup(); return fail(BSYN_ERR_ALLOC, "bsyn_advi: udraws buffer"); }
+        vp.udraws = d_u; vp.ld_u = sinks->ld_udraws;
+    }
+    if (sinks->cpo_mean) {
+        if (sinks->ld_cpo < b->maxN) { cleanup(); return fail(BSYN_ERR_ARG, "bsyn_advi: ld_cpo < max N"); }
+        if (!alloc0(&d_cpo, (size_t)b->n * std::max(1, b->maxN))) { cleanup(); return fail(BSYN_ERR_ALLOC, "bsyn_advi: cpo buffer"); }
+        vp.cpo_acc = d_cpo; vp.ld_cpo = b->maxN;
+    }
+    if ((rc = ensure(&b->d_qdraws, &b->qdraws_elems, std::max<size_t>(nrows, 1) * BSYN_NQ))) { cleanup(); return rc; }
+    if ((rc = ensure(&b->d_summary, &b->summary_elems, (size_t)b->n * BSYN_NQ * 2))) { cleanup(); return rc; }
+    b->last_chains = 1; b->last_nsave = a->output_samples; b->last_nskip = 0;
+    vp.state = d_state; vp.mean = d_mean; vp.ld_mean = b->maxD; vp.info = d_info; vp.qdraws = b->d_qdraws;
+    vp.work_counter = b->d_workctr; vp.grad_counter = b->d_gradctr;
+    cudaError_t e = cudaMemsetAsync(b->d_gradctr, 0, sizeof(unsigned long long), b->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_workctr, 0, sizeof(int), b->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_qdraws, 0, sizeof(double) * std::max<size_t>(nrows, 1) * BSYN_NQ, b->stream);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, b->stream);
+    if (e == cudaSuccess) {
+        e = variant(b->cpl)->advi(grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, vp);
+        ++g_launches;
+    }
+    if (e == cudaSuccess && ns > 0) {
+        const int g2 = std::max(1, std::min((b->n + WPC - 1) / WPC, b->num_sms * 8));
+        summary_kernel<<<g2, 32 * WPC, 0, b->stream>>>(b->d_qdraws, b->n, 1, a->output_samples, 0, b->d_summary);
+        ++g_launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(e1, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    float ms = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (elapsed_ms) *elapsed_ms = ms;
+    unsigned long long ng = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&ng, b->d_gradctr, sizeof(ng), cudaMemcpyDeviceToHost);
+    if (total_evals) *total_evals = (int64_t)ng;
+    if (e == cudaSuccess && sinks->mean) {
+        if (sinks->ld_mean < b->maxD) { cleanup(); return fail(BSYN_ERR_ARG, "bsyn_advi: ld_mean < bsyn_max_params"); }
+        e = cudaMemcpy2D(sinks->mean, sizeof(double) * sinks->ld_mean, d_mean, sizeof(double) * b->maxD, sizeof(double) * b->maxD, b->n, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess && sinks->info) e = cudaMemcpy(sinks->info, d_info, sizeof(double) * (size_t)b->n * BSYN_NVI, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && sinks->draws) e = cudaMemcpy(sinks->draws, d_draws, sizeof(double) * nrows * sinks->ld_draws, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && sinks->udraws) e = cudaMemcpy(sinks->udraws, d_u, sizeof(double) * nrows * sinks->ld_udraws, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && sinks->qdraws) e = cudaMemcpy(sinks->qdraws, b->d_qdraws, sizeof(double) * nrows * BSYN_NQ, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && sinks->summary) e = cudaMemcpy(sinks->summary, b->d_summary, sizeof(double) * (size_t)b->n * BSYN_NQ * 2, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && sinks->cpo_mean) {
+        std::vector<double> tmp((size_t)b->n * std::max(1, b->maxN));
+        e = cudaMemcpy(tmp.data(), d_cpo, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            for (int k = 0; k < b->n; ++k)
+                for (int n = 0; n < b->descs[k].N; ++n)
+                    sinks->cpo_mean[(size_t)k * sinks->ld_cpo + n] = tmp[(size_t)k * b->maxN + n] / std::max<size_t>(ns, 1);
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(BSYN_ERR_CUDA, std::string("bsyn_advi: ") + cudaGetErrorString(e));
+    return BSYN_OK;
+}
+
 extern "C" int bsyn_ess(bsyn_batch *b, int32_t q, double *ess, double *rhat)
 {
     if (!b || q < 0 || q >= BSYN_NQ || !ess) return fail(BSYN_ERR_ARG, "bsyn_ess: bad argument");

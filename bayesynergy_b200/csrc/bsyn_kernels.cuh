@@ -179,9 +179,23 @@ template <int CPL> struct VariantImpl {
         if (nw == 4) return nuts_occ<4, 168, false>(bytes, per_sm);
         return nuts_occ<1, 168, false>(bytes, per_sm);
     }
+    // full-rank ADVI: WPC warps (problems) per CTA
+    static cudaError_t advi(int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                            const double *dpool, const int *ipool, const int *tri, const AdviParams &vp)
+    {
+        advi_kernel<CPL, WPC><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, vp);
+        return cudaGetLastError();
+    }
+    static cudaError_t advi_occupancy(size_t bytes, int *per_sm)
+    {
+        cudaError_t e = cudaFuncSetAttribute(advi_kernel<CPL, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, advi_kernel<CPL, WPC>, 32 * WPC, bytes);
+    }
     static const VariantOps *ops()
     {
-        static const VariantOps o = {CPL, Cfg<CPL>::WS_DOUBLES, Cfg<CPL>::TR, Cfg<CPL>::NM, &logp, &write_array, &nuts, &nuts_occupancy};
+        static const VariantOps o = {CPL, Cfg<CPL>::WS_DOUBLES, Cfg<CPL>::TR, Cfg<CPL>::NM, &logp, &write_array, &nuts, &nuts_occupancy,
+                                     &advi, &advi_occupancy};
         return &o;
     }
 };

@@ -1,6 +1,6 @@
 // bsyn_kernels_decl.h -- launch tables of the compiled kernel variants (defined in bsyn_v*.cu)
 #pragma once
-#include "bsyn_nuts.cuh"
+#include "bsyn_advi.cuh"
 
 namespace bsyn {
 // launch table of one compiled variant
@@ -17,6 +17,9 @@ struct VariantOps {
     cudaError_t (*nuts)(int nw, int grid, size_t smem_bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                         const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp);
     cudaError_t (*nuts_occupancy)(int nw, int metric, size_t smem_bytes, int *per_sm);
+    cudaError_t (*advi)(int grid, size_t smem_bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+                        const double *dpool, const int *ipool, const int *tri, const AdviParams &vp);
+    cudaError_t (*advi_occupancy)(size_t smem_bytes, int *per_sm);
 };
 
 }  // namespace bsyn

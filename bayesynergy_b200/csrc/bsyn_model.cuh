@@ -442,12 +442,19 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     bool ok = true;
     if (gp) ok = gp_forward<CPL>(F, P, ws, cell, q.z, Gv);
     // ---- 5. monotherapy curves (gp_grid.stan:154-157) ---------------------------------------------
+    // gfin: the reference's reverse sweep yields NaN (0 * inf) exactly where 10^(...) overflows or where the Bliss
+    // product rounds to 0 or 1 (log(p0 / (1 - p0)) = +-inf); value and lp stay finite there.  The formulas below have
+    // finite limits, so those points are flagged and the gradient is replaced by NaN at the end -- the callers then
+    // do what Stan does with a non-finite gradient (divergent leapfrog / rejected initial point / ADVI error).
+    bool gfin = true;
     double om = 0.0, pmv = 0.0, lam = 0.0;
     if (lane < nm) {
         const bool d1 = lane < n1;
         const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
         lam = th[d1 ? SL_LA1 : SL_LA2];
-        const double Em = fast_exp(BSYN_LN10 * sl * (smem[P.xs + lane] - mm));
+        const double earg = BSYN_LN10 * sl * (smem[P.xs + lane] - mm);
+        gfin = earg <= 709.782712893384;
+        const double Em = fast_exp(earg);
         om = fast_rcp(1.0 + Em);
         pmv = fma(1.0 - lam, om, lam);
         pm[lane] = pmv;
@@ -474,6 +481,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         double f = p0, dfdG = 0.0, dfdb1 = 0.0, dfdb2 = 0.0, dfdp0 = 1.0;
         ok = ok && (p0 >= 0.0) && (p0 <= 1.0);
         if (gp) {
+            gfin = gfin && (!live || (p0 > 0.0 && q0 > 0.0));
             const double B = Gv[t];
             const double e1 = fast_exp(b1 * B), e2 = fast_exp(-b2 * B);
             const double iD1 = fast_rcp(fma(p0, e1, q0)), iD2 = fast_rcp(fma(q0, e2, p0));
@@ -713,6 +721,12 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     }
     lp_out = lp;
     ok = ok && (lp == lp);
+    if (!__all_sync(FULL, gfin)) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) g.z[t] = qnan;
+        g.s = qnan;
+    }
     return __all_sync(FULL, ok);
 }
 

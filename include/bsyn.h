@@ -183,6 +183,49 @@ int bsyn_sample_device(bsyn_batch *b, const bsyn_sampler_args *args, int64_t *to
  * qdraws of the last sampling call.  ess[n_problems], rhat[n_problems] (may be NULL).  Host pointers. */
 int bsyn_ess(bsyn_batch *b, int32_t q, double *ess, double *rhat);
 
+/* ---- full-rank ADVI: replaces rstan::vb(stanmodels$gp_grid, stan_data, algorithm = "fullrank", ...)
+ * (R/bayesynergy.R:225-231; the default method of synergyscreen, R/synergyscreen.R:90-93), i.e. the module's
+ * call_sampler with method = "variational" (src/stanExports_gp_grid.cc:15): Stan's advi::run for every problem
+ * of the batch in ONE launch.  Field names and defaults follow rstan::vb. */
+typedef struct bsyn_advi_args {
+    int32_t iter;            /* 10000: maximum number of stochastic-gradient iterations */
+    int32_t grad_samples;    /* 1 (the only supported value) */
+    int32_t elbo_samples;    /* 100 */
+    int32_t eval_elbo;       /* 100 */
+    double eta;              /* 1.0; ignored when adapt_engaged */
+    int32_t adapt_engaged;   /* 1 */
+    int32_t adapt_iter;      /* 50 */
+    double tol_rel_obj;      /* 0.01 */
+    int32_t output_samples;  /* 1000 draws from the approximate posterior */
+    double init_r;           /* 2.0 */
+    uint64_t seed;
+} bsyn_advi_args;
+
+void bsyn_advi_defaults(bsyn_advi_args *a);
+
+#define BSYN_NVI 8   /* per-problem info: status, eta, iterations, last ELBO, convergence bits, n_grad, n_lp, reserved */
+/* info[0] status: 0 ok, 1 initialisation failed, 2 initial ELBO failed, 3 all step sizes failed, 4 gradient
+ * failed, 5 ELBO failed (the reference throws an error in each of these cases -> returnCode 2).
+ * info[4] convergence bits: 1 mean ELBO converged, 2 median ELBO converged, 4 "may be diverging" was printed,
+ * 8 the maximum number of iterations was reached (the reference warns). */
+typedef struct bsyn_advi_sinks {
+    double *mean;            /* [n_problems][ld_mean] variational mean on the unconstrained scale (Stan order) */
+    int64_t ld_mean;
+    double *info;            /* [n_problems][BSYN_NVI] */
+    double *draws;           /* [n_problems][output_samples][ld_draws] write_array rows of the draws from the approximation */
+    int64_t ld_draws;
+    double *udraws;          /* [n_problems][output_samples][ld_udraws] */
+    int64_t ld_udraws;
+    double *qdraws;          /* [n_problems][output_samples][BSYN_NQ] */
+    double *summary;         /* [n_problems][BSYN_NQ][2] mean, sd over the output draws */
+    double *cpo_mean;        /* [n_problems][ld_cpo] */
+    int64_t ld_cpo;
+} bsyn_advi_sinks;
+
+/* total_evals (may be NULL): lp(+gradient) evaluations performed; elapsed_ms (may be NULL): device time. */
+int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *args, const bsyn_advi_sinks *sinks, int64_t *total_evals,
+              float *elapsed_ms);
+
 /* Number of CUDA kernel launches issued by this library so far in this process (for bench accounting). */
 int64_t bsyn_launch_count(void);
 

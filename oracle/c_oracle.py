@@ -32,9 +32,15 @@ class OrcNutsArgs(C.Structure):
                 ("save_warmup", C.c_int)]
 
 
+class OrcAdviArgs(C.Structure):
+    _fields_ = [("iter", C.c_int), ("grad_samples", C.c_int), ("elbo_samples", C.c_int), ("eval_elbo", C.c_int),
+                ("eta", C.c_double), ("adapt_engaged", C.c_int), ("adapt_iter", C.c_int), ("tol_rel_obj", C.c_double),
+                ("output_samples", C.c_int), ("init_radius", C.c_double), ("seed", C.c_uint64), ("chain_id", C.c_int)]
+
+
 def build(force=False):
     so = os.path.join(_HERE, "libgp_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("gp_oracle.c", "gp_oracle_batch.c", "gp_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("gp_oracle.c", "gp_oracle_batch.c", "gp_oracle_advi.c", "gp_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -57,6 +63,10 @@ def lib():
                                       dp, dp, C.c_int]
         L.orc_nuts_screen.restype = C.c_long
         L.orc_num_threads.restype = C.c_int
+        L.orc_advi_defaults.argtypes = [C.POINTER(OrcAdviArgs)]
+        L.orc_advi_screen.argtypes = [C.POINTER(OrcProblem), C.c_int, C.POINTER(OrcAdviArgs), C.c_int, C.c_int,
+                                      dp, dp, dp, C.c_int]
+        L.orc_advi_screen.restype = None
         _LIB = L
     return _LIB
 
@@ -143,3 +153,24 @@ def nuts_screen(problems, n_chains=4, num_warmup=1000, num_samples=1000, seed=1,
     sp = np.empty((len(problems), n_chains, num_samples, 7))
     ng = lib().orc_nuts_screen(arr, len(problems), n_chains, C.byref(a), stride, _dp(outs), _dp(sp), nthreads)
     return ng, outs, sp
+
+
+ADVI_INFO = ("status", "eta", "iterations", "elbo", "converged", "n_grad", "n_lp", "_")
+
+
+def advi_screen(problems, seed=1, want_outputs=True, nthreads=0, **kw):
+    """Full-rank ADVI (rstan::vb defaults unless overridden in kw) for a batch of problems over host threads.
+    Returns (mean_u[n, maxD], outputs[n, output_samples, max_out] or None, info[n, 8])."""
+    a = OrcAdviArgs()
+    lib().orc_advi_defaults(C.byref(a))
+    a.seed = seed
+    for k, v in kw.items():
+        setattr(a, k, v)
+    arr = (OrcProblem * len(problems))(*[p.c for p in problems])
+    ld_u = max(p.dim for p in problems)
+    stride = max(p.n_out for p in problems)
+    mean = np.full((len(problems), ld_u), np.nan)
+    outs = np.full((len(problems), a.output_samples, stride), np.nan) if want_outputs else None
+    info = np.zeros((len(problems), 8))
+    lib().orc_advi_screen(arr, len(problems), C.byref(a), ld_u, stride, _dp(mean), _dp(outs), _dp(info), nthreads)
+    return mean, outs, info

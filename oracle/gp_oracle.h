@@ -66,6 +66,29 @@ void orc_nuts_defaults(orc_nuts_args *a);
 long orc_nuts_chain(const orc_problem *p, const orc_nuts_args *a, double *draws_u, double *outputs,
                     double *sampler_params, double *final_stepsize, double *final_inv_metric);
 
+/* Full-rank ADVI (rstan::vb(algorithm = "fullrank") defaults; gp_oracle_advi.c). */
+typedef struct {
+    int iter, grad_samples, elbo_samples, eval_elbo;
+    double eta;
+    int adapt_engaged, adapt_iter;
+    double tol_rel_obj;
+    int output_samples;
+    double init_radius;
+    uint64_t seed;
+    int chain_id;
+} orc_advi_args;
+
+void orc_advi_defaults(orc_advi_args *a);
+
+/* mean_u[D], L_out[D*D] row-major (may be NULL), outputs[output_samples * n_out] write_array rows of the draws
+ * from the approximation (may be NULL), draws_u[output_samples * D] (may be NULL), info[8] = status, eta,
+ * iterations, last ELBO, convergence bits (1 mean, 2 median, 4 may-be-diverging message seen, 8 max iterations), number of
+ * gradient evaluations, number of lp evaluations, 0.
+ * status: 0 ok, 1 initialisation failed, 2 initial ELBO failed, 3 all step sizes failed, 4 gradient failed,
+ * 5 ELBO failed (the reference throws in each of these cases). */
+int orc_advi_fullrank(const orc_problem *p, const orc_advi_args *a, double *mean_u, double *L_out, double *outputs,
+                      double *draws_u, double *info);
+
 #ifdef __cplusplus
 }
 #endif

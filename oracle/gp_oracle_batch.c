@@ -107,3 +107,33 @@ long orc_nuts_screen(const orc_problem *probs, int n_prob, int n_chains, const o
     free(ng);
     return total;
 }
+
+/* ---- n_prob problems of full-rank ADVI, one problem per worker ----
+ * mean_u: [n_prob][ld_u] or NULL; outputs: [n_prob][output_samples][n_out_stride] or NULL; info: [n_prob][8]. */
+typedef struct {
+    const orc_problem *probs; const orc_advi_args *a; int ld_u, n_out_stride;
+    double *mean_u, *outputs, *info;
+} vb_ctx;
+static void vb_item(int ip, void *c)
+{
+    vb_ctx *C = (vb_ctx *)c;
+    orc_advi_args aa = *C->a;
+    aa.seed = C->a->seed + (uint64_t)ip * 7919u;
+    const orc_problem *p = &C->probs[ip];
+    int nout = orc_num_outputs(p), ns = aa.output_samples;
+    double *tmp = C->outputs ? (double *)malloc(sizeof(double) * (size_t)ns * nout) : NULL;
+    int st = orc_advi_fullrank(p, &aa, C->mean_u ? C->mean_u + (size_t)ip * C->ld_u : NULL, NULL, tmp, NULL,
+                               C->info + (size_t)ip * 8);
+    if (C->outputs) {
+        if (st == 0)
+            for (int s = 0; s < ns; ++s)
+                memcpy(C->outputs + ((size_t)ip * ns + s) * C->n_out_stride, tmp + (size_t)s * nout, sizeof(double) * nout);
+        free(tmp);
+    }
+}
+void orc_advi_screen(const orc_problem *probs, int n_prob, const orc_advi_args *a, int ld_u, int n_out_stride,
+                     double *mean_u, double *outputs, double *info, int nthreads)
+{
+    vb_ctx C = {probs, a, ld_u, n_out_stride, mean_u, outputs, info};
+    pool_run(n_prob, nthreads, vb_item, &C);
+}

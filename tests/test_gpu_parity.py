@@ -137,6 +137,33 @@ def test_heterogeneous_batch_and_status(built, datasets):
     b.close()
 
 
+def test_nonfinite_gradient_where_reference_autodiff_breaks(built, datasets):
+    """Where a monotherapy curve saturates so that the Bliss product rounds to exactly 1 (or 10^(...) overflows),
+    the reference's log(p0 / (1 - p0)) is infinite: lp stays finite but the reverse sweep is 0 * inf = NaN (Stan then
+    rejects the initial point / counts the leapfrog as divergent / aborts ADVI).  Same verdict on the GPU."""
+    sd = prepare(*datasets["mathews:ispinesib + ibrutinib"])
+    b = _lib.Batch([sd])
+    P = Problem(sd)
+    rng = np.random.default_rng(3)
+    U = rng.uniform(-0.5, 0.5, size=(6, P.dim))
+    off = 2 * sd.est_la
+    U[0, off + 4] = U[0, off + 5] = 3.5          # both slopes ~ 33: p01 = p02 = 1 at the lowest doses -> p0 == 1
+    U[0, off + 0], U[0, off + 1] = 1.0, 3.5
+    U[1, off + 4] = 3.5                          # only drug 1 saturates: p0 = p02 < 1 everywhere -> finite
+    U[1, off + 0] = 1.0
+    U[2, off + 4] = 6.0; U[2, off + 0] = -2.0    # 10^(slope (x - m)) overflows at the top dose
+    lp, g, st = b.logp_grad(U)
+    for k in range(6):
+        st_o, lp_o, g_o = P.logp_grad(U[k])
+        assert st[k] == st_o == 0
+        assert abs(lp[k] - lp_o) <= 5e-10 * max(1.0, abs(lp_o))
+        assert np.isfinite(g_o).all() == np.isfinite(g[k, :P.dim]).all(), k
+        if np.isfinite(g_o).all():
+            assert relerr(g[k, :P.dim], g_o) <= 5e-10
+    assert not np.isfinite(g[0, :P.dim]).any() and np.isfinite(g[1, :P.dim]).all() and not np.isfinite(g[2, :P.dim]).any()
+    b.close()
+
+
 def test_write_array_against_oracle(built, datasets, cond_fn):
     for dname, v in itertools.product(("mathews:ispinesib + ibrutinib", "synthetic:7", "oneil_failed:0"),
                                       (dict(), dict(type=2, heteroscedastic=False), dict(robust=True, lower_asymptotes=False))):
