@@ -56,6 +56,18 @@ def _sampler_kwargs(control, chains, iter, warmup, thin, seed):
     return kw
 
 
+_VB_ERRORS = {
+    1: "Initialization failed.",
+    2: "Cannot compute ELBO using the initial variational distribution. Your model may be either severely "
+       "ill-conditioned or misspecified.",
+    3: "All proposed step-sizes failed. Your model may be either severely ill-conditioned or misspecified.",
+    4: "stan::variational::normal_fullrank::calc_grad: The number of dropped evaluations has reached its maximum "
+       "amount (3). Your model may be either severely ill-conditioned or misspecified.",
+    5: "stan::variational::advi::calc_ELBO: The number of dropped evaluations has reached its maximum amount. "
+       "Your model may be either severely ill-conditioned or misspecified.",
+}
+
+
 def _diagnose(sp, chain_stats, qdraws, max_treedepth):
     """rstan-style warnings that make bayesynergy() set returnCode = 1 (R/bayesynergy.R:210-214)."""
     msgs = []
@@ -81,11 +93,17 @@ def _diagnose(sp, chain_stats, qdraws, max_treedepth):
 def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, lower_asymptotes=True,
                 heteroscedastic=True, bayes_factor=False, robust=False, rho=0.90, pcprior=False,
                 pcprior_hypers=(1, 0.1, 1, 0.2), lambda_=0.005, nu=1.5, method="sampling", control=None,
-                chains=4, iter=2000, warmup=None, thin=1, seed=1, device=0):
+                chains=4, iter=2000, warmup=None, thin=1, seed=1, device=0, vb=None):
     """Fit one experiment (R/bayesynergy.R:54).  Returns a dict with the fields of the R object:
-    posterior (= rstan::extract), posterior_mean, data, model, returnCode, LPML, divergent, messages."""
-    if method == "vb":
-        raise NotImplementedError("method='vb' (ADVI) is a 'next' row of the hot-path scope; use method='sampling'")
+    posterior (= rstan::extract), posterior_mean, data, model, returnCode, LPML, divergent, messages.
+
+    method="vb" runs full-rank ADVI (R/bayesynergy.R:225-231) with rstan::vb's defaults; `vb` is a dict of its
+    arguments (iter, elbo_samples, eval_elbo, eta, adapt_engaged, adapt_iter, tol_rel_obj, output_samples).  A fit
+    that rstan::vb would abort with an error raises RuntimeError here."""
+    if method not in ("sampling", "vb"):
+        raise ValueError("Method must be one of {'sampling','vb'}")
+    if method == "vb" and bayes_factor:
+        raise ValueError("bayes_factor needs method='sampling' (bridge sampling works on posterior draws)")
     sd = prepare(y, x, type=type, lower_asymptotes=lower_asymptotes, heteroscedastic=heteroscedastic, robust=robust,
                  rho=rho, pcprior=pcprior, pcprior_hypers=pcprior_hypers, lambda_=lambda_, nu=nu,
                  bayes_factor=bayes_factor, method=method)
@@ -97,7 +115,13 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
 
     b = _lib.Batch([sd], model="gp_grid", device=device)
     try:
-        res = b.sample(want_draws=True, want_udraws=bool(bayes_factor), want_cpo=True, **kw)
+        if method == "vb":
+            res = b.advi(want_draws=True, want_cpo=True, seed=seed, **(vb or {}))
+            st = int(res["info"][0, 0])
+            if st != 0:
+                raise RuntimeError("variational inference failed: " + _VB_ERRORS.get(st, f"status {st}"))
+        else:
+            res = b.sample(want_draws=True, want_udraws=bool(bayes_factor), want_cpo=True, **kw)
     finally:
         b.close()
     names = output_names(sd)
@@ -125,7 +149,8 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
     posterior["CPO"] = block("CPO[1]", N)
     for nm in ("ec50_1", "ec50_2", "dss_1", "dss_2", "rVUS_f", "rVUS_p0", "VUS_Delta", "VUS_syn", "VUS_ant"):
         posterior[nm] = flat[:, col[nm]]
-    posterior["lp__"] = res["sampler_params"][0][:, :, 6].reshape(-1)
+    posterior["lp__"] = (res["sampler_params"][0][:, :, 6].reshape(-1) if method == "sampling"
+                         else np.zeros(n_save))               # rstan::vb writes lp__ = 0
 
     # R/bayesynergy.R:245-291
     LPML = float(-np.sum(np.log(posterior["CPO"].sum(axis=0) / n_save)))
@@ -146,8 +171,11 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
                       if k not in skip}
     posterior_mean.update(f=f_mean, p0=p0_mean, Delta=Delta_mean)
 
-    messages, ndiv = _diagnose(res["sampler_params"][0], res["chain_stats"][0], res["qdraws"][0],
-                               kw.get("max_treedepth", 10))
+    if method == "sampling":
+        messages, ndiv = _diagnose(res["sampler_params"][0], res["chain_stats"][0], res["qdraws"][0],
+                                   kw.get("max_treedepth", 10))
+    else:
+        messages, ndiv = [], float("nan")
     returnCode = 1 if messages else 0
     # residual check (R/bayesynergy.R:305-314); f_mean is (n2+1) x (n1+1), as.vector is column-major
     fvec = f_mean.T.reshape(-1)
@@ -165,8 +193,12 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
                          units=units, indices=sd.ii_obs),
                model=dict(type=type, lower_asymptotes=lower_asymptotes, method=method, bayes_factor=bayes_factor,
                           heteroscedastic=heteroscedastic, robust=robust, pcprior=pcprior, lambda_=lambda_),
-               returnCode=returnCode, LPML=LPML, divergent=float("nan"),
-               sampler_params=res["sampler_params"][0], chain_stats=res["chain_stats"][0], n_grad=res["n_grad"])
+               returnCode=returnCode, LPML=LPML, divergent=float("nan"))
+    if method == "sampling":
+        obj.update(sampler_params=res["sampler_params"][0], chain_stats=res["chain_stats"][0], n_grad=res["n_grad"])
+    else:
+        obj.update(vb_info=dict(zip(_lib.VI_NAMES, res["info"][0])), vb_mean=res["mean"][0, :len(param_names(sd))],
+                   n_grad=res["n_evals"])
     if type == 3:
         obj["model"].update(nu=nu, pcprior_hypers=tuple(pcprior_hypers))
     if returnCode:
@@ -193,7 +225,7 @@ def shard_slices(n_items, world_size):
 
 def _screen_rows(experiments, offset, res, return_codes):
     rows = []
-    S = res["summary"]
+    S = np.where(res["summary"] == 0.0, np.nan, res["summary"])     # failed fits have no draws: scores are NaN, not 0/0
     for k, e in enumerate(experiments):
         dn = e.get("drug_names", ["DrugA", "DrugB"])
         m = {q: S[k, Q.index(q), 0] for q in Q}
@@ -236,6 +268,18 @@ def _fit_batch(sds, kw, device, max_treedepth):
     return res, rc
 
 
+def _fit_batch_vb(sds, vbkw, seed, device):
+    """One batched ADVI launch; returnCode 2 where rstan::vb would have stopped with an error."""
+    b = _lib.Batch(sds, model="gp_grid", device=device)
+    try:
+        res = b.advi(want_qdraws=False, seed=seed, **vbkw)
+    finally:
+        b.close()
+    rc = np.where(res["info"][:, 0] != 0, 2, 0).astype(np.int64)
+    res["chain_stats"] = np.zeros((len(sds), 1, 8))
+    return res, rc
+
+
 def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_params=None, device=0,
                   rank=0, world_size=1):
     """Fit a list of experiments (dicts with y, x and optional drug_names / experiment_ID) in one batched
@@ -243,8 +287,11 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
 
     With world_size > 1 this rank fits its contiguous shard only (shard_slices); gather the rows with
     `gather_screen` (a final all_gather, the only collective of the path).
-    Differences from the reference, on purpose: the default method is "sampling" (the GPU path; the
-    reference defaults to "vb" for speed, R/synergyscreen.R:91-93) and save_raw / save_plots do not exist.
+    method="vb" (bayesynergy_params) runs the reference's default, full-rank ADVI, with its retry rule: refit
+    whatever failed or ended with s > 1, up to max_retries more times (R/synergyscreen.R:159-167); `vb` holds
+    rstan::vb arguments.  Differences from the reference, on purpose: the default method is "sampling" (with the
+    whole screen in one launch NUTS no longer needs the ADVI shortcut, R/synergyscreen.R:91-93) and
+    save_raw / save_plots do not exist.
     """
     if isinstance(experiments, dict) and "failed" in experiments:     # rerun mode (R/synergyscreen.R:97-103)
         old = experiments.get("screenSummary", [])
@@ -254,8 +301,9 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
         return out
     params = dict(bayesynergy_params or {})
     method = params.pop("method", "sampling")
-    if method != "sampling":
-        raise NotImplementedError("synergyscreen on the GPU path supports method='sampling' only")
+    if method not in ("sampling", "vb"):
+        raise ValueError("Method must be one of {'sampling','vb'}")
+    vbkw = dict(params.pop("vb", None) or {})
     if return_samples:
         raise NotImplementedError("return_samples=TRUE: call bayesynergy() on the experiments of interest")
     control = params.pop("control", None)
@@ -272,7 +320,23 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
         except Exception:                      # tryCatch(... error = returnCode 2), R/synergyscreen.R:143-146
             rows_failed.append(k)
     rows = {}
-    if sds:
+    if sds and method == "vb":
+        res, rc = _fit_batch_vb(sds, vbkw, seed, device)
+        for r, k in zip(_screen_rows([mine[k] for k in ok_idx], 0, res, rc), ok_idx):
+            r["listID"] = lo + k + 1
+            rows[k] = r
+        bad = lambda j: rows[ok_idx[j]]["returnCode"] == 2 or not (rows[ok_idx[j]]["s"] <= 1)   # noqa: E731
+        retry = [j for j in range(len(sds)) if bad(j)]
+        tries = 0
+        while retry and tries <= max_retries:
+            res2, rc2 = _fit_batch_vb([sds[j] for j in retry], vbkw, seed + 1000 * (tries + 1), device)
+            new_rows = _screen_rows([mine[ok_idx[j]] for j in retry], 0, res2, rc2)
+            for r, j in zip(new_rows, retry):
+                r["listID"] = lo + ok_idx[j] + 1
+                rows[ok_idx[j]] = r
+            retry = [j for j in retry if bad(j)]
+            tries += 1
+    elif sds:
         ctl = _control_defaults(type_, robust, control)
         kw = _sampler_kwargs(ctl, chains, iter_, warmup, thin, seed)
         res, rc = _fit_batch(sds, kw, device, kw.get("max_treedepth", 10))

@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
     double *const St = vp.state + (long long)(blockIdx.x * NW + warp) * vp.state_stride;
     double *const mu = St, *const hmu = St + DP, *const init = St + 2 * DP, *const zeta = St + 3 * DP, *const gu = St + 4 * DP;
     double *const etav = St + 5 * DP;
-    double *const Lm = St + 6 * DP, *const Hm = Lm + (long long)DP * DP;
+    double *__restrict__ const Lm = St + 6 * DP;
+    double *__restrict__ const Hm = Lm + (long long)DP * DP;
     const bool lane_active = (F.active_mask >> lane) & 1u;
     __syncthreads();
 
@@ -149,9 +150,11 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
         double er[ES];
 #pragma unroll
         for (int s = 0; s < ES; ++s) er[s] = (lane + 32 * s < DP) ? etav[lane + 32 * s] : 0.0;
+#pragma unroll 4
         for (int i = 0; i < D; ++i) {
             const double gi = gu[i];
-            double *row = Lm + (long long)i * DP, *hrow = Hm + (long long)i * DP;
+            double *__restrict__ row = Lm + (long long)i * DP;
+            double *__restrict__ hrow = Hm + (long long)i * DP;
 #pragma unroll
             for (int s = 0; s < ES; ++s) {
                 const int j = lane + 32 * s;

@@ -6,6 +6,7 @@ import sys
 import textwrap
 
 import numpy as np
+import pytest
 
 from bayesynergy_b200.api import shard_slices, SCREEN_COLUMNS
 
@@ -57,3 +58,13 @@ def test_gather_screen_gloo_world2(tmp_path):
     out = json.load(open(tmp_path / "out.json"))
     assert [row["listID"] for row in out["screenSummary"]] == list(range(1, 12))
     assert out["failed"] == [dict(experiment_ID="bad")]
+
+
+def test_method_argument_is_validated():
+    from bayesynergy_b200.api import bayesynergy, synergyscreen
+    y = np.linspace(1, 0.2, 9)
+    x = np.array([[a, b] for a in (0.0, 1.0, 2.0) for b in (0.0, 1.0, 2.0)])
+    with pytest.raises(ValueError, match="Method must be one of"):
+        bayesynergy(y, x, method="opt")
+    with pytest.raises(ValueError, match="Method must be one of"):
+        synergyscreen([dict(y=y, x=x)], bayesynergy_params=dict(method="opt"))

@@ -98,3 +98,33 @@ def test_advi_sinks_and_options(built, datasets):
     r2 = b.advi(seed=1, iter=300, output_samples=50)
     assert r2["info"][0, 0] in (0.0, 3.0, 4.0, 5.0)
     b.close()
+
+
+def test_api_method_vb(built, datasets):
+    """bayesynergy(method="vb") and synergyscreen(method="vb") -- the reference's screen default -- end to end."""
+    from bayesynergy_b200.api import bayesynergy, synergyscreen
+    y, x = datasets["mathews:ispinesib + ibrutinib"]
+    fit = None
+    for seed in range(1, 6):                          # rstan::vb errors out now and then; so does this
+        try:
+            fit = bayesynergy(y, x, method="vb", seed=seed)
+            break
+        except RuntimeError as e:
+            assert "ill-conditioned or misspecified" in str(e)
+    assert fit is not None
+    pm = fit["posterior_mean"]
+    assert 72 < pm["rVUS_f"] < 92 and 60 < pm["rVUS_p0"] < 85 and -20 < pm["VUS_syn"] < 0
+    assert fit["posterior"]["Delta"].shape == (1000, 5, 5) and not fit["posterior"]["lp__"].any()
+    assert np.isfinite(fit["LPML"]) and fit["vb_info"]["status"] == 0 and fit["model"]["method"] == "vb"
+    with pytest.raises(ValueError):
+        bayesynergy(y, x, method="vb", bayes_factor=True)
+    exps = [dict(y=y, x=x, drug_names=["ispinesib", "ibrutinib"], experiment_ID=f"e{k}") for k in range(5)]
+    y2, x2 = datasets["mathews:canertinib + ibrutinib"]
+    exps.append(dict(y=y2, x=x2, drug_names=["canertinib", "ibrutinib"], experiment_ID="e5"))
+    out = synergyscreen(exps, bayesynergy_params=dict(method="vb", seed=3))
+    rows = out["screenSummary"]
+    assert len(rows) + len(out.get("failed", [])) == 6 and len(rows) >= 4
+    for r in rows:
+        assert r["returnCode"] == 0 and r["s"] <= 1 and np.isfinite(r["Synergy Score"])
+        if r["Drug A"] == "ispinesib":
+            assert 72 < r["Efficacy (mean)"] < 92

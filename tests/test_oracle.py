@@ -119,3 +119,24 @@ def test_oracle_nuts_reproduces_vignette_anchor(datasets):
     syn = outs[0, :, :, names.index("VUS_syn")].mean()
     assert 75 < f < 90 and 65 < p0 < 80 and -16 < syn < -5
     assert sp[..., 0].mean() > 0.7
+
+
+def test_oracle_advi_reproduces_vignette_anchor(datasets):
+    """Full-rank ADVI restatement (oracle/gp_oracle_advi.c): the vignette's example again (efficacy ~80, Bliss ~70,
+    i.e. interaction ~ -10; vignettes/Example_single.Rmd:62-65), plus the bookkeeping of advi::run."""
+    from oracle.c_oracle import advi_screen
+    sd = prepare(*datasets["mathews:ispinesib + ibrutinib"])
+    names = output_names(sd)
+    mean, outs, info = advi_screen([Problem(sd)] * 6, seed=2, iter=2000)
+    ok = info[:, 0] == 0
+    assert ok.sum() >= 4 and set(info[~ok, 0]) <= {3.0, 4.0}
+    assert set(info[ok, 1]) <= {100.0, 10.0, 1.0, 0.1, 0.01}
+    assert (info[ok, 2] <= 2000).all() and (info[ok, 2] % 100 == 0).all()
+    assert ((info[ok, 5] - info[ok, 2]) % 50 == 0).all()        # gradient evaluations: iterations + 50 per eta tried
+    f = outs[ok][:, :, names.index("rVUS_f")].mean()
+    p0 = outs[ok][:, :, names.index("rVUS_p0")].mean()
+    assert 76 < f < 90 and 64 < p0 < 82 and -16 < (p0 - f) < -3
+    assert np.isnan(outs[~ok]).all()
+    # without adaptation the given eta is used and the run ends at an ELBO check or at the cap
+    mean, outs, info = advi_screen([Problem(sd)], seed=4, iter=250, adapt_engaged=0, eta=0.1, output_samples=10)
+    assert info[0, 0] in (0.0, 4.0) and (info[0, 0] != 0 or (info[0, 1] == 0.1 and info[0, 2] in (100.0, 200.0, 250.0)))
