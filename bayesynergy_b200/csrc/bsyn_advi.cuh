@@ -10,7 +10,7 @@
 //   * one TICK = draw eta, zeta = mu + L eta (row sweep, 8 rows per butterfly), ONE lp+gradient evaluation, then the
 //     bookkeeping of whatever the evaluation was for (initial point, ELBO sample, gradient sample -> adaGrad sweep,
 //     output draw -> generated quantities).  As in the sampler there is a single copy of the model code in the
-//     kernel and the warps of a CTA run it in step.
+//     kernel.
 //   * grad_samples = 1 (rstan's default) is the only supported value: the gradient of L is then the rank-one
 //     g eta^T + diag(1 / L_ii), which the sweep forms on the fly instead of storing.
 #pragma once
@@ -27,7 +27,7 @@ struct AdviParams {
     unsigned long long seed;
     SmemLayout sl;
     int DP;                                   // row stride of L / H (multiple of 32, >= max D)
-    double *state; long long state_stride;    // per resident warp: 5 vectors [DP] + L [DP*DP] + H [DP*DP]
+    double *state; long long state_stride;    // per resident warp: 6 vectors [DP] + L [DP*DP] (double) + H [DP*DP] (float)
     // per-problem sinks (device; draws / udraws / cpo may be null)
     double *mean; int ld_mean;                // variational mean, unconstrained, Stan order
     double *info;                             // [n][8]: status, eta, iterations, last ELBO, convergence bits, n_grad, n_lp, 0
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
     double *const mu = St, *const hmu = St + DP, *const init = St + 2 * DP, *const zeta = St + 3 * DP, *const gu = St + 4 * DP;
     double *const etav = St + 5 * DP;
     double *__restrict__ const Lm = St + 6 * DP;
-    double *__restrict__ const Hm = Lm + (long long)DP * DP;
+    float *__restrict__ const Hm = reinterpret_cast<float *>(Lm + (long long)DP * DP);   // adaGrad history of L: FP32 is plenty
     const bool lane_active = (F.active_mask >> lane) & 1u;
     __syncthreads();
 
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
         for (int i = 0; i < D; ++i)
             for (int s = 0; s < ES; ++s) {
                 const int j = lane + 32 * s;
-                if (j <= i) { if (also_mu) Lm[(long long)i * DP + j] = (j == i) ? 1.0 : 0.0; Hm[(long long)i * DP + j] = 0.0; }
+                if (j <= i) { if (also_mu) Lm[(long long)i * DP + j] = (j == i) ? 1.0 : 0.0; Hm[(long long)i * DP + j] = 0.0f; }
             }
         __syncwarp();
     };
@@ -112,19 +112,24 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
         for (int s = 0; s < ES; ++s)
             if (lane + 32 * s < DP) etav[lane + 32 * s] = er[s];
         for (int i0 = 0; i0 < D; i0 += 8) {
-            double v[8];
+            // all loads of the 8-row block are issued before the first use (the sweep is DRAM-latency bound)
+            double lv[8][ES];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const int i = i0 + r;
-                double part = 0.0;
-                if (i < D) {
-                    const double *row = Lm + (long long)i * DP;
+                const double *row = Lm + (long long)i * DP;
 #pragma unroll
-                    for (int s = 0; s < ES; ++s) {
-                        const int j = lane + 32 * s;
-                        if (j <= i) part = fma(row[j], er[s], part);
-                    }
+                for (int s = 0; s < ES; ++s) {
+                    const int j = lane + 32 * s;
+                    lv[r][s] = (i < D && j <= i) ? row[j] : 0.0;
                 }
+            }
+            double v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                double part = 0.0;
+#pragma unroll
+                for (int s = 0; s < ES; ++s) part = fma(lv[r][s], er[s], part);
                 v[r] = part;
             }
             const double tot = warp_sum8(v);
@@ -150,21 +155,40 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
         double er[ES];
 #pragma unroll
         for (int s = 0; s < ES; ++s) er[s] = (lane + 32 * s < DP) ? etav[lane + 32 * s] : 0.0;
-#pragma unroll 4
-        for (int i = 0; i < D; ++i) {
-            const double gi = gu[i];
-            double *__restrict__ row = Lm + (long long)i * DP;
-            double *__restrict__ hrow = Hm + (long long)i * DP;
+        const float esf = (float)es;
+        constexpr int RB = 4;               // rows per block: RB * ES loads of L and of its history in flight per lane
+        for (int i0 = 0; i0 < D; i0 += RB) {
+            double lv[RB][ES], gi[RB];
+            float hv[RB][ES];
 #pragma unroll
-            for (int s = 0; s < ES; ++s) {
-                const int j = lane + 32 * s;
-                if (j <= i) {
-                    const double l = row[j];
-                    double gl = zero ? 0.0 : gi * er[s];
-                    if (j == i && !zero) gl += 1.0 / l;
-                    const double h = first ? hrow[j] + gl * gl : 0.9 * gl * gl + 0.1 * hrow[j];
-                    hrow[j] = h;
-                    row[j] = l + es * gl / (1.0 + sqrt(h));
+            for (int r = 0; r < RB; ++r) {
+                const int i = i0 + r;
+                gi[r] = (i < D && !zero) ? gu[i] : 0.0;
+                const double *row = Lm + (long long)i * DP;
+                const float *hrow = Hm + (long long)i * DP;
+#pragma unroll
+                for (int s = 0; s < ES; ++s) {
+                    const int j = lane + 32 * s;
+                    const bool in = i < D && j <= i;
+                    lv[r][s] = in ? row[j] : 1.0;
+                    hv[r][s] = in ? hrow[j] : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int i = i0 + r;
+#pragma unroll
+                for (int s = 0; s < ES; ++s) {
+                    const int j = lane + 32 * s;
+                    if (i < D && j <= i) {
+                        const double l = lv[r][s];
+                        double gl = gi[r] * er[s];
+                        if (j == i && !zero) gl += 1.0 / l;
+                        const float gf = (float)gl;
+                        const float h = first ? fmaf(gf, gf, hv[r][s]) : fmaf(0.9f * gf, gf, 0.1f * hv[r][s]);
+                        Hm[(long long)i * DP + j] = h;
+                        Lm[(long long)i * DP + j] = fma(gl, (double)__fdividef(esf, 1.0f + sqrtf(h)), l);
+                    }
                 }
             }
         }
@@ -203,7 +227,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
     };
 
     for (;;) {
-        if (__syncthreads_and(stage == VS_DONE)) break;
+        if (stage == VS_DONE) break;        // warps run free: the ticks are dominated by the sweeps over L, not by code fetch
         if (stage == VS_FETCH) {
             int item = 0;
             if (lane == 0) item = atomicAdd(vp.work_counter, 1);

@@ -655,7 +655,7 @@ extern "C" int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *a, const bsyn_advi
     }
     const int grid = std::max(1, std::min((b->n + WPC - 1) / WPC, per_sm * b->num_sms));
     vp.DP = (b->maxD + 31) / 32 * 32;
-    vp.state_stride = 6LL * vp.DP + 2LL * vp.DP * vp.DP;
+    vp.state_stride = 6LL * vp.DP + (3LL * vp.DP * vp.DP) / 2;   // 6 vectors + L (double) + its adaGrad history (float)
     const size_t ns = (size_t)a->output_samples, nrows = (size_t)b->n * ns;
     double *d_state = nullptr, *d_mean = nullptr, *d_info = nullptr, *d_draws = nullptr, *d_u = nullptr, *d_cpo = nullptr;
     int rc = BSYN_OK;
