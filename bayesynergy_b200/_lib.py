@@ -23,7 +23,7 @@ EXPORTS = [
     "bsyn_batch_create", "bsyn_batch_destroy", "bsyn_last_error", "bsyn_version", "bsyn_num_params",
     "bsyn_num_outputs", "bsyn_max_params", "bsyn_max_outputs", "bsyn_num_problems", "bsyn_logp_grad",
     "bsyn_logp_grad_device", "bsyn_write_array", "bsyn_unconstrain", "bsyn_sampler_defaults", "bsyn_sample",
-    "bsyn_sample_device", "bsyn_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi",
+    "bsyn_sample_device", "bsyn_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare",
 ]
 VI_NAMES = ["status", "eta", "iterations", "elbo", "converged", "n_grad", "n_lp", "_reserved"]
 
@@ -111,6 +111,8 @@ def load():
     L.bsyn_sample_device.argtypes = [vp, C.POINTER(BsynSamplerArgs), C.POINTER(C.c_int64), C.POINTER(C.c_float),
                                      C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.bsyn_ess.argtypes = [vp, C.c_int32, dp, dp]
+    i32p = C.POINTER(C.c_int32)
+    L.bsyn_prepare.argtypes = [dp, dp, C.c_int32, C.c_int32, dp, i32p, dp, i32p, dp, ip, i32p, i32p, i32p]
     L.bsyn_advi_defaults.argtypes = [C.POINTER(BsynAdviArgs)]
     L.bsyn_advi_defaults.restype = None
     L.bsyn_advi.argtypes = [vp, C.POINTER(BsynAdviArgs), C.POINTER(BsynAdviSinks), C.POINTER(C.c_int64),
@@ -142,6 +144,26 @@ def options_from(sd, model="gp_grid") -> BsynOptions:
         o.pcprior_hypers[k] = float(sd.pcprior_hypers[k])
     o.rho, o.lambda_ = sd.rho, sd.lambda_
     return o
+
+
+def prepare_native(y, x):
+    """bsyn_prepare: (x1, x2, y_obs, ii_obs, nrep, nmissing) from y [n] or [n, nrep] (NaN = missing) and x [n, 2]."""
+    y = np.asarray(y, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if y.ndim == 1:
+        y = y[:, None]
+    n, nrep = y.shape
+    yc = np.ascontiguousarray(y.T)                   # column-major: replicate r of row i at [r * n + i]
+    x1, x2 = np.empty(n), np.empty(n)
+    yo, io = np.empty(n * nrep), np.empty(n * nrep, dtype=np.int32)
+    n1, n2, N, nr, nm = (C.c_int32() for _ in range(5))
+    rc = load().bsyn_prepare(_dp(yc), _dp(x), n, nrep, _dp(x1), C.byref(n1), _dp(x2), C.byref(n2), _dp(yo),
+                             io.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(N), C.byref(nr), C.byref(nm))
+    if rc == 5:
+        raise ValueError("Missing monotherapy data! Make sure 'x' contains zero concentrations")
+    if rc != 0:
+        raise ValueError("bsyn_prepare: invalid concentrations")
+    return x1[:n1.value].copy(), x2[:n2.value].copy(), yo[:N.value].copy(), io[:N.value].copy(), nr.value, nm.value
 
 
 class Batch:

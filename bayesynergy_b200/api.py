@@ -106,7 +106,7 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
         raise ValueError("bayes_factor needs method='sampling' (bridge sampling works on posterior draws)")
     sd = prepare(y, x, type=type, lower_asymptotes=lower_asymptotes, heteroscedastic=heteroscedastic, robust=robust,
                  rho=rho, pcprior=pcprior, pcprior_hypers=pcprior_hypers, lambda_=lambda_, nu=nu,
-                 bayes_factor=bayes_factor, method=method)
+                 bayes_factor=bayes_factor, method=method, native=True)
     control = _control_defaults(type, robust, control)
     kw = _sampler_kwargs(control, chains, iter, warmup, thin, seed)
     drug_names = list(drug_names) if drug_names is not None else ["Drug1", "Drug2"]
@@ -315,7 +315,7 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
     sds, ok_idx, rows_failed = [], [], []
     for k, e in enumerate(mine):
         try:
-            sds.append(prepare(e["y"], e["x"], **params))
+            sds.append(prepare(e["y"], e["x"], native=True, **params))
             ok_idx.append(k)
         except Exception:                      # tryCatch(... error = returnCode 2), R/synergyscreen.R:143-146
             rows_failed.append(k)

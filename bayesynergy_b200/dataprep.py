@@ -69,8 +69,12 @@ class StanData:
 
 def prepare(y, x, type=3, lower_asymptotes=True, heteroscedastic=True, robust=False, rho=0.90,
             pcprior=False, pcprior_hypers=(1, 0.1, 1, 0.2), lambda_=0.005, nu=1.5,
-            bayes_factor=False, method="sampling") -> StanData:
+            bayes_factor=False, method="sampling", native=False) -> StanData:
     """R/bayesynergy.R:54-200 up to (not including) the sampler call.
+
+    native=True does the grid / ii_obs / missing-value work (R/bayesynergy.R:129-154) in libbsyn's bsyn_prepare
+    (what api.bayesynergy / api.synergyscreen use); native=False is the numpy statement of the same steps that the
+    CPU-only tests use.
 
     `y`: [n] vector or [n, nrep] matrix (NaN = missing).  `x`: [n, 2] concentrations
     (zero = monotherapy).  Error messages follow the reference's `stop()` texts.
@@ -104,6 +108,13 @@ def prepare(y, x, type=3, lower_asymptotes=True, heteroscedastic=True, robust=Fa
         raise ValueError("Missing monotherapy data! Make sure 'x' contains zero concentrations")
     if bayes_factor and method != "sampling":
         raise ValueError("Computing the Bayes factor requires method = 'sampling')")
+
+    if native:
+        from . import _lib
+        unq1, unq2, yv, ii_obs, nrep, nmissing = _lib.prepare_native(y, x)
+        n1, n2 = len(unq1), len(unq2)
+        return _finish(unq1, unq2, n1, n2, yv, ii_obs, nrep, nmissing, type, nu, lower_asymptotes, robust, pcprior,
+                       heteroscedastic, pcprior_hypers, rho, lambda_)
 
     # R/bayesynergy.R:129-137
     with np.errstate(divide="ignore"):
@@ -142,6 +153,12 @@ def prepare(y, x, type=3, lower_asymptotes=True, heteroscedastic=True, robust=Fa
         nmissing = ngrid * nrep - ii_obs.shape[0]
         yv = yv[keep]
 
+    return _finish(unq1, unq2, n1, n2, yv, ii_obs, nrep, nmissing, type, nu, lower_asymptotes, robust, pcprior,
+                   heteroscedastic, pcprior_hypers, rho, lambda_)
+
+
+def _finish(unq1, unq2, n1, n2, yv, ii_obs, nrep, nmissing, type, nu, lower_asymptotes, robust, pcprior,
+            heteroscedastic, pcprior_hypers, rho, lambda_) -> StanData:
     kernel, nu_matern, est_alpha = KERNEL_MATERN, 2, 0
     if type == 2:
         kernel, nu_matern, est_alpha = KERNEL_RBF, 0, 0

@@ -210,7 +210,8 @@ def run_ours(args):
     d2h = 8 * (args.combos * 12 * 2 + args.combos * args.chains * 8)
     # ---- reduce over ranks -------------------------------------------------------------------------
     stats = torch.tensor([tot_ms, float(tot_grad), wall, float(np.nansum(ess)), float(np.sum(e2e_grad)),
-                          float(np.sum(e2e_t)), float(np.isnan(ess).sum()), float(launches)], dtype=torch.float64, device="cuda")
+                          float(np.sum(e2e_t)), float(np.isnan(ess).sum()), float(launches),
+                          float((ess >= 400).sum())], dtype=torch.float64, device="cuda")
     mx = stats.clone()
     sm = stats.clone()
     if world > 1:
@@ -238,6 +239,9 @@ def run_ours(args):
             "ess_per_sec_per_combo": float(sm[3] / n_combo_total / step_time),
             "total_ess_per_sec": float(sm[3] / step_time),
             "ess_min_syn_ant_mean": float(sm[3] / n_combo_total), "ess_nan_combos": int(sm[6]),
+            # time until every combination of the step has ESS >= 400 -- the step itself when all do
+            "ess_ge_400_frac": float(sm[8] / n_combo_total),
+            "time_to_ess400_all_s": float(step_time) if int(sm[8]) == n_combo_total else None,
             "grad_evals_per_step": sm[1] / args.steps,
             "wall_s_timed_region": float(mx[2]),
             "e2e": {"value": e2e_value, "unit": "grad evals/s", "h2d_bytes_per_step": h2d_bytes(sds),
@@ -250,7 +254,11 @@ def run_ours(args):
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          "flop_per_eval": FLOP_PER_EVAL, "per_gpu": True,
                          "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "note": "state is on-chip; HBM is not the bound"},
-                         "traffic": None},
+                         # DRAM bytes of one sampler launch: 13.3 B per gradient evaluation (dram__bytes_read.sum +
+                         # dram__bytes_write.sum of the ncu --set full capture in profiles/r01_nuts_v6_summary.txt)
+                         # x the evaluations of one launch; the algorithmic figure is ~0 (state is resident)
+                         "traffic": 13.3 * sm[1] / args.steps / world,
+                         "traffic_unit": "bytes per launch (extrapolated from a 444-combination ncu capture)"},
         }
         if world == 1 and not args.no_cpu:
             from oracle.c_oracle import lib

@@ -29,7 +29,8 @@ enum {
     BSYN_ERR_ARG = 1,        /* invalid argument / inconsistent sizes */
     BSYN_ERR_UNSUPPORTED = 2,/* grid too large for the compiled kernel variants, etc. */
     BSYN_ERR_CUDA = 3,       /* CUDA runtime error or no device */
-    BSYN_ERR_ALLOC = 4
+    BSYN_ERR_ALLOC = 4,
+    BSYN_ERR_DOMAIN = 5      /* bsyn_prepare: monotherapy (zero-concentration) rows are missing */
 };
 
 enum { BSYN_MODEL_GP_GRID = 0, BSYN_MODEL_NOINTERACTION = 1 };
@@ -182,6 +183,16 @@ int bsyn_sample_device(bsyn_batch *b, const bsyn_sampler_args *args, int64_t *to
  * as rstan::summary's n_eff) of generated scalar `q` for every problem, computed on the device from the
  * qdraws of the last sampling call.  ess[n_problems], rhat[n_problems] (may be NULL).  Host pointers. */
 int bsyn_ess(bsyn_batch *b, int32_t q, double *ess, double *rhat);
+
+/* ---- data preparation in native code: R/bayesynergy.R:129-154 (the step before the path; no GPU involved).
+ * y: [n x nrep_in] column-major (replicate r of row i at y[i + r n]), NaN = missing.  x: [n x 2] row-major
+ * concentrations (0 = monotherapy).  Outputs (caller-allocated): x1_out[>= n], x2_out[>= n] log10 dose levels,
+ * y_out / ii_out [>= n nrep_in] the non-missing observations and their 1-based positions in the column-major
+ * (n2+1) x (n1+1) grid, and the sizes.  nrep_in == 1: replicates are repeated rows and nrep = the largest
+ * multiplicity (R/bayesynergy.R:149-154).  Returns BSYN_ERR_DOMAIN when a drug has no zero concentration. */
+int bsyn_prepare(const double *y, const double *x, int32_t n, int32_t nrep_in, double *x1_out, int32_t *n1_out,
+                 double *x2_out, int32_t *n2_out, double *y_out, int32_t *ii_out, int32_t *N_out,
+                 int32_t *nrep_out, int32_t *nmissing_out);
 
 /* ---- full-rank ADVI: replaces rstan::vb(stanmodels$gp_grid, stan_data, algorithm = "fullrank", ...)
  * (R/bayesynergy.R:225-231; the default method of synergyscreen, R/synergyscreen.R:90-93), i.e. the module's
