@@ -144,7 +144,8 @@ static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t
     const int nblk = per_warp_problem ? warps : 1;
     sl.pi_off = sl.pd_off + nblk * sl.pd_stride;
     sl.ws_off = even(sl.pi_off + nblk * sl.pi_stride);
-    *bytes = sizeof(double) * (size_t)(sl.ws_off + warps * variant(b->cpl)->ws_doubles);
+    sl.park_off = even(sl.ws_off + warps * variant(b->cpl)->ws_doubles);
+    *bytes = sizeof(double) * (size_t)(sl.park_off + warps * PARK_DOUBLES);
     return sl;
 }
 

@@ -21,7 +21,9 @@ namespace bsyn {
 // shared-memory layout (offsets in doubles), computed on the host from the batch maxima
 struct SmemLayout {
     int tri_off, pd_off, pi_off, ws_off, pd_stride, pi_stride;   // *_stride: per-warp problem blocks (logp kernel)
+    int park_off;                                                // sampler: per-warp parking area (PARK_DOUBLES each)
 };
+constexpr int PARK_DOUBLES = 48;   // 30 doubles + 24 ints + slack: warp-uniform chain state parked during an evaluation
 
 struct SamplerParams {
     int n_problems, chains;
@@ -50,7 +52,9 @@ struct SamplerParams {
 };
 
 enum ArenaSlot {
-    A_OQ = 0, A_OP, A_OG, A_SQ, A_SG, A_PQ, A_PG, A_RHO_OLD, A_P_OLD_NEAR, A_P_NEW_NEAR, A_WM, A_WM2, A_PREV, A_LVL
+    A_OQ = 0, A_OP, A_OG, A_SQ, A_SG, A_PQ, A_PG, A_RHO_OLD, A_P_OLD_NEAR, A_P_NEW_NEAR, A_WM, A_WM2, A_PREV,
+    A_PARK_S, A_PARK_PREV, A_PARK_MINV,   // chain vectors parked in the arena while the evaluation runs
+    A_LVL
 };
 __host__ __device__ inline int arena_vectors(int max_depth) { return A_LVL + 3 * (max_depth > 2 ? max_depth - 1 : 1); }
 
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     const int s_pd = pin_uniform(sp.sl.pd_off + warp * sp.sl.pd_stride);
     const int s_pi = pin_uniform(2 * (sp.sl.pi_off + warp * sp.sl.pi_stride));
     const int ws = pin_uniform(sp.sl.ws_off + warp * C::WS_DOUBLES);
+    const int s_park = pin_uniform(sp.sl.park_off + warp * PARK_DOUBLES);
     for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
     for (int e = lane; e < C::WS_DOUBLES; e += 32) smem[ws + e] = 0.0;   // the factor's upper triangle must stay zero
     double *const A = sp.arena + (long long)(blockIdx.x * NW + warp) * sp.arena_stride;
@@ -478,8 +483,46 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 rng_u2(rk, RT_GQ, 0xFFu, it, 0, gq.uz[0], gq.uz[1]);
                 rng_u2(rk, RT_GQ, 0xFFu, it, 1, gq.uz[2], gq.uz[3]);
             }
+            // Warp-uniform chain scalars (60+ registers replicated in every lane) go to shared memory for the
+            // duration of the evaluation, whose schedule is register-starved otherwise (profiles/: the same kernel
+            // with 255 registers runs each warp 1.45x faster).
+#define BSYN_PARK_D(X) X(eps) X(mu) X(sbar) X(xbar) X(cnt) X(wn) X(n_div) X(n_maxd) X(nleap_tot) X(nleap_samp) X(acc_sum) \
+    X(n_samp_it) X(is_H0) X(is_V0) X(eps_try) X(e_used) X(H0) X(otherV) X(sampleV) X(sampleH) X(proposeV) X(proposeH)    \
+    X(lsw) X(summetro) X(lsw_sub) X(u_leaf) X(info.accept) X(info.energy)
+#define BSYN_PARK_I(X) X(it) X(isave) X(win_size) X(win_end) X(init_try) X(is_it) X(is_dir) X(curdir) X(depth) X(nleap) \
+    X(k) X(nleaf) X(info.depth) X(info.nleap) X(info.divergent)
+            {
+                int o = s_park;
+#define BSYN_ST(v) smem[o++] = v;
+                BSYN_PARK_D(BSYN_ST)
+#undef BSYN_ST
+                o = 2 * (s_park + 30);
+#define BSYN_ST(v) SMI(o++) = v;
+                BSYN_PARK_I(BSYN_ST)
+#undef BSYN_ST
+                SMI(o++) = (int)need_istep; SMI(o++) = (int)divergent; SMI(o++) = (int)istep_tag;
+            }
+            // The evaluation needs every register it can get; S, pprev and minv are dead weight across it.  Parking
+            // them in the arena (L2-resident, coalesced) beats the compiler's choice of what to spill.
+            vstore<CPL>(A + A_PARK_S * VS, S); vstore<CPL>(A + A_PARK_PREV * VS, pprev);
+            if constexpr (!DENSE) vstore<CPL>(A + A_PARK_MINV * VS, minv);
             double lp;
             const bool okv = warp_logp_grad<CPL, false>(F, P, ws, cell, q, sp.jacobian, lp, g, nullptr, gq);
+            vload<CPL>(A + A_PARK_S * VS, S); vload<CPL>(A + A_PARK_PREV * VS, pprev);
+            if constexpr (!DENSE) vload<CPL>(A + A_PARK_MINV * VS, minv);
+            {
+                int o = s_park;
+#define BSYN_LD(v) v = smem[o++];
+                BSYN_PARK_D(BSYN_LD)
+#undef BSYN_LD
+                o = 2 * (s_park + 30);
+#define BSYN_LD(v) v = SMI(o++);
+                BSYN_PARK_I(BSYN_LD)
+#undef BSYN_LD
+                need_istep = SMI(o++) != 0; divergent = SMI(o++) != 0; istep_tag = (uint32_t)SMI(o++);
+            }
+#undef BSYN_PARK_D
+#undef BSYN_PARK_I
             if (!gq.on) ++ngrad;
             if (!okv || !(fabs(lp) < INFINITY)) {   // domain error in the reference => infinite potential
                 V = INFINITY;
