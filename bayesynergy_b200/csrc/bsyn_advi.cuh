@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
     const int s_pd = pin_uniform(vp.sl.pd_off + warp * vp.sl.pd_stride);
     const int s_pi = pin_uniform(2 * (vp.sl.pi_off + warp * vp.sl.pi_stride));
     const int ws = pin_uniform(vp.sl.ws_off + warp * C::WS_DOUBLES);
+    const int s_gq = pin_uniform(vp.sl.park_off + warp * PARK_DOUBLES + PARK_GQ);
     for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
     for (int e = lane; e < C::WS_DOUBLES; e += 32) smem[ws + e] = 0.0;   // the factor's upper triangle must stay zero
     const int DP = vp.DP;
@@ -268,16 +269,14 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
         // ---- the one evaluation of this tick ----
         GQ gq;
         gq.on = (stage == VS_DRAW);
-        gq.D = pd.D; gq.yglob = yglob; gq.iiglob = iiglob;
-        gq.row = nullptr; gq.qout = nullptr; gq.cpo_acc = nullptr;
-        gq.uz[0] = gq.uz[1] = gq.uz[2] = gq.uz[3] = 0.5;
+        gq.so = s_gq;
         if (gq.on) {
             const long long rowi = (long long)ip * vp.output_samples + idraw;
-            gq.row = vp.draws ? vp.draws + rowi * vp.ld_draws : nullptr;
-            gq.qout = vp.qdraws ? vp.qdraws + rowi * 12 : nullptr;
-            gq.cpo_acc = cpo_acc;
-            rng_u2(rk, RT_GQ, 0xFFu, (uint32_t)idraw, 0, gq.uz[0], gq.uz[1]);
-            rng_u2(rk, RT_GQ, 0xFFu, (uint32_t)idraw, 1, gq.uz[2], gq.uz[3]);
+            double uz[4];
+            rng_u2(rk, RT_GQ, 0xFFu, (uint32_t)idraw, 0, uz[0], uz[1]);
+            rng_u2(rk, RT_GQ, 0xFFu, (uint32_t)idraw, 1, uz[2], uz[3]);
+            gq_publish(gq.so, pd.D, yglob, iiglob, uz, vp.draws ? vp.draws + rowi * vp.ld_draws : nullptr,
+                       vp.qdraws ? vp.qdraws + rowi * 12 : nullptr, cpo_acc);
             if (vp.udraws) store_user_vec<CPL>(F, pd, cell, q, vp.udraws + rowi * vp.ld_u);
         }
         double lp;

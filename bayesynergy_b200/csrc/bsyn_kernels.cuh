@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const Pro
         load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
         double lpv;
         GQ gq{};
-        gq.on = false;
+        gq.on = false; gq.so = 0;
         const bool ok = warp_logp_grad<CPL, DBG>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr, gq);
         if (!ok) {
             lpv = -INFINITY;
@@ -96,13 +96,13 @@ __global__ void __launch_bounds__(32 * WPC) write_array_kernel(const Flags F, co
         RngKey rk;
         rk.k0 = (uint32_t)seed; rk.k1 = (uint32_t)(seed >> 32); rk.chain = (uint32_t)pt;
         GQ gq{};
-        gq.on = true;
-        gq.D = pd.D;
-        gq.yglob = dpool + pd.off_d + pool_y_off(pd);
-        gq.iiglob = ipool + pd.off_i + pool_ii_off(pd);
-        rng_u2(rk, RT_GQ, 0xFFu, 0, 0, gq.uz[0], gq.uz[1]);
-        rng_u2(rk, RT_GQ, 0xFFu, 0, 1, gq.uz[2], gq.uz[3]);
-        gq.row = out + (size_t)pt * ldo; gq.qout = nullptr; gq.cpo_acc = nullptr;
+        gq.on = true; gq.so = sl.park_off + warp * PARK_DOUBLES + PARK_GQ;
+        double uz[4];
+        rng_u2(rk, RT_GQ, 0xFFu, 0, 0, uz[0], uz[1]);
+        rng_u2(rk, RT_GQ, 0xFFu, 0, 1, uz[2], uz[3]);
+        __syncwarp();
+        gq_publish(gq.so, pd.D, dpool + pd.off_d + pool_y_off(pd), ipool + pd.off_i + pool_ii_off(pd), uz,
+                   out + (size_t)pt * ldo, nullptr, nullptr);
         WVec<CPL> gtmp;
         double lpv;
         const bool ok = warp_logp_grad<CPL, false>(F, P, ws, cell, q, 1, lpv, gtmp, nullptr, gq);

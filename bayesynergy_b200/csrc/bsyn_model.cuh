@@ -345,12 +345,29 @@ __device__ __forceinline__ double lik_cell_normal(const Flags &F, const ProbS &P
 // sampler kernel -- its instruction footprint is what bounds the sampler (profiles/).
 struct GQ {
     bool on;
-    int D;                    // number of unconstrained parameters of this problem
-    const double *yglob;      // y[N] in original order (global memory)
-    const int *iiglob;        // 0-based f index of every observation, original order
-    double uz[4];             // U(0,1) draws for the zero-VUS replacement (gp_grid.stan:294-297)
-    double *row, *qout, *cpo_acc;
+    int so;   // offset (doubles) of the sink block in shared memory, see GqSlot; read only where gq.on
 };
+// The sinks live in a small shared-memory block written by the caller (gq_publish) instead of in the struct: as
+// struct members they would occupy ~25 registers through every evaluation, 99 % of which have gq.on == false.
+enum GqSlot { GQS_ROW = 0, GQS_QOUT, GQS_CPO, GQS_Y, GQS_II, GQS_UZ = 5 /* 4 doubles */, GQS_D = 9, GQ_DOUBLES = 10 };
+__device__ __forceinline__ void gq_publish(const int so, const int D, const double *yglob, const int *iiglob,
+                                           const double (&uz)[4], double *row, double *qout, double *cpo_acc)
+{
+    // every lane stores the same values to the same addresses
+    smem[so + GQS_ROW] = __longlong_as_double((long long)row);
+    smem[so + GQS_QOUT] = __longlong_as_double((long long)qout);
+    smem[so + GQS_CPO] = __longlong_as_double((long long)cpo_acc);
+    smem[so + GQS_Y] = __longlong_as_double((long long)yglob);
+    smem[so + GQS_II] = __longlong_as_double((long long)iiglob);
+    smem[so + GQS_UZ] = uz[0]; smem[so + GQS_UZ + 1] = uz[1]; smem[so + GQS_UZ + 2] = uz[2]; smem[so + GQS_UZ + 3] = uz[3];
+    SMI(2 * (so + GQS_D)) = D;
+    __syncwarp();
+}
+template <class T> __device__ __forceinline__ T *gq_ptr(const GQ &gq, const int k)
+{
+    return reinterpret_cast<T *>(__double_as_longlong(smem[gq.so + k]));
+}
+__device__ __forceinline__ int gq_D(const GQ &gq) { return SMI(2 * (gq.so + GQS_D)); }
 
 // ---------------------------------------------------------------------------------------------------
 // lp(u) and d lp / d u for one (problem, point), cooperatively on one warp.
@@ -381,9 +398,10 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     double e;
     const double thv = constrain_slot(F, u, ws + C::OFF_TH, ws + C::OFF_UR, e);
     const int npre = 2 * F.est_la + 6 + (gp ? 4 + F.est_alpha : 0);
-    if (gq.on && gq.row && act) {   // constrained parameters in declaration order
-        const int pos = (lane < SL_M1) ? lane : (lane <= SL_ALPHA) ? lane - (F.est_la ? 0 : 2) : gq.D - 3 + (lane - SL_S);
-        gq.row[pos] = thv;
+    if (gq.on && act) {   // constrained parameters in declaration order
+        double *const row = gq_ptr<double>(gq, GQS_ROW);
+        const int pos = (lane < SL_M1) ? lane : (lane <= SL_ALPHA) ? lane - (F.est_la ? 0 : 2) : gq_D(gq) - 3 + (lane - SL_S);
+        if (row) row[pos] = thv;
     }
     double lpl = 0.0;   // lane-local part of lp
     double tb = 0.0;    // d lp / d(constrained scalar of this lane)
@@ -468,8 +486,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     double b1bar = 0.0, b2bar = 0.0, slogbar = 0.0, vprod = 1.0;
     // generated quantities (only when gq.on): output offsets, VUS accumulators, f on its (n2+1) x (n1+1) grid
     const int G = P.G;
-    const int o_p0 = gq.D, o_p01 = o_p0 + G, o_delta = o_p01 + nm, o_gp = o_delta + G;
-    const int o_ec = gp ? o_gp + G : o_delta, o_cpo = o_ec + 2, o_dss = o_cpo + P.N, o_vus = o_dss + 2;
+    // row layout: [params D][p0 G][p01 n1][p02 n2][Delta G][GP G][ec50 2][CPO N][dss 2][VUS 2 (+3)]
     double *const fg = Lb1;   // (n2+1)(n1+1) <= 2 NN doubles: spans Lb1..Lb2, both free until the adjoint products
     double vus[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -498,7 +515,11 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
             if (gq.on && live) {
                 const double w = smem[P.vw + j] * smem[P.vw + n1 + i];
                 vus[2] = fma(w, Delta, vus[2]); vus[3] = fma(w, fmin(Delta, 0.0), vus[3]); vus[4] = fma(w, fmax(Delta, 0.0), vus[4]);
-                if (gq.row) { const int c = lane + 32 * t; gq.row[npre + c] = q.z[t]; gq.row[o_delta + c] = Delta; gq.row[o_gp + c] = B; }
+                double *const row = gq_ptr<double>(gq, GQS_ROW);
+                if (row) {
+                    const int c = lane + 32 * t, o_delta = gq_D(gq) + G + nm;
+                    row[npre + c] = q.z[t]; row[o_delta + c] = Delta; row[o_delta + G + c] = B;
+                }
             }
         }
         const int fc = (i + 1) + (j + 1) * (n2 + 1);
@@ -506,7 +527,8 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
             const double w = smem[P.vw + j] * smem[P.vw + n1 + i];
             vus[0] = fma(w, 1.0 - f, vus[0]); vus[1] = fma(w, 1.0 - p0, vus[1]);
             fg[fc] = f;
-            if (gq.row) gq.row[o_p0 + lane + 32 * t] = p0;
+            double *const row = gq_ptr<double>(gq, GQS_ROW);
+            if (row) row[gq_D(gq) + lane + 32 * t] = p0;
         }
         double fbar;
         if (!F.robust) fbar = lik_cell_normal(F, P, fc, f, is2, live, lpl, slogbar, vprod, ok);
@@ -523,24 +545,31 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         pmbar = lik_cell(F, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, vprod, ok);
         if (gq.on) {
             fg[fc] = lane < nm ? pmv : 1.0;
-            if (gq.row && lane < nm) gq.row[o_p01 + lane] = pmv;   // p01 then p02 are contiguous
+            double *const row = gq_ptr<double>(gq, GQS_ROW);
+            if (row && lane < nm) row[gq_D(gq) + G + lane] = pmv;   // p01 then p02 are contiguous
         }
     }
     if (F.het) lpl += -0.5 * fast_log(vprod);
     if (gq.on) {
         __syncwarp();
+        double *const row = gq_ptr<double>(gq, GQS_ROW), *const qout = gq_ptr<double>(gq, GQS_QOUT);
+        double *const cpo_acc = gq_ptr<double>(gq, GQS_CPO);
+        const double *const yglob = gq_ptr<const double>(gq, GQS_Y);
+        const int *const iiglob = gq_ptr<const int>(gq, GQS_II);
+        const int o_delta = gq_D(gq) + G + nm, o_ec = gp ? o_delta + 2 * G : o_delta, o_cpo = o_ec + 2;
+        const int o_dss = o_cpo + P.N, o_vus = o_dss + 2;
         const double vr = warp_sum8(vus);                       // lane L holds the total of vus[L & 7]
         double v_f = __shfl_sync(FULL, vr, 0), v_p0 = __shfl_sync(FULL, vr, 1), v_d = __shfl_sync(FULL, vr, 2);
         double v_syn = __shfl_sync(FULL, vr, 3), v_ant = __shfl_sync(FULL, vr, 4);
         // CPO (always the Normal density, even when robust: gp_grid.stan:264-270)
-        if (gq.row || gq.cpo_acc) {
+        if (row || cpo_acc) {
             for (int n = lane; n < P.N; n += 32) {
-                const double fv = fg[gq.iiglob[n]];
+                const double fv = fg[iiglob[n]];
                 const double sd = F.het ? s * sqrt(fv + F.lambda) : s;
-                const double r = (gq.yglob[n] - fv) / sd;
+                const double r = (yglob[n] - fv) / sd;
                 const double cpo = cold_exp(BSYN_LOG_2PI_HALF + cold_log(sd) + 0.5 * r * r);
-                if (gq.row) gq.row[o_cpo + n] = cpo;
-                if (gq.cpo_acc) gq.cpo_acc[n] += cpo;
+                if (row) row[o_cpo + n] = cpo;
+                if (cpo_acc) cpo_acc[n] += cpo;
             }
         }
         // ec50, dss (include/dss.stan) on lanes 0 / 1
@@ -558,21 +587,21 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         }
         const double ec2 = __shfl_sync(FULL, ec, 1), ds2 = __shfl_sync(FULL, ds, 1);
         // zero-valued integrals are replaced by U(1e-6,1e-4) draws (gp_grid.stan:294-297)
-        if (v_f == 0.0) v_f = 1e-6 + (1e-4 - 1e-6) * gq.uz[0];
-        if (v_p0 == 0.0) v_p0 = 1e-6 + (1e-4 - 1e-6) * gq.uz[1];
+        if (v_f == 0.0) v_f = 1e-6 + (1e-4 - 1e-6) * smem[gq.so + GQS_UZ + 0];
+        if (v_p0 == 0.0) v_p0 = 1e-6 + (1e-4 - 1e-6) * smem[gq.so + GQS_UZ + 1];
         if (gp) {
-            if (v_syn == 0.0) v_syn = 1e-6 + (1e-4 - 1e-6) * gq.uz[2];
-            if (v_ant == 0.0) v_ant = 1e-6 + (1e-4 - 1e-6) * gq.uz[3];
+            if (v_syn == 0.0) v_syn = 1e-6 + (1e-4 - 1e-6) * smem[gq.so + GQS_UZ + 2];
+            if (v_ant == 0.0) v_ant = 1e-6 + (1e-4 - 1e-6) * smem[gq.so + GQS_UZ + 3];
         }
         if (lane == 0) {
-            if (gq.row) {
-                gq.row[o_ec] = ec; gq.row[o_ec + 1] = ec2; gq.row[o_dss] = ds; gq.row[o_dss + 1] = ds2;
-                gq.row[o_vus] = v_f; gq.row[o_vus + 1] = v_p0;
-                if (gp) { gq.row[o_vus + 2] = v_d; gq.row[o_vus + 3] = v_syn; gq.row[o_vus + 4] = v_ant; }
+            if (row) {
+                row[o_ec] = ec; row[o_ec + 1] = ec2; row[o_dss] = ds; row[o_dss + 1] = ds2;
+                row[o_vus] = v_f; row[o_vus + 1] = v_p0;
+                if (gp) { row[o_vus + 2] = v_d; row[o_vus + 3] = v_syn; row[o_vus + 4] = v_ant; }
             }
-            if (gq.qout) {
-                gq.qout[0] = ec; gq.qout[1] = ec2; gq.qout[2] = ds; gq.qout[3] = ds2; gq.qout[4] = s;
-                gq.qout[5] = v_f; gq.qout[6] = v_p0; gq.qout[7] = v_d; gq.qout[8] = v_syn; gq.qout[9] = v_ant;
+            if (qout) {
+                qout[0] = ec; qout[1] = ec2; qout[2] = ds; qout[3] = ds2; qout[4] = s;
+                qout[5] = v_f; qout[6] = v_p0; qout[7] = v_d; qout[8] = v_syn; qout[9] = v_ant;
             }
         }
     }

@@ -23,7 +23,9 @@ struct SmemLayout {
     int tri_off, pd_off, pi_off, ws_off, pd_stride, pi_stride;   // *_stride: per-warp problem blocks (logp kernel)
     int park_off;                                                // sampler: per-warp parking area (PARK_DOUBLES each)
 };
-constexpr int PARK_DOUBLES = 48;   // 30 doubles + 24 ints + slack: warp-uniform chain state parked during an evaluation
+// per-warp parking area: warp-uniform chain state parked during an evaluation (34 doubles, then up to 32 ints), and
+// the generated-quantities sink block (GQ_DOUBLES) read by the evaluation when gq.on
+constexpr int PARK_INTS = 34, PARK_GQ = 50, PARK_DOUBLES = 60;
 
 struct SamplerParams {
     int n_problems, chains;
@@ -53,7 +55,7 @@ struct SamplerParams {
 
 enum ArenaSlot {
     A_OQ = 0, A_OP, A_OG, A_SQ, A_SG, A_PQ, A_PG, A_RHO_OLD, A_P_OLD_NEAR, A_P_NEW_NEAR, A_WM, A_WM2, A_PREV,
-    A_PARK_S, A_PARK_PREV, A_PARK_MINV,   // chain vectors parked in the arena while the evaluation runs
+    A_PARK_S, A_PARK_PREV, A_PARK_MINV, A_PARK_P,   // chain vectors parked in the arena while the evaluation runs
     A_LVL
 };
 __host__ __device__ inline int arena_vectors(int max_depth) { return A_LVL + 3 * (max_depth > 2 ? max_depth - 1 : 1); }
@@ -472,16 +474,14 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             }
             GQ gq;
             gq.on = (phase == PH_GQ);
-            gq.D = pd.D; gq.yglob = yglob; gq.iiglob = iiglob;
-            gq.row = nullptr; gq.qout = nullptr; gq.cpo_acc = nullptr;
-            gq.uz[0] = gq.uz[1] = gq.uz[2] = gq.uz[3] = 0.5;
+            gq.so = s_park + PARK_GQ;
             if (gq.on) {
                 const long long rowi = cg * sp.n_save + isave;
-                gq.row = sp.draws ? sp.draws + rowi * sp.ld_draws : nullptr;
-                gq.qout = sp.qdraws ? sp.qdraws + rowi * 12 : nullptr;
-                gq.cpo_acc = (it >= nw) ? cpo_acc : nullptr;
-                rng_u2(rk, RT_GQ, 0xFFu, it, 0, gq.uz[0], gq.uz[1]);
-                rng_u2(rk, RT_GQ, 0xFFu, it, 1, gq.uz[2], gq.uz[3]);
+                double uz[4];
+                rng_u2(rk, RT_GQ, 0xFFu, it, 0, uz[0], uz[1]);
+                rng_u2(rk, RT_GQ, 0xFFu, it, 1, uz[2], uz[3]);
+                gq_publish(gq.so, pd.D, yglob, iiglob, uz, sp.draws ? sp.draws + rowi * sp.ld_draws : nullptr,
+                           sp.qdraws ? sp.qdraws + rowi * 12 : nullptr, (it >= nw) ? cpo_acc : nullptr);
             }
             // Warp-uniform chain scalars (60+ registers replicated in every lane) go to shared memory for the
             // duration of the evaluation, whose schedule is register-starved otherwise (profiles/: the same kernel
@@ -489,40 +489,50 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
 #define BSYN_PARK_D(X) X(eps) X(mu) X(sbar) X(xbar) X(cnt) X(wn) X(n_div) X(n_maxd) X(nleap_tot) X(nleap_samp) X(acc_sum) \
     X(n_samp_it) X(is_H0) X(is_V0) X(eps_try) X(e_used) X(H0) X(otherV) X(sampleV) X(sampleH) X(proposeV) X(proposeH)    \
     X(lsw) X(summetro) X(lsw_sub) X(u_leaf) X(info.accept) X(info.energy)
+#define BSYN_PARK_P(X) X(cg) X(ngrad) X(cs) X(cpo_acc) X(yglob) X(iiglob)     /* 64-bit integers / pointers */
 #define BSYN_PARK_I(X) X(it) X(isave) X(win_size) X(win_end) X(init_try) X(is_it) X(is_dir) X(curdir) X(depth) X(nleap) \
-    X(k) X(nleaf) X(info.depth) X(info.nleap) X(info.divergent)
+    X(k) X(nleaf) X(info.depth) X(info.nleap) X(info.divergent) X(pd.n1) X(pd.n2) X(pd.N) X(pd.G) X(pd.ncf) X(pd.D)       \
+    X(pd.n_out) X(pd.off_d) X(pd.off_i) X(pd.n_d_smem) X(pd.n_i_smem)
             {
                 int o = s_park;
 #define BSYN_ST(v) smem[o++] = v;
                 BSYN_PARK_D(BSYN_ST)
 #undef BSYN_ST
-                o = 2 * (s_park + 30);
+#define BSYN_ST(v) smem[o++] = __longlong_as_double((long long)v);
+                BSYN_PARK_P(BSYN_ST)
+#undef BSYN_ST
+                o = 2 * (s_park + PARK_INTS);
 #define BSYN_ST(v) SMI(o++) = v;
                 BSYN_PARK_I(BSYN_ST)
 #undef BSYN_ST
                 SMI(o++) = (int)need_istep; SMI(o++) = (int)divergent; SMI(o++) = (int)istep_tag;
             }
-            // The evaluation needs every register it can get; S, pprev and minv are dead weight across it.  Parking
+            // The evaluation needs every register it can get; S, pprev, p and minv are dead weight across it.  Parking
             // them in the arena (L2-resident, coalesced) beats the compiler's choice of what to spill.
-            vstore<CPL>(A + A_PARK_S * VS, S); vstore<CPL>(A + A_PARK_PREV * VS, pprev);
+            vstore<CPL>(A + A_PARK_S * VS, S); vstore<CPL>(A + A_PARK_PREV * VS, pprev); vstore<CPL>(A + A_PARK_P * VS, p);
             if constexpr (!DENSE) vstore<CPL>(A + A_PARK_MINV * VS, minv);
             double lp;
             const bool okv = warp_logp_grad<CPL, false>(F, P, ws, cell, q, sp.jacobian, lp, g, nullptr, gq);
-            vload<CPL>(A + A_PARK_S * VS, S); vload<CPL>(A + A_PARK_PREV * VS, pprev);
+            vload<CPL>(A + A_PARK_S * VS, S); vload<CPL>(A + A_PARK_PREV * VS, pprev); vload<CPL>(A + A_PARK_P * VS, p);
             if constexpr (!DENSE) vload<CPL>(A + A_PARK_MINV * VS, minv);
             {
                 int o = s_park;
 #define BSYN_LD(v) v = smem[o++];
                 BSYN_PARK_D(BSYN_LD)
 #undef BSYN_LD
-                o = 2 * (s_park + 30);
+#define BSYN_LD(v) v = (decltype(v))__double_as_longlong(smem[o++]);
+                BSYN_PARK_P(BSYN_LD)
+#undef BSYN_LD
+                o = 2 * (s_park + PARK_INTS);
 #define BSYN_LD(v) v = SMI(o++);
                 BSYN_PARK_I(BSYN_LD)
 #undef BSYN_LD
                 need_istep = SMI(o++) != 0; divergent = SMI(o++) != 0; istep_tag = (uint32_t)SMI(o++);
             }
 #undef BSYN_PARK_D
+#undef BSYN_PARK_P
 #undef BSYN_PARK_I
+            rk.k0 = (uint32_t)sp.seed; rk.k1 = (uint32_t)(sp.seed >> 32); rk.chain = (uint32_t)cg;
             if (!gq.on) ++ngrad;
             if (!okv || !(fabs(lp) < INFINITY)) {   // domain error in the reference => infinite potential
                 V = INFINITY;
