@@ -44,16 +44,22 @@ def main():
     x = np.array(e["x"]).reshape(2, -1).T
     y = np.array(e["y"])
     res = []
-    res.append(run("cfg1 mathews_DLBCL[[1]] Matern 3/2 (package default)", [prepare(y, x)] * nb))
-    res.append(run("cfg1' mathews_DLBCL[[1]] RBF (type=2)", [prepare(y, x, type=2)] * nb))
+    only = os.environ.get("CB_ONLY", "")          # e.g. CB_ONLY=cfg1 : just the configurations whose name starts with it
+
+    def go(name, *a, **k):
+        if only and not name.startswith(only):
+            return dict(config=name, skipped=True)
+        return run(name, *a, **k)
+    res.append(go("cfg1 mathews_DLBCL[[1]] Matern 3/2 (package default)", [prepare(y, x)] * nb))
+    res.append(go("cfg1' mathews_DLBCL[[1]] RBF (type=2)", [prepare(y, x, type=2)] * nb))
     on = [prepare(*synthetic_oneil_experiment(k)) for k in range(min(nb, 583))]
-    res.append(run("cfg2 O'Neil-shaped screen, default options", on))
+    res.append(go("cfg2 O'Neil-shaped screen, default options", on))
     onr = [prepare(*synthetic_oneil_experiment(k), robust=True, pcprior=True) for k in range(min(nb, 583))]
-    res.append(run("cfg3 O'Neil-shaped, robust + PC prior, dense_e + jitter 0.5", onr, metric=1, stepsize_jitter=0.5))
-    res.append(run("cfg3-diag same model with diag_e (for comparison)", onr, metric=0, stepsize_jitter=0.5))
+    res.append(go("cfg3 O'Neil-shaped, robust + PC prior, dense_e + jitter 0.5", onr, metric=1, stepsize_jitter=0.5))
+    res.append(go("cfg3-diag same model with diag_e (for comparison)", onr, metric=0, stepsize_jitter=0.5))
     syn = [prepare(*synthetic_experiment(k)) for k in range(nb)]
-    res.append(run("cfg4 nointeraction (H0 of the Bayes factor) on cfg5 data", syn, model="nointeraction"))
-    res.append(run("cfg5 synthetic 10x10x3 (bench line)", syn))
+    res.append(go("cfg4 nointeraction (H0 of the Bayes factor) on cfg5 data", syn, model="nointeraction"))
+    res.append(go("cfg5 synthetic 10x10x3 (bench line)", syn))
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "config_bench.json"), "w"), indent=1)
 
 
