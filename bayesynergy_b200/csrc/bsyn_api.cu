@@ -493,8 +493,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     size_t bytes = 0;
     int nw = 0, per_sm = 0;
     const int want = getenv("BSYN_NUTS_NW") ? atoi(getenv("BSYN_NUTS_NW")) : 0;
-    for (int cand : {16, 12, 6, 4, 1}) {
-        if (cand == 16 && (want != 16 || b->cpl > 2 || a->metric == 1)) continue;   // small grids: 16 warps x 128 registers (on request)
+    for (int cand : {12, 6, 4, 1}) {
         if (want && cand != want) continue;
         if (a->metric == 1 && cand != 12 && cand != 4) continue;
         sp.sl = make_layout(b, true, &bytes, cand);

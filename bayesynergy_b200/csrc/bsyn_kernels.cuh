@@ -164,9 +164,6 @@ template <int CPL> struct VariantImpl {
             return nuts_launch<4, 168, true>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
         }
         if (nw == 12) return nuts_launch<12, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        if constexpr (CPL <= 2) {
-            if (nw == 16) return nuts_launch<16, 128, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        }
         if (nw == 6) return nuts_launch<6, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
         if (nw == 4) return nuts_launch<4, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
         return nuts_launch<1, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
@@ -178,9 +175,6 @@ template <int CPL> struct VariantImpl {
             return nuts_occ<4, 168, true>(bytes, per_sm);
         }
         if (nw == 12) return nuts_occ<12, 168, false>(bytes, per_sm);
-        if constexpr (CPL <= 2) {
-            if (nw == 16) return nuts_occ<16, 128, false>(bytes, per_sm);
-        }
         if (nw == 6) return nuts_occ<6, 168, false>(bytes, per_sm);
         if (nw == 4) return nuts_occ<4, 168, false>(bytes, per_sm);
         return nuts_occ<1, 168, false>(bytes, per_sm);
