@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
         // ---- the one evaluation of this tick ----
         GQ gq;
         gq.on = (stage == VS_DRAW);
-        gq.so = s_gq;
+        gq.so = s_gq; gq.fwd = (stage == VS_ELBO);
         if (gq.on) {
             const long long rowi = (long long)ip * vp.output_samples + idraw;
             double uz[4];

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const Pro
         load_user_vec<CPL>(F, pd, cell, u + (size_t)pt * ldu, q);
         double lpv;
         GQ gq{};
-        gq.on = false; gq.so = 0;
+        gq.on = false; gq.so = 0; gq.fwd = (grad == nullptr) && !DBG;   // value-only calls (log_prob(upar, jacobian, gradient = FALSE)) skip the reverse sweep
         const bool ok = warp_logp_grad<CPL, DBG>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr, gq);
         if (!ok) {
             lpv = -INFINITY;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(32 * WPC) write_array_kernel(const Flags F, co
         RngKey rk;
         rk.k0 = (uint32_t)seed; rk.k1 = (uint32_t)(seed >> 32); rk.chain = (uint32_t)pt;
         GQ gq{};
-        gq.on = true; gq.so = sl.park_off + warp * PARK_DOUBLES + PARK_GQ;
+        gq.on = true; gq.so = sl.park_off + warp * PARK_DOUBLES + PARK_GQ; gq.fwd = false;
         double uz[4];
         rng_u2(rk, RT_GQ, 0xFFu, 0, 0, uz[0], uz[1]);
         rng_u2(rk, RT_GQ, 0xFFu, 0, 1, uz[2], uz[3]);

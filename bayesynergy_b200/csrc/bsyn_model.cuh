@@ -346,6 +346,7 @@ __device__ __forceinline__ double lik_cell_normal(const Flags &F, const ProbS &P
 struct GQ {
     bool on;
     int so;   // offset (doubles) of the sink block in shared memory, see GqSlot; read only where gq.on
+    bool fwd; // value only: return after the forward pass with lp (ADVI's ELBO samples, log_prob<false, true>)
 };
 // The sinks live in a small shared-memory block written by the caller (gq_publish) instead of in the struct: as
 // struct members they would occupy ~25 registers through every evaluation, 99 % of which have gq.on == false.
@@ -606,6 +607,18 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         }
     }
     __syncwarp();
+    if (gq.fwd) {   // lp without the reverse sweep: add the N(0,1) prior of z and reduce
+        if (gp) {
+#pragma unroll
+            for (int t = 0; t < CPL; ++t)
+                if (cell[t] >> 16) lpl = fma(-0.5 * q.z[t], q.z[t], lpl);
+        }
+        double lpf = warp_sum(lpl) - (double)P.N * (BSYN_LOG_2PI_HALF + ur[SL_S]);
+        if (gp) lpf += -(double)P.G * BSYN_LOG_2PI_HALF;
+        lp_out = lpf;
+        ok = ok && (lpf == lpf);
+        return __all_sync(FULL, ok);
+    }
     // ---- 7. adjoints of the monotherapy curves: 6 sums delivered to their owner lanes by one butterfly ----
     {
         double v8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};

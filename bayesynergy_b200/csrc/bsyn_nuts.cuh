@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             }
             GQ gq;
             gq.on = (phase == PH_GQ);
-            gq.so = s_park + PARK_GQ;
+            gq.so = s_park + PARK_GQ; gq.fwd = false;
             if (gq.on) {
                 const long long rowi = cg * sp.n_save + isave;
                 double uz[4];

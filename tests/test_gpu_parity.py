@@ -164,6 +164,28 @@ def test_nonfinite_gradient_where_reference_autodiff_breaks(built, datasets):
     b.close()
 
 
+def test_value_only_path_matches_full_evaluation(built, datasets):
+    """log_prob(upar, jacobian, gradient = FALSE) skips the reverse sweep (bridge sampling, ADVI's ELBO samples):
+    same lp and status as the full evaluation, for every likelihood / kernel family and both models."""
+    rng = np.random.default_rng(12)
+    for dname, kw, model in (("mathews:ispinesib + ibrutinib", {}, "gp_grid"),
+                             ("synthetic:7", dict(robust=True, pcprior=True), "gp_grid"),
+                             ("oneil_failed:1", dict(type=4, heteroscedastic=False), "gp_grid"),
+                             ("mathews:canertinib + ibrutinib", dict(type=2), "nointeraction")):
+        sd = prepare(*datasets[dname], **kw)
+        b = _lib.Batch([sd], model=model)
+        U = rng.uniform(-1.0, 1.0, size=(24, b.num_params(0)))
+        U[5, 2 * sd.est_la + 6 + (3 if model == "gp_grid" else 0)] = 800.0      # a rejected point
+        for jac in (True, False):
+            lp_f, g, st_f = b.logp_grad(U, jacobian=jac)
+            lp_v, none, st_v = b.logp_grad(U, jacobian=jac, want_grad=False)
+            assert none is None and np.array_equal(st_f, st_v)
+            okm = st_f == 0
+            assert np.allclose(lp_v[okm], lp_f[okm], rtol=1e-13, atol=1e-12), (dname, jac)
+            assert np.array_equal(np.isinf(lp_v), np.isinf(lp_f))
+        b.close()
+
+
 def test_write_array_against_oracle(built, datasets, cond_fn):
     for dname, v in itertools.product(("mathews:ispinesib + ibrutinib", "synthetic:7", "oneil_failed:0"),
                                       (dict(), dict(type=2, heteroscedastic=False), dict(robust=True, lower_asymptotes=False))):
