@@ -203,10 +203,12 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
         }
         return warp_sum(part) + 0.5 * D * (1.0 + 1.8378770664093453);   // log(2 pi)
     };
-    auto start_elbo = [&](int purpose) { efor = purpose; e_done = 0; e_drop = 0; e_sum = 0.0; stage = VS_ELBO; draw_sample(); };
-    auto start_grad = [&]() { stage = VS_GRAD; draw_sample(); };
+    // The sweeps are inlined ONCE, at the top of the tick: the bookkeeping only raises these flags
+    bool need_reset = false, need_sample = false;
+    auto start_elbo = [&](int purpose) { efor = purpose; e_done = 0; e_drop = 0; e_sum = 0.0; stage = VS_ELBO; need_sample = true; };
+    auto start_grad = [&]() { stage = VS_GRAD; need_sample = true; };
     auto start_main = [&]() {
-        reset_q(true);
+        need_reset = true;
         in_adapt = false; it = 1; elbo = 0.0; elbo_best = -DBL_MAX; cbv = 0.0; cb_n = 0; cb_head = 0;
         start_grad();
     };
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
             if (i < D && vp.mean) vp.mean[(long long)ip * vp.ld_mean + i] = mu[i];
         }
         idraw = 0;
-        if (vp.output_samples > 0) { stage = VS_DRAW; draw_sample(); }
+        if (vp.output_samples > 0) { stage = VS_DRAW; need_sample = true; }
         else { finish(); stage = VS_FETCH; }
     };
 
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
                 iiglob = ipool + pd.off_i + pool_ii_off(pd);
                 cpo_acc = vp.cpo_acc ? vp.cpo_acc + (long long)ip * vp.ld_cpo : nullptr;
                 if (cpo_acc) for (int e = lane; e < pd.N; e += 32) cpo_acc[e] = 0.0;
+                need_reset = false; need_sample = false;
                 tick = 0; init_try = 0; status = 0; conv = 0; iters = 0; n_grad = 0.0; n_lp = 0.0; elbo = 0.0; eta = vp.eta;
                 stage = VS_INIT;
             }
@@ -266,6 +269,8 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
             rng_u2(rk, RT_INIT, lane, (uint32_t)init_try, CPL + 1, ua, ub);
             q.s = lane_active ? vp.init_r * (2.0 * ua - 1.0) : 0.0;
         }
+        if (need_reset) { reset_q(true); need_reset = false; }
+        if (need_sample) { draw_sample(); need_sample = false; }
         // ---- the one evaluation of this tick ----
         GQ gq;
         gq.on = (stage == VS_DRAW);
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
                 __syncwarp();
                 store_user_vec<CPL>(F, pd, cell, q, init);
                 __syncwarp();
-                reset_q(true);
+                need_reset = true;
                 if (vp.adapt_engaged) {
                     in_adapt = true; k_eta = 0; elbo_best = -DBL_MAX; eta_best = 0.0;
                     start_elbo(VE_INIT);
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
             if (lp_ok) { e_sum += lp; done = (++e_done == vp.elbo_samples); }
             else failed = (++e_drop >= vp.elbo_samples);
             if (!done && !failed) {
-                draw_sample();
+                need_sample = true;
             } else {
                 const double el = failed ? -DBL_MAX : e_sum / vp.elbo_samples + entropy();
                 if (efor == VE_INIT) {
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
                         else { status = 3; }
                     }
                     if (status) { finish(); stage = VS_FETCH; }
-                    else if (more) { ++k_eta; reset_q(true); it = 1; start_grad(); }
+                    else if (more) { ++k_eta; need_reset = true; it = 1; start_grad(); }
                     else { eta = eta_best; start_main(); }
                 } else {
                     if (failed) { status = 5; finish(); stage = VS_FETCH; }
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
         } else if (stage == VS_DRAW) {
             if (vp.qdraws && lane == 0) { double *qo = vp.qdraws + ((long long)ip * vp.output_samples + idraw) * 12; qo[10] = lp; qo[11] = 0.0; }
             if (++idraw == vp.output_samples) { finish(); stage = VS_FETCH; }
-            else draw_sample();
+            else need_sample = true;
         }
     }
 }
