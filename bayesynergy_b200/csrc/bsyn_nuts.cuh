@@ -486,26 +486,27 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             // Warp-uniform chain scalars (60+ registers replicated in every lane) go to shared memory for the
             // duration of the evaluation, whose schedule is register-starved otherwise (profiles/: the same kernel
             // with 255 registers runs each warp 1.45x faster).
-#define BSYN_PARK_D(X) X(eps) X(mu) X(sbar) X(xbar) X(cnt) X(wn) X(n_div) X(n_maxd) X(nleap_tot) X(nleap_samp) X(acc_sum) \
-    X(n_samp_it) X(is_H0) X(is_V0) X(eps_try) X(e_used) X(H0) X(otherV) X(sampleV) X(sampleH) X(proposeV) X(proposeH)    \
-    X(lsw) X(summetro) X(lsw_sub) X(u_leaf) X(info.accept) X(info.energy)
-#define BSYN_PARK_P(X) X(cg) X(ngrad) X(cs) X(cpo_acc) X(yglob) X(iiglob)     /* 64-bit integers / pointers */
-#define BSYN_PARK_I(X) X(it) X(isave) X(win_size) X(win_end) X(init_try) X(is_it) X(is_dir) X(curdir) X(depth) X(nleap) \
-    X(k) X(nleaf) X(info.depth) X(info.nleap) X(info.divergent) X(pd.n1) X(pd.n2) X(pd.N) X(pd.G) X(pd.ncf) X(pd.D)       \
-    X(pd.n_out) X(pd.off_d) X(pd.off_i) X(pd.n_d_smem) X(pd.n_i_smem)
-            {
-                int o = s_park;
-#define BSYN_ST(v) smem[o++] = v;
-                BSYN_PARK_D(BSYN_ST)
+#define BSYN_PARK_D2(X) X(eps, mu) X(sbar, xbar) X(cnt, wn) X(n_div, n_maxd) X(nleap_tot, nleap_samp) X(acc_sum, n_samp_it)      \
+    X(is_H0, is_V0) X(eps_try, e_used) X(H0, otherV) X(sampleV, sampleH) X(proposeV, proposeH) X(lsw, summetro)                 \
+    X(lsw_sub, u_leaf) X(info.accept, info.energy)
+#define BSYN_PARK_P2(X) X(cg, ngrad) X(cs, cpo_acc) X(yglob, iiglob)          /* 64-bit integers / pointers */
+#define BSYN_PARK_I4(X) X(it, isave, win_size, win_end) X(init_try, is_it, is_dir, curdir) X(depth, nleap, k, nleaf)           \
+    X(info.depth, info.nleap, info.divergent, pd.n1) X(pd.n2, pd.N, pd.G, pd.ncf) X(pd.D, pd.n_out, pd.off_d, pd.off_i)        \
+    X(pd.n_d_smem, pd.n_i_smem, flag_istep, flag_div)
+            {   // 128-bit stores: 14 + 3 + 7 STS.128 (every lane writes the same values to the same addresses)
+                int flag_istep = (int)need_istep, flag_div = (int)divergent;
+                double2 *pk = reinterpret_cast<double2 *>(smem + s_park);
+#define BSYN_ST(a, b) *pk++ = make_double2(a, b);
+                BSYN_PARK_D2(BSYN_ST)
 #undef BSYN_ST
-#define BSYN_ST(v) smem[o++] = __longlong_as_double((long long)v);
-                BSYN_PARK_P(BSYN_ST)
+#define BSYN_ST(a, b) *pk++ = make_double2(__longlong_as_double((long long)a), __longlong_as_double((long long)b));
+                BSYN_PARK_P2(BSYN_ST)
 #undef BSYN_ST
-                o = 2 * (s_park + PARK_INTS);
-#define BSYN_ST(v) SMI(o++) = v;
-                BSYN_PARK_I(BSYN_ST)
+                int4 *pi = reinterpret_cast<int4 *>(smem + s_park + PARK_INTS);
+#define BSYN_ST(a, b, c, d) *pi++ = make_int4(a, b, c, d);
+                BSYN_PARK_I4(BSYN_ST)
 #undef BSYN_ST
-                SMI(o++) = (int)need_istep; SMI(o++) = (int)divergent; SMI(o++) = (int)istep_tag;
+                SMI(2 * (s_park + PARK_INTS) + 28) = (int)istep_tag;
             }
             // The evaluation needs every register it can get; S, pprev, p and minv are dead weight across it.  Parking
             // them in the arena (L2-resident, coalesced) beats the compiler's choice of what to spill.
@@ -516,22 +517,24 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             vload<CPL>(A + A_PARK_S * VS, S); vload<CPL>(A + A_PARK_PREV * VS, pprev); vload<CPL>(A + A_PARK_P * VS, p);
             if constexpr (!DENSE) vload<CPL>(A + A_PARK_MINV * VS, minv);
             {
-                int o = s_park;
-#define BSYN_LD(v) v = smem[o++];
-                BSYN_PARK_D(BSYN_LD)
+                int flag_istep, flag_div;
+                const double2 *pk = reinterpret_cast<const double2 *>(smem + s_park);
+#define BSYN_LD(a, b) { const double2 t2 = *pk++; a = t2.x; b = t2.y; }
+                BSYN_PARK_D2(BSYN_LD)
 #undef BSYN_LD
-#define BSYN_LD(v) v = (decltype(v))__double_as_longlong(smem[o++]);
-                BSYN_PARK_P(BSYN_LD)
+#define BSYN_LD(a, b) { const double2 t2 = *pk++; a = (decltype(a))__double_as_longlong(t2.x); b = (decltype(b))__double_as_longlong(t2.y); }
+                BSYN_PARK_P2(BSYN_LD)
 #undef BSYN_LD
-                o = 2 * (s_park + PARK_INTS);
-#define BSYN_LD(v) v = SMI(o++);
-                BSYN_PARK_I(BSYN_LD)
+                const int4 *pi = reinterpret_cast<const int4 *>(smem + s_park + PARK_INTS);
+#define BSYN_LD(a, b, c, d) { const int4 t4 = *pi++; a = t4.x; b = t4.y; c = t4.z; d = t4.w; }
+                BSYN_PARK_I4(BSYN_LD)
 #undef BSYN_LD
-                need_istep = SMI(o++) != 0; divergent = SMI(o++) != 0; istep_tag = (uint32_t)SMI(o++);
+                need_istep = flag_istep != 0; divergent = flag_div != 0;
+                istep_tag = (uint32_t)SMI(2 * (s_park + PARK_INTS) + 28);
             }
-#undef BSYN_PARK_D
-#undef BSYN_PARK_P
-#undef BSYN_PARK_I
+#undef BSYN_PARK_D2
+#undef BSYN_PARK_P2
+#undef BSYN_PARK_I4
             rk.k0 = (uint32_t)sp.seed; rk.k1 = (uint32_t)(sp.seed >> 32); rk.chain = (uint32_t)cg;
             if (!gq.on) ++ngrad;
             if (!okv || !(fabs(lp) < INFINITY)) {   // domain error in the reference => infinite potential
