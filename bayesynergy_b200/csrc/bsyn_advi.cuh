@@ -42,6 +42,7 @@ struct AdviParams {
 enum AdviStage { VS_FETCH = 0, VS_INIT, VS_ELBO, VS_GRAD, VS_DRAW, VS_DONE };
 enum AdviElboFor { VE_INIT = 0, VE_ADAPT, VE_MAIN };
 constexpr uint32_t RT_VB = 9;   // RNG stream tag of the eta draws
+constexpr int ADVI_NW = 12;     // warps (experiments) per CTA
 
 template <int CPL, int NW>
 __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, const ProbDesc *__restrict__ descs,
@@ -230,7 +231,9 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
     };
 
     for (;;) {
-        if (stage == VS_DONE) break;        // warps run free: the ticks are dominated by the sweeps over L, not by code fetch
+        // tick barrier as in the sampler: free-running warps spent half their time waiting for instructions
+        // (no_instruction 5.5 cycles per issue, profiles/r01_advi_v1_summary.txt)
+        if (__syncthreads_and(stage == VS_DONE)) break;
         if (stage == VS_FETCH) {
             int item = 0;
             if (lane == 0) item = atomicAdd(vp.work_counter, 1);

@@ -648,13 +648,13 @@ extern "C" int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *a, const bsyn_advi
     vp.adapt_engaged = a->adapt_engaged; vp.adapt_iter = a->adapt_iter; vp.output_samples = a->output_samples;
     vp.cb_size = cb_size; vp.eta = a->eta; vp.tol_rel_obj = a->tol_rel_obj; vp.init_r = a->init_r; vp.seed = a->seed;
     size_t bytes = 0;
-    vp.sl = make_layout(b, true, &bytes, WPC);
+    vp.sl = make_layout(b, true, &bytes, ADVI_NW);
     int per_sm = 0;
     if (bytes > 227 * 1024 || variant(b->cpl)->advi_occupancy(bytes, &per_sm) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         return fail(BSYN_ERR_UNSUPPORTED, "ADVI kernel does not fit on an SM");
     }
-    const int grid = std::max(1, std::min((b->n + WPC - 1) / WPC, per_sm * b->num_sms));
+    const int grid = std::max(1, std::min((b->n + ADVI_NW - 1) / ADVI_NW, per_sm * b->num_sms));
     vp.DP = (b->maxD + 31) / 32 * 32;
     vp.state_stride = 6LL * vp.DP + (3LL * vp.DP * vp.DP) / 2;   // 6 vectors + L (double) + its adaGrad history (float)
     const size_t ns = (size_t)a->output_samples, nrows = (size_t)b->n * ns;
@@ -665,7 +665,7 @@ extern "C" int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *a, const bsyn_advi
         if (cudaMalloc(p, sizeof(double) * std::max<size_t>(n, 1)) != cudaSuccess) return false;
         return cudaMemsetAsync(*p, 0, sizeof(double) * std::max<size_t>(n, 1), b->stream) == cudaSuccess;
     };
-    if (!alloc0(&d_state, (size_t)grid * WPC * vp.state_stride) || !alloc0(&d_mean, (size_t)b->n * b->maxD) ||
+    if (!alloc0(&d_state, (size_t)grid * ADVI_NW * vp.state_stride) || !alloc0(&d_mean, (size_t)b->n * b->maxD) ||
         !alloc0(&d_info, (size_t)b->n * BSYN_NVI)) { cleanup(); return fail(BSYN_ERR_ALLOC, "bsyn_advi: device allocation failed"); }
     if (sinks->draws) {
         if (sinks->ld_draws < b->maxOut) { cleanup(); return fail(BSYN_ERR_ARG, "bsyn_advi: ld_draws < bsyn_max_outputs"); }

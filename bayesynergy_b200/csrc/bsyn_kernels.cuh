@@ -179,18 +179,18 @@ template <int CPL> struct VariantImpl {
         if (nw == 4) return nuts_occ<4, 168, false>(bytes, per_sm);
         return nuts_occ<1, 168, false>(bytes, per_sm);
     }
-    // full-rank ADVI: WPC warps (problems) per CTA
+    // full-rank ADVI: ADVI_NW warps (problems) per CTA, one CTA per SM
     static cudaError_t advi(int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                             const double *dpool, const int *ipool, const int *tri, const AdviParams &vp)
     {
-        advi_kernel<CPL, WPC><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, vp);
+        advi_kernel<CPL, ADVI_NW><<<grid, 32 * ADVI_NW, bytes, st>>>(F, descs, dpool, ipool, tri, vp);
         return cudaGetLastError();
     }
     static cudaError_t advi_occupancy(size_t bytes, int *per_sm)
     {
-        cudaError_t e = cudaFuncSetAttribute(advi_kernel<CPL, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(advi_kernel<CPL, ADVI_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, advi_kernel<CPL, WPC>, 32 * WPC, bytes);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, advi_kernel<CPL, ADVI_NW>, 32 * ADVI_NW, bytes);
     }
     static const VariantOps *ops()
     {
