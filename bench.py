@@ -158,7 +158,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     from bayesynergy_b200 import _lib
     L = _lib.load()
-    it, wu = args.iter, args.iter // 2
+    it = args.iter
+    wu = args.warmup_iter if args.warmup_iter is not None else args.iter // 2
     sds = make_experiments(rank * args.combos, args.combos)
 
     def barrier():
@@ -287,6 +288,9 @@ def main():
                          "per resident warp slot keeps a step at ~30 s so that W + K steps finish within minutes)")
     ap.add_argument("--chains", type=int, default=4)
     ap.add_argument("--iter", type=int, default=2000)
+    ap.add_argument("--warmup-iter", type=int, default=None,
+                    help="warm-up iterations per chain (default iter / 2 as in rstan); e.g. --iter 1150 --warmup-iter 1000 "
+                         "samples just long enough for ESS >= 400 per combination")
     ap.add_argument("--ref-iter", type=int, default=600, help="iterations per chain in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
