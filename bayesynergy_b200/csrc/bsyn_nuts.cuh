@@ -55,7 +55,7 @@ struct SamplerParams {
 
 enum ArenaSlot {
     A_OQ = 0, A_OP, A_OG, A_SQ, A_SG, A_PQ, A_PG, A_RHO_OLD, A_P_OLD_NEAR, A_P_NEW_NEAR, A_WM, A_WM2, A_PREV,
-    A_PARK_S, A_PARK_PREV, A_PARK_MINV, A_PARK_P,   // chain vectors parked in the arena while the evaluation runs
+    A_PARK_S, A_PARK_PREV, A_PARK_MINV, A_PARK_P, A_PARK_YV,   // chain vectors parked in the arena while the evaluation runs
     A_LVL
 };
 __host__ __device__ inline int arena_vectors(int max_depth) { return A_LVL + 3 * (max_depth > 2 ? max_depth - 1 : 1); }
@@ -275,6 +275,10 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     RngKey rk;
     long long cg = 0;
     WVec<CPL> q, p, g, minv, S, pprev;
+    // dense_e: M^-1 p and M^-1 g of the state in registers, so that a leapfrog costs ONE matrix-vector product:
+    // M^-1 (p + e/2 g) = M^-1 p + e/2 M^-1 g before the evaluation, and the same update with the new g after it
+    WVec<CPL> ps_c, mg_c, yv_keep;
+    bool sharp_valid = false;
     double V = 0.0, step = 0.0;
     unsigned long long ngrad = 0;
     // chain level
@@ -466,11 +470,18 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             for (int t = 0; t < CPL; ++t) p.z[t] = fma(he, g.z[t], p.z[t]);
             p.s = fma(he, g.s, p.s);
             {
-                WVec<CPL> yv;
-                sharp(p, yv);   // dtau/dp = M^-1 p
+                WVec<CPL> yv;   // dtau/dp = M^-1 p
+                if (DENSE && sharp_valid) {
+#pragma unroll
+                    for (int t = 0; t < CPL; ++t) yv.z[t] = fma(he, mg_c.z[t], ps_c.z[t]);
+                    yv.s = fma(he, mg_c.s, ps_c.s);
+                } else {
+                    sharp(p, yv);
+                }
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) q.z[t] = fma(step, yv.z[t], q.z[t]);
                 q.s = fma(step, yv.s, q.s);
+                if constexpr (DENSE) yv_keep = yv;
             }
             GQ gq;
             gq.on = (phase == PH_GQ);
@@ -512,10 +523,12 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             // them in the arena (L2-resident, coalesced) beats the compiler's choice of what to spill.
             vstore<CPL>(A + A_PARK_S * VS, S); vstore<CPL>(A + A_PARK_PREV * VS, pprev); vstore<CPL>(A + A_PARK_P * VS, p);
             if constexpr (!DENSE) vstore<CPL>(A + A_PARK_MINV * VS, minv);
+            else vstore<CPL>(A + A_PARK_YV * VS, yv_keep);
             double lp;
             const bool okv = warp_logp_grad<CPL, false>(F, P, ws, cell, q, sp.jacobian, lp, g, nullptr, gq);
             vload<CPL>(A + A_PARK_S * VS, S); vload<CPL>(A + A_PARK_PREV * VS, pprev); vload<CPL>(A + A_PARK_P * VS, p);
             if constexpr (!DENSE) vload<CPL>(A + A_PARK_MINV * VS, minv);
+            else vload<CPL>(A + A_PARK_YV * VS, yv_keep);
             {
                 int flag_istep, flag_div;
                 const double2 *pk = reinterpret_cast<const double2 *>(smem + s_park);
@@ -549,11 +562,22 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             for (int t = 0; t < CPL; ++t) p.z[t] = fma(he, g.z[t], p.z[t]);
             p.s = fma(he, g.s, p.s);
         }
-        WVec<CPL> ps;   // sharp momentum of the state just reached; lives only until the next evaluation
-        sharp(p, ps);
+        WVec<CPL> ps;   // sharp momentum of the state just reached
+        if constexpr (DENSE) {
+            const double he = 0.5 * step;
+            sharp(g, mg_c);
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) ps.z[t] = fma(he, mg_c.z[t], yv_keep.z[t]);
+            ps.s = fma(he, mg_c.s, yv_keep.s);
+            ps_c = ps;
+            sharp_valid = true;   // cleared below wherever the bookkeeping replaces p, g or the metric
+        } else {
+            sharp(p, ps);
+        }
         auto kinetic = [&]() { return 0.5 * vdot2<CPL>(p, ps); };
         // ---- bookkeeping of this chain ---------------------------------------------------------------
         int next = N_NONE;
+        bool keep_sharp = false;   // set where the next leapfrog starts from exactly this (p, g): the next leaf of a subtree
         if (phase == PH_INIT) {
             // services::util::initialize: u ~ U(-R, R) until lp and its gradient are finite (<= 100 tries)
             bool fin = V < INFINITY && fabs(g.s) < INFINITY;
@@ -685,6 +709,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 ++k;
                 pprev = p;
                 sh_store(A_PREV, ps);
+                keep_sharp = true;
             } else {
                 // ---- subtree complete: multinomial sample across subtrees (biased progressive sampling) ----
                 ++depth;
@@ -944,6 +969,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             pprev = p;
             phase = PH_TREE;
         }
+        if (!keep_sharp) sharp_valid = false;
     }
     if (lane == 0 && ngrad) atomicAdd(sp.grad_counter, ngrad);
 }

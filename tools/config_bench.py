@@ -21,7 +21,7 @@ from bayesynergy_b200 import _lib  # noqa: E402
 from bayesynergy_b200.dataprep import prepare, synthetic_experiment, synthetic_oneil_experiment  # noqa: E402
 
 
-def run(name, sds, model="gp_grid", iters=2000, **kw):
+def run(name, sds, model="gp_grid", iters=int(os.environ.get("CB_ITER", "2000")), **kw):
     b = _lib.Batch(sds, model=model)
     b.sample_device(chains=4, iter=200, warmup=100, seed=9, **kw)     # warm-up launch
     ng, ms = b.sample_device(chains=4, iter=iters, warmup=iters // 2, seed=1, **kw)
