@@ -249,6 +249,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "seconds_per_step": float(mx[5] / len(e2e_t))},
             "gpu_launches": int(mx[7]),
             "clocks": clocks.summary(),
+            # the bound of this path is FP64 issue throughput (neither HBM nor tensor cores)
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak_tflops if peak_tflops > 0 else None,
                          "peak_source": "bsyn_measure_fp64_peak: register-resident DFMA microbenchmark, measured in this run "
