@@ -86,6 +86,9 @@ int32_t bsyn_num_problems(const bsyn_batch *b);
  * B evaluation points; point k uses problem prob_idx[k] and u + k*ldu (first D entries).
  * lp[B], grad[B*ldu] (may be NULL), status[B]: 0 ok, 1 = the reference would throw std::domain_error
  * (non-PD kernel matrix, transformed parameter out of range, NaN): lp = -inf, grad = 0.
+ * Where the reference's reverse sweep yields NaN although lp is finite (the Bliss product rounds to exactly 0 or 1,
+ * so log(p0 / (1 - p0)) in gp_grid.stan:160-161 is infinite, or 10^(slope (x - m)) overflows) the gradient is NaN
+ * with status 0 and the finite lp, as from grad_log_prob.  grad == NULL takes a value-only path (no reverse sweep).
  * Host pointers (copies are made inside the call). */
 int bsyn_logp_grad(bsyn_batch *b, int32_t B, const int32_t *prob_idx, const double *u, int32_t ldu,
                    int32_t jacobian, double *lp, double *grad, int32_t *status);
