@@ -87,15 +87,15 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
     double n_grad = 0.0, n_lp = 0.0;
 
     // Q(cont_params): mu = init, L = I, histories = 0
-    auto reset_q = [&](bool also_mu) {
+    auto reset_q = [&]() {
         for (int s = 0; s < ES; ++s) {
             const int i = lane + 32 * s;
-            if (i < DP) { if (also_mu) mu[i] = init[i]; hmu[i] = 0.0; }
+            if (i < DP) { mu[i] = init[i]; hmu[i] = 0.0; }
         }
         for (int i = 0; i < D; ++i)
             for (int s = 0; s < ES; ++s) {
                 const int j = lane + 32 * s;
-                if (j <= i) { if (also_mu) Lm[(long long)i * DP + j] = (j == i) ? 1.0 : 0.0; Hm[(long long)i * DP + j] = 0.0f; }
+                if (j <= i) { Lm[(long long)i * DP + j] = (j == i) ? 1.0 : 0.0; Hm[(long long)i * DP + j] = 0.0f; }
             }
         __syncwarp();
     };
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(32 * NW, 12 / NW) advi_kernel(const Flags F, c
             rng_u2(rk, RT_INIT, lane, (uint32_t)init_try, CPL + 1, ua, ub);
             q.s = lane_active ? vp.init_r * (2.0 * ua - 1.0) : 0.0;
         }
-        if (need_reset) { reset_q(true); need_reset = false; }
+        if (need_reset) { reset_q(); need_reset = false; }
         if (need_sample) { draw_sample(); need_sample = false; }
         // ---- the one evaluation of this tick ----
         GQ gq;
