@@ -5,6 +5,8 @@ import subprocess
 import sys
 import textwrap
 
+import warnings
+
 import numpy as np
 import pytest
 
@@ -68,3 +70,64 @@ def test_method_argument_is_validated():
         bayesynergy(y, x, method="opt")
     with pytest.raises(ValueError, match="Method must be one of"):
         synergyscreen([dict(y=y, x=x)], bayesynergy_params=dict(method="opt"))
+
+
+def _fake_res(n, s_vals, syn=5.0):
+    from bayesynergy_b200._lib import Q_NAMES, BSYN_NQ
+    S = np.ones((n, BSYN_NQ, 2))
+    S[:, Q_NAMES.index("s"), 0] = s_vals
+    S[:, Q_NAMES.index("VUS_syn"), 0] = syn
+    return dict(summary=S, chain_stats=np.zeros((n, 4, 8)))
+
+
+def _toy_experiments(n):
+    y = np.linspace(1, 0.2, 9)
+    x = np.array([[a, b] for a in (0.0, 1.0, 2.0) for b in (0.0, 1.0, 2.0)])
+    return [dict(y=y, x=x, drug_names=[f"A{k}", f"B{k}"], experiment_ID=f"e{k}") for k in range(n)]
+
+
+def test_synergyscreen_vb_retry_rule(monkeypatch):
+    """method="vb": whatever errored (returnCode 2) or ended with s > 1 is refitted, up to max_retries more times
+    (R/synergyscreen.R:159-167); what still fails is dropped from the summary and returned in `failed`."""
+    from bayesynergy_b200 import api
+    calls = []
+
+    def fake_vb(sds, vbkw, seed, device):
+        calls.append((len(sds), seed))
+        n = len(sds)
+        if len(calls) == 1:      # first pass over 5 experiments: #1 errors, #3 has s > 1
+            rc = np.array([0, 2, 0, 0, 0])
+            return _fake_res(n, [0.1, 0.0, 0.2, 1.7, 0.3]), rc
+        if len(calls) == 2:      # retry of (#1, #3): #1 fine now, #3 still bad
+            return _fake_res(n, [0.15, 2.5]), np.array([0, 0])
+        return _fake_res(n, [3.0]), np.array([0])           # #3 never recovers
+
+    monkeypatch.setattr(api, "_fit_batch_vb", fake_vb)
+    monkeypatch.setattr(api, "prepare", lambda y, x, **kw: ("sd", len(y)))
+    out = api.synergyscreen(_toy_experiments(5), max_retries=2, bayesynergy_params=dict(method="vb", seed=10))
+    assert [c[0] for c in calls] == [5, 2, 1, 1]            # 1 + (max_retries + 1) passes, shrinking
+    assert len({c[1] for c in calls}) == len(calls)         # a fresh seed per pass
+    rows = out["screenSummary"]
+    assert [r["Experiment ID"] for r in rows] == ["e0", "e1", "e2", "e4"]
+    assert rows[1]["s"] == 0.15 and all(r["returnCode"] == 0 for r in rows)
+    assert [e["experiment_ID"] for e in out["failed"]] == ["e3"]
+
+
+def test_synergyscreen_sampling_retry_raises_adapt_delta(monkeypatch):
+    """method="sampling": experiments with warnings are rerun with adapt_delta = 0.99 (R/synergyscreen.R:149-157)."""
+    from bayesynergy_b200 import api
+    seen = []
+
+    def fake_fit(sds, kw, device, max_treedepth):
+        seen.append((len(sds), kw["adapt_delta"]))
+        n = len(sds)
+        rc = np.array([0, 1, 0]) if len(seen) == 1 else np.zeros(n, dtype=int)
+        return _fake_res(n, [0.1] * n), rc
+
+    monkeypatch.setattr(api, "_fit_batch", fake_fit)
+    monkeypatch.setattr(api, "prepare", lambda y, x, **kw: ("sd", len(y)))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = api.synergyscreen(_toy_experiments(3))
+    assert seen == [(3, 0.9), (1, 0.99)]
+    assert len(out["screenSummary"]) == 3 and "failed" not in out
