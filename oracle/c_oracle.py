@@ -29,7 +29,7 @@ class OrcNutsArgs(C.Structure):
                 ("gamma", C.c_double), ("kappa", C.c_double), ("t0", C.c_double),
                 ("init_buffer", C.c_int), ("term_buffer", C.c_int), ("window", C.c_int),
                 ("init_radius", C.c_double), ("seed", C.c_uint64), ("chain_id", C.c_int),
-                ("save_warmup", C.c_int)]
+                ("save_warmup", C.c_int), ("metric", C.c_int)]
 
 
 class OrcAdviArgs(C.Structure):
@@ -142,11 +142,12 @@ class Problem:
 
 
 def nuts_screen(problems, n_chains=4, num_warmup=1000, num_samples=1000, seed=1, adapt_delta=0.9,
-                want_outputs=True, nthreads=0):
+                want_outputs=True, nthreads=0, metric=0, stepsize_jitter=0.0):
     """Batch of problems x chains over host threads.  Returns (n_grad_total, outputs, sampler_params)."""
     a = OrcNutsArgs()
     lib().orc_nuts_defaults(C.byref(a))
     a.num_warmup, a.num_samples, a.seed, a.adapt_delta = num_warmup, num_samples, seed, adapt_delta
+    a.metric, a.stepsize_jitter = metric, stepsize_jitter
     arr = (OrcProblem * len(problems))(*[p.c for p in problems])
     stride = max(p.n_out for p in problems)
     outs = np.full((len(problems), n_chains, num_samples, stride), np.nan) if want_outputs else None

@@ -674,15 +674,29 @@ void orc_nuts_defaults(orc_nuts_args *a)
     a->stepsize = 1.0; a->stepsize_jitter = 0.0;
     a->gamma = 0.05; a->kappa = 0.75; a->t0 = 10;
     a->init_buffer = 75; a->term_buffer = 50; a->window = 25;
-    a->init_radius = 2.0; a->seed = 1; a->chain_id = 1; a->save_warmup = 0;
+    a->init_radius = 2.0; a->seed = 1; a->chain_id = 1; a->save_warmup = 0; a->metric = 0;
 }
 
 typedef struct {
     const orc_problem *p;
     int D;
-    const double *minv; /* diagonal inverse metric */
+    const double *minv; /* diagonal inverse metric (diag_e) */
     long n_grad;
+    int dense;          /* dense_e_metric: inverse metric Minv [D*D] (symmetric) and its Cholesky factor Lm (lower, row-major) */
+    const double *Minv, *Lm;
 } ham_t;
+
+/* p_sharp = M^-1 p  (diag_e_metric / dense_e_metric ::dtau_dp) */
+static void sharp(const ham_t *H, const double *p, double *out)
+{
+    int D = H->D;
+    if (!H->dense) { for (int i = 0; i < D; ++i) out[i] = H->minv[i] * p[i]; return; }
+    for (int i = 0; i < D; ++i) {
+        double s = 0;
+        for (int j = 0; j < D; ++j) s += H->Minv[(size_t)i * D + j] * p[j];
+        out[i] = s;
+    }
+}
 
 typedef struct { double *q, *p, *g; double V; } ps_t; /* V = -lp */
 
@@ -705,7 +719,14 @@ static void update_pg(ham_t *H, ps_t *z)
 static double kinetic(const ham_t *H, const ps_t *z)
 {
     double s = 0;
-    for (int i = 0; i < H->D; ++i) s += z->p[i] * z->p[i] * H->minv[i];
+    if (!H->dense) {
+        for (int i = 0; i < H->D; ++i) s += z->p[i] * z->p[i] * H->minv[i];
+    } else {
+        double *t = (double *)malloc(sizeof(double) * H->D);
+        sharp(H, z->p, t);
+        for (int i = 0; i < H->D; ++i) s += z->p[i] * t[i];
+        free(t);
+    }
     return 0.5 * s;
 }
 static double hamil(const ham_t *H, const ps_t *z) { return z->V + kinetic(H, z); }
@@ -713,7 +734,14 @@ static void leapfrog(ham_t *H, ps_t *z, double eps)
 {
     int D = H->D;
     for (int i = 0; i < D; ++i) z->p[i] -= 0.5 * eps * z->g[i];
-    for (int i = 0; i < D; ++i) z->q[i] += eps * H->minv[i] * z->p[i];
+    if (!H->dense) {
+        for (int i = 0; i < D; ++i) z->q[i] += eps * H->minv[i] * z->p[i];
+    } else {
+        double *t = (double *)malloc(sizeof(double) * D);
+        sharp(H, z->p, t);
+        for (int i = 0; i < D; ++i) z->q[i] += eps * t[i];
+        free(t);
+    }
     update_pg(H, z);
     for (int i = 0; i < D; ++i) z->p[i] -= 0.5 * eps * z->g[i];
 }
@@ -749,8 +777,9 @@ static int build_tree(tree_ctx *T, int depth, ps_t *z, ps_t *z_propose, double *
         *log_sum_weight = log_sum_exp2(*log_sum_weight, T->H0 - h);
         T->sum_metro += (T->H0 - h > 0) ? 1.0 : exp(T->H0 - h);
         ps_copy(z_propose, z, D);
+        sharp(H, z->p, psharp_beg);
         for (int i = 0; i < D; ++i) {
-            psharp_beg[i] = psharp_end[i] = H->minv[i] * z->p[i];
+            psharp_end[i] = psharp_beg[i];
             rho[i] += z->p[i];
             p_beg[i] = p_end[i] = z->p[i];
         }
@@ -789,11 +818,24 @@ static int build_tree(tree_ctx *T, int depth, ps_t *z, ps_t *z_propose, double *
 
 typedef struct { double accept, stepsize; int depth, n_leapfrog, divergent; double energy; } trans_info;
 
+/* diag_e_metric::sample_p: p_i = N(0,1) / sqrt(minv_i);  dense_e_metric::sample_p: p = L^-T z with M^-1 = L L^T */
+static void sample_p(const ham_t *H, double *p, uint64_t *rng)
+{
+    int D = H->D;
+    if (!H->dense) { for (int i = 0; i < D; ++i) p[i] = rnorm(rng) / sqrt(H->minv[i]); return; }
+    for (int i = 0; i < D; ++i) p[i] = rnorm(rng);
+    for (int i = D - 1; i >= 0; --i) {      /* back substitution on L^T */
+        double s = p[i];
+        for (int j = i + 1; j < D; ++j) s -= H->Lm[(size_t)j * D + i] * p[j];
+        p[i] = s / H->Lm[(size_t)i * D + i];
+    }
+}
+
 /* base_nuts::transition; z holds the current state (q, g, V) and is overwritten with the sample */
 static void nuts_transition(ham_t *H, ps_t *z, double eps, int max_depth, uint64_t *rng, trans_info *info)
 {
     int D = H->D;
-    for (int i = 0; i < D; ++i) z->p[i] = rnorm(rng) / sqrt(H->minv[i]);
+    sample_p(H, z->p, rng);
     ps_t z_fwd, z_bck, z_sample, z_propose;
     ps_alloc(&z_fwd, D); ps_alloc(&z_bck, D); ps_alloc(&z_sample, D); ps_alloc(&z_propose, D);
     ps_copy(&z_fwd, z, D); ps_copy(&z_bck, z, D); ps_copy(&z_sample, z, D); ps_copy(&z_propose, z, D);
@@ -801,9 +843,10 @@ static void nuts_transition(ham_t *H, ps_t *z, double eps, int max_depth, uint64
     double *p_fwd_fwd = w, *ps_fwd_fwd = w + D, *p_fwd_bck = w + 2 * D, *ps_fwd_bck = w + 3 * D;
     double *p_bck_fwd = w + 4 * D, *ps_bck_fwd = w + 5 * D, *p_bck_bck = w + 6 * D, *ps_bck_bck = w + 7 * D;
     double *rho = w + 8 * D, *rho_fwd = w + 9 * D, *rho_bck = w + 10 * D;
+    sharp(H, z->p, ps_fwd_fwd);
     for (int i = 0; i < D; ++i) {
         p_fwd_fwd[i] = p_fwd_bck[i] = p_bck_fwd[i] = p_bck_bck[i] = rho[i] = z->p[i];
-        ps_fwd_fwd[i] = ps_fwd_bck[i] = ps_bck_fwd[i] = ps_bck_bck[i] = H->minv[i] * z->p[i];
+        ps_fwd_bck[i] = ps_bck_fwd[i] = ps_bck_bck[i] = ps_fwd_fwd[i];
     }
     double lsw = 0, H0 = hamil(H, z);
     tree_ctx T = {H, eps, H0, 1, 0, 0.0, 0, rng};
@@ -864,7 +907,7 @@ static double init_stepsize(ham_t *H, ps_t *z, double eps, uint64_t *rng)
     ps_t z0;
     ps_alloc(&z0, D);
     ps_copy(&z0, z, D);
-    for (int i = 0; i < D; ++i) z->p[i] = rnorm(rng) / sqrt(H->minv[i]);
+    sample_p(H, z->p, rng);
     update_pg(H, z);
     double H0 = hamil(H, z);
     leapfrog(H, z, eps);
@@ -874,7 +917,7 @@ static double init_stepsize(ham_t *H, ps_t *z, double eps, uint64_t *rng)
     int dir = dH > log(0.8) ? 1 : -1;
     while (1) {
         ps_copy(z, &z0, D);
-        for (int i = 0; i < D; ++i) z->p[i] = rnorm(rng) / sqrt(H->minv[i]);
+        sample_p(H, z->p, rng);
         update_pg(H, z);
         H0 = hamil(H, z);
         leapfrog(H, z, eps);
@@ -898,7 +941,14 @@ long orc_nuts_chain(const orc_problem *p, const orc_nuts_args *a, double *draws_
     uint64_t rng = a->seed * 0x9E3779B97F4A7C15ULL + (uint64_t)a->chain_id * 0xD1B54A32D192ED03ULL + 12345;
     double *minv = (double *)malloc(sizeof(double) * D);
     for (int i = 0; i < D; ++i) minv[i] = 1.0;
-    ham_t H = {p, D, minv, 0};
+    const int dense = a->metric == 1;
+    double *Minv = NULL, *Lm = NULL, *cm = NULL, *cm2 = NULL;   /* dense_e: M^-1, chol(M^-1), Welford mean / cross products */
+    if (dense) {
+        Minv = (double *)calloc(2 * (size_t)D * D, sizeof(double)); Lm = Minv + (size_t)D * D;
+        cm = (double *)calloc((size_t)D + (size_t)D * D, sizeof(double)); cm2 = cm + D;
+        for (int i = 0; i < D; ++i) Minv[(size_t)i * D + i] = Lm[(size_t)i * D + i] = 1.0;
+    }
+    ham_t H = {p, D, minv, 0, dense, Minv, Lm};
     ps_t z;
     ps_alloc(&z, D);
     /* services::util::initialize: u ~ U(-R, R) until lp and gradient are finite (<= 100 tries) */
@@ -947,7 +997,7 @@ long orc_nuts_chain(const orc_problem *p, const orc_nuts_args *a, double *draws_
             eps = exp(x);
             /* windowed_adaptation / var_adaptation::learn_variance */
             int in_window = (it >= init_buffer) && (it < nw - term_buffer) && (it != nw);
-            if (in_window) {
+            if (in_window && !dense) {
                 wn += 1;
                 for (int i = 0; i < D; ++i) {
                     double d = z.q[i] - wm[i];
@@ -955,10 +1005,37 @@ long orc_nuts_chain(const orc_problem *p, const orc_nuts_args *a, double *draws_
                     wm2[i] += (z.q[i] - wm[i]) * d;
                 }
             }
+            if (in_window && dense) {   /* welford_covar_estimator::add_sample */
+                wn += 1;
+                double *dl = (double *)malloc(sizeof(double) * D);
+                for (int i = 0; i < D; ++i) { dl[i] = z.q[i] - cm[i]; cm[i] += dl[i] / wn; }
+                for (int i = 0; i < D; ++i)
+                    for (int j = 0; j < D; ++j) cm2[(size_t)i * D + j] += (z.q[i] - cm[i]) * dl[j];
+                free(dl);
+            }
             if (in_window && it == win_end) {
-                for (int i = 0; i < D; ++i) {
-                    double var = wm2[i] / (wn - 1.0);
-                    minv[i] = (wn / (wn + 5.0)) * var + 1e-3 * (5.0 / (wn + 5.0));
+                if (!dense) {
+                    for (int i = 0; i < D; ++i) {
+                        double var = wm2[i] / (wn - 1.0);
+                        minv[i] = (wn / (wn + 5.0)) * var + 1e-3 * (5.0 / (wn + 5.0));
+                    }
+                } else {   /* covar_adaptation::learn_covariance, then the factor dense_e_metric::sample_p needs */
+                    for (int i = 0; i < D; ++i)
+                        for (int j = 0; j < D; ++j)
+                            Minv[(size_t)i * D + j] = (wn / (wn + 5.0)) * cm2[(size_t)i * D + j] / (wn - 1.0) +
+                                                      (i == j ? 1e-3 * (5.0 / (wn + 5.0)) : 0.0);
+                    for (int i = 0; i < D; ++i)           /* symmetrise (the Welford update is not exactly symmetric) */
+                        for (int j = 0; j < i; ++j) {
+                            double v = 0.5 * (Minv[(size_t)i * D + j] + Minv[(size_t)j * D + i]);
+                            Minv[(size_t)i * D + j] = Minv[(size_t)j * D + i] = v;
+                        }
+                    for (int i = 0; i < D; ++i)
+                        for (int j = 0; j <= i; ++j) {
+                            double sum = Minv[(size_t)i * D + j];
+                            for (int k = 0; k < j; ++k) sum -= Lm[(size_t)i * D + k] * Lm[(size_t)j * D + k];
+                            Lm[(size_t)i * D + j] = (i == j) ? sqrt(sum) : sum / Lm[(size_t)j * D + j];
+                        }
+                    memset(cm, 0, sizeof(double) * ((size_t)D + (size_t)D * D));
                 }
                 wn = 0;
                 memset(wm, 0, sizeof(double) * 2 * D);
@@ -988,8 +1065,11 @@ long orc_nuts_chain(const orc_problem *p, const orc_nuts_args *a, double *draws_
         }
     }
     if (final_stepsize) *final_stepsize = eps;
-    if (final_inv_metric) memcpy(final_inv_metric, minv, sizeof(double) * D);
+    if (final_inv_metric) {
+        if (!dense) memcpy(final_inv_metric, minv, sizeof(double) * D);
+        else for (int i = 0; i < D; ++i) final_inv_metric[i] = Minv[(size_t)i * D + i];
+    }
     long ng = H.n_grad;
-    free(wm); free(minv); free(z.q);
+    free(wm); free(minv); free(z.q); free(Minv); free(cm);
     return ng;
 }

@@ -54,11 +54,12 @@ typedef struct {
     uint64_t seed;
     int chain_id;
     int save_warmup;
+    int metric;           /* 0 = diag_e, 1 = dense_e (what robust = TRUE selects, R/bayesynergy.R:112-115) */
 } orc_nuts_args;
 
 void orc_nuts_defaults(orc_nuts_args *a);
 
-/* One chain of diag_e adaptive NUTS (Stan's hmc_nuts_diag_e_adapt).
+/* One chain of adaptive NUTS (Stan's hmc_nuts_diag_e_adapt, or hmc_nuts_dense_e_adapt when a->metric == 1).
  * draws_u: [n_save * D] unconstrained draws (may be NULL); outputs: [n_save * n_out] write_array rows
  * (may be NULL); sampler_params: [n_save * 7] = accept_stat, stepsize, treedepth, n_leapfrog, divergent,
  * energy, lp (may be NULL).  n_save = num_samples (+ num_warmup if save_warmup).

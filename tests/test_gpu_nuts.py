@@ -134,6 +134,31 @@ def test_dense_metric_agrees_with_diag(built, datasets):
         b.close()
 
 
+def test_dense_tree_statistics_match_oracle(built, datasets):
+    """dense_e against the oracle's hmc_nuts_dense_e_adapt restatement (Welford covariance windows, regularisation,
+    p = L^-T z): adapted step size, tree depth and posterior means agree over 24 chains each."""
+    y, x = datasets["mathews:ispinesib + ibrutinib"]
+    sd = prepare(y, x)
+    nrep = 6
+    b = _lib.Batch([sd] * nrep)
+    res = b.sample(chains=4, iter=1000, warmup=500, seed=41, metric=1)
+    b.close()
+    sp = res["sampler_params"]
+    ng, outs, spo = nuts_screen([Problem(sd)] * nrep, n_chains=4, num_warmup=500, num_samples=500, seed=43, metric=1)
+    eps_g, eps_o = np.log(sp[..., 1].mean(axis=2)).ravel(), np.log(spo[..., 1].mean(axis=2)).ravel()
+    dep_g, dep_o = sp[..., 2].mean(axis=2).ravel(), spo[..., 2].mean(axis=2).ravel()
+    se_eps = np.hypot(eps_g.std(ddof=1), eps_o.std(ddof=1)) / np.sqrt(len(eps_g))
+    se_dep = np.hypot(dep_g.std(ddof=1), dep_o.std(ddof=1)) / np.sqrt(len(dep_g))
+    assert abs(eps_g.mean() - eps_o.mean()) < 4 * se_eps + 0.05, (eps_g.mean(), eps_o.mean(), se_eps)
+    assert abs(dep_g.mean() - dep_o.mean()) < 4 * se_dep + 0.1, (dep_g.mean(), dep_o.mean(), se_dep)
+    names = output_names(sd)
+    for qn in ("rVUS_f", "rVUS_p0", "VUS_syn", "VUS_ant"):
+        a = res["qdraws"][..., Q.index(qn)].reshape(4 * nrep, -1)
+        c = outs[..., names.index(qn)].reshape(4 * nrep, -1)
+        se = np.hypot(mcse_mean(a), mcse_mean(c))
+        assert abs(a.mean() - c.mean()) <= 3.0 * se + 1e-6, (qn, a.mean(), c.mean(), se)
+
+
 def test_oneil_shaped_screen(built, datasets):
     """cfg2-shaped problems (11x11 grid, 32 of 144 cells observed, 9-12 replicates; the two raw experiments shipped in
     ONeil_A375$failed) through synergyscreen(): two-pass strip products, unobserved cells, > 4 replicates per cell."""
