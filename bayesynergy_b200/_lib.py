@@ -23,7 +23,7 @@ EXPORTS = [
     "bsyn_batch_create", "bsyn_batch_destroy", "bsyn_last_error", "bsyn_version", "bsyn_num_params",
     "bsyn_num_outputs", "bsyn_max_params", "bsyn_max_outputs", "bsyn_num_problems", "bsyn_logp_grad",
     "bsyn_logp_grad_device", "bsyn_write_array", "bsyn_unconstrain", "bsyn_sampler_defaults", "bsyn_sample",
-    "bsyn_sample_device", "bsyn_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare",
+    "bsyn_sample_device", "bsyn_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare", "bsyn_output_name",
 ]
 VI_NAMES = ["status", "eta", "iterations", "elbo", "converged", "n_grad", "n_lp", "_reserved"]
 
@@ -113,6 +113,7 @@ def load():
     L.bsyn_ess.argtypes = [vp, C.c_int32, dp, dp]
     i32p = C.POINTER(C.c_int32)
     L.bsyn_prepare.argtypes = [dp, dp, C.c_int32, C.c_int32, dp, i32p, dp, i32p, dp, ip, i32p, i32p, i32p]
+    L.bsyn_output_name.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
     L.bsyn_advi_defaults.argtypes = [C.POINTER(BsynAdviArgs)]
     L.bsyn_advi_defaults.restype = None
     L.bsyn_advi.argtypes = [vp, C.POINTER(BsynAdviArgs), C.POINTER(BsynAdviSinks), C.POINTER(C.c_int64),
@@ -220,6 +221,15 @@ class Batch:
         return load().bsyn_num_outputs(self.h, k)
 
     # -- log_prob / grad_log_prob -----------------------------------------------------------------
+    def output_names(self, k=0):
+        """Flat names of one write_array row of experiment k, from the library (bsyn_output_name)."""
+        buf = C.create_string_buffer(48)
+        out = []
+        for i in range(self.num_outputs(k)):
+            _check(load().bsyn_output_name(self.h, k, i, buf, 48), "bsyn_output_name")
+            out.append(buf.value.decode())
+        return out
+
     def logp_grad(self, u, prob_idx=None, jacobian=True, want_grad=True, debug=False):
         """u: [B, >=D].  Returns (lp[B], grad[B, ld] or None, status[B][, dbg])."""
         u = np.atleast_2d(np.asarray(u, dtype=np.float64))

@@ -297,6 +297,53 @@ extern "C" void bsyn_batch_destroy(bsyn_batch *b)
 
 extern "C" int32_t bsyn_num_params(const bsyn_batch *b, int32_t k) { return (b && k >= 0 && k < b->n) ? b->descs[k].D : -1; }
 extern "C" int32_t bsyn_num_outputs(const bsyn_batch *b, int32_t k) { return (b && k >= 0 && k < b->n) ? b->descs[k].n_out : -1; }
+// Flat name of entry `index` of one write_array row of problem k (the first bsyn_num_params entries are the
+// parameters): declaration order of src/stanExports_gp_grid.h:1588-1622 / :2256-2402, matrices column-major.
+extern "C" int bsyn_output_name(const bsyn_batch *b, int32_t k, int32_t index, char *buf, int32_t buflen)
+{
+    if (!b || k < 0 || k >= b->n || !buf || buflen < 2) return fail(BSYN_ERR_ARG, "bsyn_output_name: bad argument");
+    const ProbDesc &d = b->descs[k];
+    if (index < 0 || index >= d.n_out) return fail(BSYN_ERR_ARG, "bsyn_output_name: index out of range");
+    const bool gp = b->opts.model == BSYN_MODEL_GP_GRID;
+    const int n1 = d.n1, n2 = d.n2, G = n1 * n2;
+    int i = index;
+    auto put = [&](const char *fmt, int a, int c) { snprintf(buf, (size_t)buflen, fmt, a, c); return BSYN_OK; };
+    auto mat = [&](const char *name) {   // (row = drug-2 level, column = drug-1 level), column-major
+        char f[32];
+        snprintf(f, sizeof f, "%s[%%d,%%d]", name);
+        return put(f, i % n2 + 1, i / n2 + 1);
+    };
+    auto vec = [&](const char *name) { char f[32]; snprintf(f, sizeof f, "%s[%%d]", name); return put(f, i + 1, 0); };
+    static const char *pre[] = {"la_1[1]", "la_2[1]", "log10_ec50_1", "log10_ec50_2", "theta_1", "theta_2", "slope_1", "slope_2",
+                                "b1", "b2", "ell", "sigma_f", "alpha[1]"};
+    const int skip = b->opts.est_la ? 0 : 2;
+    const int npre = 8 - skip + (gp ? 4 + (b->opts.est_alpha ? 1 : 0) : 0);
+    if (i < npre) return put(pre[i + skip], 0, 0);
+    i -= npre;
+    if (gp) { if (i < G) return mat("z"); i -= G; }
+    static const char *post[] = {"s", "s2_log10_ec50_1", "s2_log10_ec50_2"};
+    if (i < 3) return put(post[i], 0, 0);
+    i -= 3;
+    if (i < G) return mat("p0");
+    i -= G;
+    if (i < n1) return vec("p01");
+    i -= n1;
+    if (i < n2) return vec("p02");
+    i -= n2;
+    if (gp) {
+        if (i < G) return mat("Delta");
+        i -= G;
+        if (i < G) return mat("GP");
+        i -= G;
+    }
+    if (i < 2) return put(i ? "ec50_2" : "ec50_1", 0, 0);
+    i -= 2;
+    if (i < d.N) return vec("CPO");
+    i -= d.N;
+    static const char *tail[] = {"dss_1", "dss_2", "rVUS_f", "rVUS_p0", "VUS_Delta", "VUS_syn", "VUS_ant"};
+    return put(tail[i], 0, 0);
+}
+
 extern "C" int32_t bsyn_max_params(const bsyn_batch *b) { return b ? b->maxD : -1; }
 extern "C" int32_t bsyn_max_outputs(const bsyn_batch *b) { return b ? b->maxOut : -1; }
 extern "C" int32_t bsyn_num_problems(const bsyn_batch *b) { return b ? b->n : -1; }

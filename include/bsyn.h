@@ -75,6 +75,10 @@ int bsyn_version(void);
  * Replace: num_pars_unconstrained, param_names/param_dims/param_fnames_oi (cc:16-21, 29). */
 int32_t bsyn_num_params(const bsyn_batch *b, int32_t problem);     /* D, unconstrained */
 int32_t bsyn_num_outputs(const bsyn_batch *b, int32_t problem);    /* one write_array row (without lp__) */
+/* Flat name ("z[3,2]", "CPO[17]", "VUS_syn", ...) of entry `index` of one write_array row of `problem`: what
+ * param_names / param_fnames_oi (cc:16-18) report, in the declaration order of src/stanExports_gp_grid.h:2256-2402.
+ * The first bsyn_num_params entries are the parameters.  Host-only (no GPU involved). */
+int bsyn_output_name(const bsyn_batch *b, int32_t problem, int32_t index, char *buf, int32_t buflen);
 int32_t bsyn_max_params(const bsyn_batch *b);
 int32_t bsyn_max_outputs(const bsyn_batch *b);
 int32_t bsyn_num_problems(const bsyn_batch *b);

@@ -186,6 +186,20 @@ def test_value_only_path_matches_full_evaluation(built, datasets):
         b.close()
 
 
+def test_output_names_from_the_library(built, datasets):
+    """bsyn_output_name (what the Rcpp shim needs for param_names / param_fnames_oi, cc:16-18) against the Python
+    statement of the declaration order (src/stanExports_gp_grid.h:2256-2402), for every layout variant."""
+    for dname, kw, model in (("mathews:ispinesib + ibrutinib", {}, "gp_grid"),
+                             ("mathews:ispinesib + ibrutinib", dict(lower_asymptotes=False), "gp_grid"),
+                             ("oneil_failed:1", dict(type=4), "gp_grid"),
+                             ("synthetic:7", {}, "nointeraction"),
+                             ("synthetic:7", dict(lower_asymptotes=False), "nointeraction")):
+        sd = prepare(*datasets[dname], **kw)
+        b = _lib.Batch([sd], model=model)
+        assert b.output_names(0) == output_names(sd, model), (dname, kw, model)
+        b.close()
+
+
 def test_write_array_against_oracle(built, datasets, cond_fn):
     for dname, v in itertools.product(("mathews:ispinesib + ibrutinib", "synthetic:7", "oneil_failed:0"),
                                       (dict(), dict(type=2, heteroscedastic=False), dict(robust=True, lower_asymptotes=False))):
