@@ -56,3 +56,14 @@ def mcse_mean(x):
     """Monte Carlo standard error of the posterior mean of x[chains, draws]."""
     ess, _ = split_ess_rhat(x)
     return float(np.std(x, ddof=1) / np.sqrt(max(ess, 1.0)))
+
+
+def bulk_ess_rhat(x):
+    """Rank-normalised split-chain bulk-ESS and R-hat (Vehtari, Gelman, Simpson, Carpenter & Buerkner 2021; what newer
+    rstan prints as Bulk_ESS): the pooled draws are replaced by normal scores of their fractional ranks, then the
+    split-chain estimator above is applied.  x: [chains, draws]."""
+    from scipy.stats import norm, rankdata
+    x = np.asarray(x, dtype=np.float64)
+    r = rankdata(x.reshape(-1), method="average").reshape(x.shape)
+    z = norm.ppf((r - 0.375) / (x.size + 0.25))
+    return split_ess_rhat(z)

@@ -79,3 +79,21 @@ def test_bayesynergy_api_with_bayes_factor(built, datasets):
     assert np.isfinite(fit["LPML"]) and fit["returnCode"] in (0, 1)
     assert fit["posterior"]["Delta"].shape == (2000, 5, 5) and fit["posterior"]["CPO"].shape == (2000, 36)
     assert fit["bayesfactor"] > 1.0          # strong interaction in this experiment (the vignette reports synergy)
+
+
+def test_bulk_ess_rank_normalised():
+    """Host-side rank-normalised bulk ESS: ~N for independent draws whatever the tails, and close to the classic
+    estimator for a Gaussian AR(1) chain."""
+    from bayesynergy_b200.diagnostics import bulk_ess_rhat, split_ess_rhat
+    rng = np.random.default_rng(5)
+    x = rng.standard_cauchy(size=(4, 1000))
+    ess, rhat = bulk_ess_rhat(x)
+    assert 3000 < ess < 5200 and abs(rhat - 1.0) < 0.01
+    phi = 0.8
+    e = rng.standard_normal((4, 2000))
+    y = np.zeros_like(e)
+    for t in range(1, 2000):
+        y[:, t] = phi * y[:, t - 1] + e[:, t]
+    eb, _ = bulk_ess_rhat(y)
+    ec, _ = split_ess_rhat(y)
+    assert abs(eb - ec) < 0.15 * ec and 500 < ec < 1400      # theory: 8000 (1 - phi) / (1 + phi) = 889
