@@ -686,6 +686,7 @@ extern "C" int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *a, const bsyn_advi
         !(a->tol_rel_obj > 0) || !(a->eta > 0))
         return fail(BSYN_ERR_ARG, "bsyn_advi: bad arguments");
     if (a->grad_samples != 1) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_advi: grad_samples must be 1");
+    if (sinks->mean && sinks->ld_mean < b->maxD) return fail(BSYN_ERR_ARG, "bsyn_advi: ld_mean < bsyn_max_params");
     const int cb_size = (int)std::max(0.1 * a->iter / a->eval_elbo, 2.0);
     if (cb_size > 32) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_advi: iter / eval_elbo > 320 is not supported");
     CK(cudaSetDevice(b->device));
@@ -762,7 +763,6 @@ extern "C" int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *a, const bsyn_advi
     if (e == cudaSuccess) e = cudaMemcpy(&ng, b->d_gradctr, sizeof(ng), cudaMemcpyDeviceToHost);
     if (total_evals) *total_evals = (int64_t)ng;
     if (e == cudaSuccess && sinks->mean) {
-        if (sinks->ld_mean < b->maxD) { cleanup(); return fail(BSYN_ERR_ARG, "bsyn_advi: ld_mean < bsyn_max_params"); }
         e = cudaMemcpy2D(sinks->mean, sizeof(double) * sinks->ld_mean, d_mean, sizeof(double) * b->maxD, sizeof(double) * b->maxD, b->n, cudaMemcpyDeviceToHost);
     }
     if (e == cudaSuccess && sinks->info) e = cudaMemcpy(sinks->info, d_info, sizeof(double) * (size_t)b->n * BSYN_NVI, cudaMemcpyDeviceToHost);
