@@ -23,7 +23,7 @@ EXPORTS = [
     "bsyn_batch_create", "bsyn_batch_destroy", "bsyn_last_error", "bsyn_version", "bsyn_num_params",
     "bsyn_num_outputs", "bsyn_max_params", "bsyn_max_outputs", "bsyn_num_problems", "bsyn_logp_grad",
     "bsyn_logp_grad_device", "bsyn_write_array", "bsyn_unconstrain", "bsyn_sampler_defaults", "bsyn_sample",
-    "bsyn_sample_device", "bsyn_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare", "bsyn_output_name",
+    "bsyn_sample_device", "bsyn_ess", "bsyn_bulk_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare", "bsyn_output_name",
 ]
 VI_NAMES = ["status", "eta", "iterations", "elbo", "converged", "n_grad", "n_lp", "_reserved"]
 
@@ -111,6 +111,7 @@ def load():
     L.bsyn_sample_device.argtypes = [vp, C.POINTER(BsynSamplerArgs), C.POINTER(C.c_int64), C.POINTER(C.c_float),
                                      C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.bsyn_ess.argtypes = [vp, C.c_int32, dp, dp]
+    L.bsyn_bulk_ess.argtypes = [vp, C.c_int32, dp, dp, dp]
     i32p = C.POINTER(C.c_int32)
     L.bsyn_prepare.argtypes = [dp, dp, C.c_int32, C.c_int32, dp, i32p, dp, i32p, dp, ip, i32p, i32p, i32p]
     L.bsyn_output_name.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
@@ -359,6 +360,13 @@ class Batch:
         _check(load().bsyn_sample_device(self.h, C.byref(a), C.byref(ng), C.byref(ms), None, None, None),
                "bsyn_sample_device")
         return ng.value, ms.value
+
+    def bulk_ess(self, q):
+        """Rank-normalised bulk ESS, R-hat and tail ESS per experiment, on the device (bsyn_bulk_ess)."""
+        qi = Q_NAMES.index(q) if isinstance(q, str) else int(q)
+        ess, rhat, tail = np.empty(self.n), np.empty(self.n), np.empty(self.n)
+        _check(load().bsyn_bulk_ess(self.h, qi, _dp(ess), _dp(rhat), _dp(tail)), "bsyn_bulk_ess")
+        return ess, rhat, tail
 
     def ess(self, q):
         qi = Q_NAMES.index(q) if isinstance(q, str) else int(q)

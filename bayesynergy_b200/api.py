@@ -245,6 +245,22 @@ def _screen_rows(experiments, offset, res, return_codes):
     return rows
 
 
+_PREPARE_KEYS = {"type", "lower_asymptotes", "heteroscedastic", "robust", "rho", "pcprior", "pcprior_hypers", "lambda_",
+                 "nu", "bayes_factor"}
+
+
+def _check_prepare_params(params):
+    """Validate bayesynergy_params ONCE, before the per-experiment loop: an unknown key is the caller's error (a
+    TypeError), not a failed experiment.  `lambda` is accepted as the reference spells it (R/bayesynergy.R:57)."""
+    if "lambda" in params:
+        params["lambda_"] = params.pop("lambda")
+    for k in ("units", "drug_names", "experiment_ID"):    # presentation-only arguments of bayesynergy()
+        params.pop(k, None)
+    unknown = sorted(set(params) - _PREPARE_KEYS)
+    if unknown:
+        raise TypeError(f"unknown bayesynergy_params: {unknown}")
+
+
 def _fit_batch(sds, kw, device, max_treedepth):
     """One batched launch over a list of prepared experiments; returns (res, returnCode[n])."""
     b = _lib.Batch(sds, model="gp_grid", device=device)
@@ -280,7 +296,7 @@ def _fit_batch_vb(sds, vbkw, seed, device):
     return res, rc
 
 
-def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_params=None, device=0,
+def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_params=None, device=None,
                   rank=0, world_size=1):
     """Fit a list of experiments (dicts with y, x and optional drug_names / experiment_ID) in one batched
     device launch (R/synergyscreen.R:58-463).  Returns dict(screenSummary=[rows], failed=[experiments]).
@@ -299,6 +315,9 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
                             world_size)
         out["screenSummary"] = list(old) + out["screenSummary"]
         return out
+    if device is None:      # one process per GPU: under torchrun every rank lands on its own device
+        import os
+        device = int(os.environ.get("LOCAL_RANK", "0")) if world_size > 1 else 0
     params = dict(bayesynergy_params or {})
     method = params.pop("method", "sampling")
     if method not in ("sampling", "vb"):
@@ -312,13 +331,17 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
     type_, robust = params.get("type", 3), params.get("robust", False)
     lo, hi = shard_slices(len(experiments), world_size)[rank]
     mine = experiments[lo:hi]
-    sds, ok_idx, rows_failed = [], [], []
+    sds, ok_idx, rows_failed, fail_reason = [], [], [], {}
+    _lib.load()                                 # a missing / unbuilt libbsyn.so is not a per-experiment failure
+    _check_prepare_params(params)
     for k, e in enumerate(mine):
         try:
             sds.append(prepare(e["y"], e["x"], native=True, **params))
             ok_idx.append(k)
-        except Exception:                      # tryCatch(... error = returnCode 2), R/synergyscreen.R:143-146
-            rows_failed.append(k)
+        except (ValueError, NotImplementedError) as err:   # the mirrored stop() cases of bayesynergy(): tryCatch(...
+            rows_failed.append(k)                           # error = returnCode 2), R/synergyscreen.R:143-146
+            fail_reason[k] = f"{type(err).__name__}: {err}"
+
     rows = {}
     if sds and method == "vb":
         res, rc = _fit_batch_vb(sds, vbkw, seed, device)
@@ -346,7 +369,7 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
         # retry the experiments with warnings at adapt_delta = 0.99 (R/synergyscreen.R:149-171), as ONE smaller launch
         retry = [j for j in range(len(sds)) if rc[j] != 0]
         tries = 0
-        while retry and tries < max_retries:
+        while retry and tries <= max_retries:   # the reference's loop body runs max_retries + 1 times (quirk 9)
             ctl2 = dict(ctl, adapt_delta=0.99)
             kw2 = _sampler_kwargs(ctl2, chains, iter_, warmup, thin, seed + 1000 * (tries + 1))
             res2, rc2 = _fit_batch([sds[j] for j in retry], kw2, device, kw2.get("max_treedepth", 10))
@@ -366,6 +389,7 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
     out = dict(screenSummary=kept)
     if failed_ids:
         out["failed"] = [mine[k] for k in failed_ids]
+        out["failed_reason"] = {lo + k + 1: fail_reason.get(k, "returnCode 2") for k in failed_ids}
     n_warn = sum(1 for r in kept if r["returnCode"] > 0)
     if kept and n_warn:
         warnings.warn(f"{100.0 * n_warn / len(kept):.2f}% of experiments returned a warning or error -- check these.")

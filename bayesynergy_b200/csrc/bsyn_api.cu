@@ -5,6 +5,7 @@
 #include "../../include/bsyn.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -19,7 +20,7 @@
 using namespace bsyn;
 
 static thread_local std::string g_err;
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // batches on different host threads share it
 
 #define CK(call)                                                                                      \
     do {                                                                                              \
@@ -36,6 +37,17 @@ static int fail(int code, const std::string &msg)
     return code;
 }
 
+
+// device allocation that frees itself on every return path
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)); }
+    operator T *() const { return p; }
+};
 
 struct bsyn_batch {
     int device = 0;
@@ -151,7 +163,7 @@ static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t
 
 extern "C" const char *bsyn_last_error(void) { return g_err.c_str(); }
 extern "C" int bsyn_version(void) { return BSYN_VERSION; }
-extern "C" int64_t bsyn_launch_count(void) { return g_launches; }
+extern "C" int64_t bsyn_launch_count(void) { return g_launches.load(); }
 
 extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const bsyn_options *opts, int32_t device,
                                  bsyn_batch **out)
@@ -167,20 +179,24 @@ extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const 
     if (device < 0 || device >= ndev) return fail(BSYN_ERR_ARG, "bsyn_batch_create: bad device ordinal");
     CK(cudaSetDevice(device));
     bsyn_batch *b = new bsyn_batch();
+    struct Guard {   // every early return below destroys the half-built batch (stream, device buffers)
+        bsyn_batch *b;
+        ~Guard() { if (b) bsyn_batch_destroy(b); }
+    } guard{b};
     b->device = device; b->n = n; b->F = F; b->opts = *opts;
     // pick the smallest kernel variant that fits every problem
     int cpl = 1;
     for (int k = 0; k < n; ++k) {
         const bsyn_problem &p = problems[k];
-        if (p.n1 < 1 || p.n2 < 1 || p.N < 0 || !p.y || !p.ii_obs || !p.x1 || !p.x2) { delete b; return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": bad sizes or null pointer"); }
+        if (p.n1 < 1 || p.n2 < 1 || p.N < 0 || !p.y || !p.ii_obs || !p.x1 || !p.x2) { return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": bad sizes or null pointer"); }
         const long long Nexp = (long long)(p.n1 + p.n2 + p.n1 * p.n2 + 1) * p.nrep - p.nmissing;
-        if (Nexp != p.N) { delete b; return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": N != (n1+n2+n1*n2+1)*nrep - nmissing (gp_grid.stan:31)"); }
+        if (Nexp != p.N) { return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": N != (n1+n2+n1*n2+1)*nrep - nmissing (gp_grid.stan:31)"); }
         while (cpl <= 8) {
             bool f = cpl == 1 ? fits<1>(p.n1, p.n2) : cpl == 2 ? fits<2>(p.n1, p.n2) : cpl == 4 ? fits<4>(p.n1, p.n2) : fits<8>(p.n1, p.n2);
             if (f) break;
             cpl *= 2;
         }
-        if (cpl > 8) { delete b; return fail(BSYN_ERR_UNSUPPORTED, "problem " + std::to_string(k) + ": dose grid larger than 16 x 15 is not supported by the compiled kernel variants"); }
+        if (cpl > 8) { return fail(BSYN_ERR_UNSUPPORTED, "problem " + std::to_string(k) + ": dose grid larger than 16 x 15 is not supported by the compiled kernel variants"); }
     }
     b->cpl = cpl;
     std::vector<double> dpool;
@@ -229,8 +245,8 @@ extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const 
         std::vector<int> cstart(ncf + 1, 0);
         for (int t = 0; t < N; ++t) {
             const int c = p.ii_obs[t] - 1;
-            if (c < 0 || c >= ncf) { delete b; return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": ii_obs out of range"); }
-            if (!(p.y[t] == p.y[t])) { delete b; return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": y contains NaN (missing values must be removed, R/bayesynergy.R:153-154)"); }
+            if (c < 0 || c >= ncf) { return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": ii_obs out of range"); }
+            if (!(p.y[t] == p.y[t])) { return fail(BSYN_ERR_ARG, "problem " + std::to_string(k) + ": y contains NaN (missing values must be removed, R/bayesynergy.R:153-154)"); }
             cnt[c] += 1.0; sum[c] += p.y[t];
         }
         for (int c = 0; c < ncf; ++c) { if (cnt[c] > 0) sum[c] /= cnt[c]; cstart[c + 1] = cstart[c] + (int)cnt[c]; }
@@ -280,6 +296,7 @@ extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const 
     if (pin_i) cudaHostUnregister(ipool.data());
     if (ce != cudaSuccess) { g_err = std::string("upload of the problem pools: ") + cudaGetErrorString(ce); return BSYN_ERR_CUDA; }
     CK(cudaMemcpy(b->d_tri, tri.data(), sizeof(int) * tri.size(), cudaMemcpyHostToDevice));
+    guard.b = nullptr;
     *out = b;
     return BSYN_OK;
 }
@@ -393,12 +410,12 @@ static int logp_host(bsyn_batch *b, int B, const int *prob_idx, const double *u,
     for (int k = 0; k < B; ++k)
         if (prob_idx[k] < 0 || prob_idx[k] >= b->n) return fail(BSYN_ERR_ARG, "bsyn_logp_grad: prob_idx out of range");
     CK(cudaSetDevice(b->device));
-    int *d_idx = nullptr, *d_st = nullptr;
-    double *d_u = nullptr, *d_lp = nullptr, *d_g = nullptr, *d_dbg = nullptr;
-    CK(cudaMalloc(&d_idx, sizeof(int) * B)); CK(cudaMalloc(&d_st, sizeof(int) * B));
-    CK(cudaMalloc(&d_u, sizeof(double) * (size_t)B * ldu)); CK(cudaMalloc(&d_lp, sizeof(double) * B));
-    if (grad) { CK(cudaMalloc(&d_g, sizeof(double) * (size_t)B * ldu)); CK(cudaMemsetAsync(d_g, 0, sizeof(double) * (size_t)B * ldu, b->stream)); }
-    if (dbg) { CK(cudaMalloc(&d_dbg, sizeof(double) * (size_t)B * dbg_stride)); CK(cudaMemsetAsync(d_dbg, 0, sizeof(double) * (size_t)B * dbg_stride, b->stream)); }
+    DevBuf<int> d_idx, d_st;
+    DevBuf<double> d_u, d_lp, d_g, d_dbg;
+    CK(d_idx.alloc(B)); CK(d_st.alloc(B));
+    CK(d_u.alloc((size_t)B * ldu)); CK(d_lp.alloc(B));
+    if (grad) { CK(d_g.alloc((size_t)B * ldu)); CK(cudaMemsetAsync(d_g, 0, sizeof(double) * (size_t)B * ldu, b->stream)); }
+    if (dbg) { CK(d_dbg.alloc((size_t)B * dbg_stride)); CK(cudaMemsetAsync(d_dbg, 0, sizeof(double) * (size_t)B * dbg_stride, b->stream)); }
     CK(cudaMemcpyAsync(d_idx, prob_idx, sizeof(int) * B, cudaMemcpyHostToDevice, b->stream));
     CK(cudaMemcpyAsync(d_u, u, sizeof(double) * (size_t)B * ldu, cudaMemcpyHostToDevice, b->stream));
     int rc = launch_logp(b, B, d_idx, d_u, ldu, jac, d_lp, d_g, d_st, d_dbg, dbg_stride, b->stream);
@@ -409,7 +426,6 @@ static int logp_host(bsyn_batch *b, int B, const int *prob_idx, const double *u,
         if (dbg) CK(cudaMemcpyAsync(dbg, d_dbg, sizeof(double) * (size_t)B * dbg_stride, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
     }
-    cudaFree(d_idx); cudaFree(d_st); cudaFree(d_u); cudaFree(d_lp); cudaFree(d_g); cudaFree(d_dbg);
     return rc;
 }
 
@@ -440,10 +456,10 @@ extern "C" int bsyn_write_array(bsyn_batch *b, int32_t B, const int32_t *prob_id
     for (int k = 0; k < B; ++k)
         if (prob_idx[k] < 0 || prob_idx[k] >= b->n) return fail(BSYN_ERR_ARG, "bsyn_write_array: prob_idx out of range");
     CK(cudaSetDevice(b->device));
-    int *d_idx = nullptr, *d_st = nullptr;
-    double *d_u = nullptr, *d_out = nullptr;
-    CK(cudaMalloc(&d_idx, sizeof(int) * B)); CK(cudaMalloc(&d_st, sizeof(int) * B));
-    CK(cudaMalloc(&d_u, sizeof(double) * (size_t)B * ldu)); CK(cudaMalloc(&d_out, sizeof(double) * (size_t)B * ldo));
+    DevBuf<int> d_idx, d_st;
+    DevBuf<double> d_u, d_out;
+    CK(d_idx.alloc(B)); CK(d_st.alloc(B));
+    CK(d_u.alloc((size_t)B * ldu)); CK(d_out.alloc((size_t)B * ldo));
     CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)B * ldo, b->stream));
     CK(cudaMemcpyAsync(d_idx, prob_idx, sizeof(int) * B, cudaMemcpyHostToDevice, b->stream));
     CK(cudaMemcpyAsync(d_u, u, sizeof(double) * (size_t)B * ldu, cudaMemcpyHostToDevice, b->stream));
@@ -456,7 +472,6 @@ extern "C" int bsyn_write_array(bsyn_batch *b, int32_t B, const int32_t *prob_id
     CK(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)B * ldo, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(status, d_st, sizeof(int) * B, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    cudaFree(d_idx); cudaFree(d_st); cudaFree(d_u); cudaFree(d_out);
     return BSYN_OK;
 }
 
@@ -511,11 +526,17 @@ struct DevSinks {
     int ld_cpo = 0, ld_im = 0;
 };
 
-static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks &ds, int64_t *total_grad, float *elapsed_ms)
+static int check_sampler_args(const bsyn_sampler_args *a)
 {
     if (a->chains < 1 || a->iter < 1 || a->warmup < 0 || a->warmup > a->iter || a->thin < 1 || a->max_treedepth < 1 || a->max_treedepth > 20)
         return fail(BSYN_ERR_ARG, "bsyn_sample: bad sampler arguments");
     if (a->metric != 0 && a->metric != 1) return fail(BSYN_ERR_ARG, "bsyn_sample: metric must be 0 (diag_e) or 1 (dense_e)");
+    return BSYN_OK;
+}
+
+static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks &ds, int64_t *total_grad, float *elapsed_ms)
+{
+    if (int rc0 = check_sampler_args(a)) return rc0;
     CK(cudaSetDevice(b->device));
     SamplerParams sp{};
     sp.n_problems = b->n; sp.chains = a->chains;
@@ -609,6 +630,8 @@ extern "C" int bsyn_sample_device(bsyn_batch *b, const bsyn_sampler_args *args, 
 extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const bsyn_sample_sinks *sinks, int64_t *total_grad_evals)
 {
     if (!b || !args || !sinks) return fail(BSYN_ERR_ARG, "bsyn_sample: null argument");
+    if (int rc0 = check_sampler_args(args)) return rc0;   // before any buffer is sized from them
+    if (sinks->cpo_mean && args->iter == args->warmup) return fail(BSYN_ERR_ARG, "bsyn_sample: cpo_mean needs at least one sampling iteration");
     CK(cudaSetDevice(b->device));
     const int ns_samp = (args->iter - args->warmup + args->thin - 1) / std::max(1, args->thin);
     const int ns_warm = args->save_warmup ? (args->warmup + args->thin - 1) / std::max(1, args->thin) : 0;
@@ -799,5 +822,34 @@ extern "C" int bsyn_ess(bsyn_batch *b, int32_t q, double *ess, double *rhat)
     CK(cudaStreamSynchronize(b->stream));
     cudaFree(d_out);
     for (int k = 0; k < b->n; ++k) { ess[k] = tmp[2 * k]; if (rhat) rhat[k] = tmp[2 * k + 1]; }
+    return BSYN_OK;
+}
+
+// Rank-normalised bulk ESS / R-hat and tail ESS of generated scalar q for every problem (bulk_ess_kernel).
+extern "C" int bsyn_bulk_ess(bsyn_batch *b, int32_t q, double *ess_bulk, double *rhat, double *ess_tail)
+{
+    if (!b || q < 0 || q >= BSYN_NQ || !ess_bulk) return fail(BSYN_ERR_ARG, "bsyn_bulk_ess: bad argument");
+    const int ns = b->last_nsave - b->last_nskip;
+    if (!b->d_qdraws || ns < 8) return fail(BSYN_ERR_ARG, "bsyn_bulk_ess: no draws from a previous bsyn_sample call");
+    if ((long long)ns * b->last_chains > BULK_MAX_DRAWS)
+        return fail(BSYN_ERR_UNSUPPORTED, "bsyn_bulk_ess: more than 8192 pooled draws per problem (use bsyn_ess)");
+    CK(cudaSetDevice(b->device));
+    DevBuf<double> d_out;
+    CK(d_out.alloc(4 * (size_t)b->n));
+    const size_t bytes = bulk_ess_smem_bytes(ns * b->last_chains);
+    CK(cudaFuncSetAttribute(bulk_ess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const int grid = std::max(1, std::min(b->n, b->num_sms * 4));
+    bulk_ess_kernel<<<grid, BULK_THREADS, bytes, b->stream>>>(b->d_qdraws, b->n, nullptr, b->last_chains, b->last_nsave,
+                                                              b->last_nskip, ns, nullptr, q, d_out);
+    ++g_launches;
+    CK(cudaGetLastError());
+    std::vector<double> tmp(4 * (size_t)b->n);
+    CK(cudaMemcpyAsync(tmp.data(), d_out, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int k = 0; k < b->n; ++k) {
+        ess_bulk[k] = tmp[4 * k];
+        if (rhat) rhat[k] = tmp[4 * k + 1];
+        if (ess_tail) ess_tail[k] = tmp[4 * k + 2];
+    }
     return BSYN_OK;
 }

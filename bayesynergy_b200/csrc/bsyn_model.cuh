@@ -24,6 +24,10 @@ namespace bsyn {
 #define BSYN_IG55_C 4.869135731822556          /* 5 log 5 - lgamma(5) */
 #define BSYN_IG32_C 1.38629436111989061883     /* 3 log 2 - lgamma(3) */
 #define BSYN_LOG_0_1 (-2.30258509299404568402)
+// The heteroscedastic -n/2 log(f + lambda) terms of a lane are folded into ONE logarithm of a product of up to 9 factors
+// v^n, n <= 4; a factor below this bound (only possible with a user lambda << the default 0.005) takes its own logarithm
+// instead, so the product stays a normal double (1e-8^36 = 1e-288).
+#define BSYN_VPROD_MIN 1e-8
 
 template <int CPL> struct WVec {
     double z[CPL];
@@ -266,7 +270,7 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
         const double v = f + F.lambda;
         if (!(v > 0.0)) { ok = false; return 0.0; }
         iv = fast_rcp(v);
-        if (n <= 4.0) {
+        if (n <= 4.0 && v >= BSYN_VPROD_MIN) {
             const double v2 = v * v;
             vprod *= (n == 1.0) ? v : (n == 2.0) ? v2 : (n == 3.0) ? v2 * v : v2 * v2;
         } else {
@@ -323,8 +327,9 @@ __device__ __forceinline__ double lik_cell_normal(const Flags &F, const ProbS &P
         ok = ok && ((v > 0.0) || (n == 0.0));
         const double iv = fast_rcp(v);
         const double v2 = v * v;
-        vprod *= (n == 0.0) ? 1.0 : (n == 1.0) ? v : (n == 2.0) ? v2 : (n == 3.0) ? v2 * v : (n == 4.0) ? v2 * v2 : 1.0;
-        if (n > 4.0) lpl += -0.5 * n * cold_log(v);
+        const bool fold = v >= BSYN_VPROD_MIN;
+        vprod *= (n == 0.0 || !fold) ? 1.0 : (n == 1.0) ? v : (n == 2.0) ? v2 : (n == 3.0) ? v2 * v : (n == 4.0) ? v2 * v2 : 1.0;
+        if ((n > 4.0 || !fold) && n > 0.0) lpl += -0.5 * n * cold_log(v);
         const double qi = Q * is2 * iv;
         lpl = fma(-0.5, qi, lpl);
         slogbar += qi - n;

@@ -913,7 +913,17 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                     cs[0] = eps; cs[1] = n_div; cs[2] = n_maxd; cs[3] = nleap_tot; cs[4] = nleap_samp;
                     cs[5] = n_samp_it > 0 ? acc_sum / n_samp_it : 0.0; cs[6] = 0.0; cs[7] = (double)isave;
                 }
-                if (sp.inv_metric) store_user_vec<CPL>(F, pd, cell, minv, sp.inv_metric + cg * sp.ld_im);
+                if (sp.inv_metric) {
+                    if constexpr (DENSE) {   // the sink is a D-vector: the diagonal of the adapted dense M^-1
+                        WVec<CPL> dgm;
+#pragma unroll
+                        for (int t = 0; t < CPL; ++t) dgm.z[t] = (double)Mf[(size_t)(t * 32 + lane) * (DI + 1)];
+                        dgm.s = (double)Mf[(size_t)(CPL * 32 + lane) * (DI + 1)];
+                        store_user_vec<CPL>(F, pd, cell, dgm, sp.inv_metric + cg * sp.ld_im);
+                    } else {
+                        store_user_vec<CPL>(F, pd, cell, minv, sp.inv_metric + cg * sp.ld_im);
+                    }
+                }
                 phase = PH_FETCH;
                 next = N_NONE;
             } else if (need_istep) {

@@ -119,3 +119,173 @@ __global__ void ess_kernel(const double *__restrict__ qdraws, const int n_proble
 }
 
 }  // namespace bsyn
+
+namespace bsyn {
+
+// ---------------------------------------------------------------------------------------------------
+// Rank-normalised split-chain bulk ESS / R-hat and tail ESS (Vehtari, Gelman, Simpson, Carpenter & Buerkner 2021;
+// what rstan >= 2.21 prints as Bulk_ESS / Tail_ESS and what SURVEY.md §8(d) defines the ESS metric on).
+// One CTA per problem: the pooled draws of generated scalar q are sorted in shared memory (bitonic, value + position),
+// replaced by the normal scores of their average ranks, z = Phi^-1((r - 3/8) / (S + 1/4)), and the split-chain
+// estimator of ess_kernel (Geyer's initial positive + monotone sequence) is applied to z.  Tail ESS = the smaller of
+// the split-chain ESS of the indicators I(x <= q05) and I(x <= q95), quantiles from the same sort.
+// qdraws[(k*chains + c)*ld_save + i][NQ]; draws n_skip .. n_skip + ns - 1 of every chain are used, ns = ns_p[k] when
+// ns_p != nullptr (problems sampled for different lengths), else ns_all.  prob_list (may be null) selects problems.
+// out[k][4] = bulk ess, bulk rhat, tail ess, draws used.
+constexpr int BULK_THREADS = 256;
+constexpr int BULK_MAX_DRAWS = 8192;
+
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double t = (l < BULK_THREADS / 32) ? red[l] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+// split-chain ESS (and R-hat) of z[chains][ns] in shared memory, every thread of the CTA returns the same values
+__device__ void split_ess_block(const double *z, const int chains, const int ns, double *red, double *mu_s, double &ess_out,
+                                double &rhat_out)
+{
+    const int n = ns / 2, second = ns - n, m = 2 * chains;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    ess_out = qnan; rhat_out = qnan;
+    if (n < 4 || m > 64) return;
+    double mean_var = 0.0, mm = 0.0;
+    for (int j = 0; j < m; ++j) {
+        const double *x = z + (size_t)(j >> 1) * ns + ((j & 1) ? second : 0);
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += BULK_THREADS) s += x[i];
+        const double mu = block_sum(s, red) / n;
+        double v = 0.0;
+        for (int i = threadIdx.x; i < n; i += BULK_THREADS) { const double d = x[i] - mu; v = fma(d, d, v); }
+        v = block_sum(v, red) / n;
+        __syncthreads();
+        if (threadIdx.x == 0) mu_s[j] = mu;
+        mean_var += v * n / (n - 1.0);
+        mm += mu;
+    }
+    __syncthreads();
+    mean_var /= m; mm /= m;
+    double var_means = 0.0;
+    for (int j = 0; j < m; ++j) { const double d = mu_s[j] - mm; var_means = fma(d, d, var_means); }
+    var_means /= (m - 1.0);
+    const double var_plus = mean_var * (n - 1.0) / n + var_means;
+    if (!(var_plus > 0.0) || !(mean_var > 0.0)) return;
+    rhat_out = sqrt(var_plus / mean_var);
+    auto mean_acov = [&](int t) -> double {
+        double tot = 0.0;
+        for (int j = 0; j < m; ++j) {
+            const double *x = z + (size_t)(j >> 1) * ns + ((j & 1) ? second : 0);
+            const double mu = mu_s[j];
+            for (int i = threadIdx.x; i + t < n; i += BULK_THREADS) tot = fma(x[i] - mu, x[i + t] - mu, tot);
+        }
+        return block_sum(tot, red) / ((double)n * m);
+    };
+    double rho_even = 1.0;
+    double rho_odd = 1.0 - (mean_var - mean_acov(1)) / var_plus;
+    double acc = 0.0, prev_sum = 0.0, pend_sum = rho_even + rho_odd, pend_even = rho_even;
+    int npair = 1, s = 1;
+    while (s < n - 4 && (rho_even + rho_odd) > 0.0) {
+        double ps = pend_sum;
+        if (npair >= 2 && ps > prev_sum) ps = prev_sum;
+        acc += ps; prev_sum = ps;
+        rho_even = 1.0 - (mean_var - mean_acov(s + 1)) / var_plus;
+        rho_odd = 1.0 - (mean_var - mean_acov(s + 2)) / var_plus;
+        if (rho_even + rho_odd >= 0.0) { pend_sum = rho_even + rho_odd; pend_even = rho_even; }
+        else { pend_sum = 0.0; pend_even = 0.0; }
+        ++npair;
+        s += 2;
+    }
+    const double tau = -1.0 + 2.0 * (acc + pend_even) + (rho_even > 0.0 ? rho_even : 0.0);
+    const double ntot = (double)n * m;
+    double ess = ntot / tau;
+    const double cap = ntot * log10(ntot);
+    if (!(ess < cap)) ess = cap;
+    ess_out = ess;
+}
+
+__global__ void __launch_bounds__(BULK_THREADS) bulk_ess_kernel(const double *__restrict__ qdraws, const int n_list,
+                                                                 const int *__restrict__ prob_list, const int chains,
+                                                                 const int ld_save, const int n_skip, const int ns_all,
+                                                                 const int *__restrict__ ns_p, const int q,
+                                                                 double *__restrict__ out)
+{
+    extern __shared__ double bsm[];
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const int k = prob_list ? prob_list[li] : li;
+        const int ns = ns_p ? ns_p[k] : ns_all;
+        const int S = chains * ns;
+        int S2 = 1;
+        while (S2 < S) S2 <<= 1;
+        // layout: key[S2] | z[S] | idx[S2] (ints) | red[8] | mu[64]
+        double *key = bsm, *z = bsm + S2;
+        int *idx = reinterpret_cast<int *>(z + S + (S & 1));
+        double *red = reinterpret_cast<double *>(idx + S2), *mu_s = red + 8;
+        __syncthreads();
+        if (S < 16 || S > BULK_MAX_DRAWS) {
+            if (threadIdx.x == 0) { const double qn = nan(""); out[4 * k] = qn; out[4 * k + 1] = qn; out[4 * k + 2] = qn; out[4 * k + 3] = (double)S; }
+            continue;
+        }
+        const double *base = qdraws + (size_t)k * chains * ld_save * NQ + q;
+        for (int e = threadIdx.x; e < S2; e += BULK_THREADS) {
+            double v = INFINITY;
+            if (e < S) { const int c = e / ns, i = e - c * ns; v = base[((size_t)c * ld_save + n_skip + i) * NQ]; }
+            key[e] = v; idx[e] = e;
+        }
+        __syncthreads();
+        for (int kk = 2; kk <= S2; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int e = threadIdx.x; e < S2; e += BULK_THREADS) {
+                    const int p = e ^ j;
+                    if (p > e) {
+                        const bool up = (e & kk) == 0;
+                        const double a = key[e], b = key[p];
+                        const bool sw = up ? (a > b || (a == b && idx[e] > idx[p])) : (a < b || (a == b && idx[e] < idx[p]));
+                        if (sw) { key[e] = b; key[p] = a; const int t = idx[e]; idx[e] = idx[p]; idx[p] = t; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // tail quantiles (type-7-free: order statistics at floor(0.05 S), floor(0.95 S))
+        const double q05 = key[(int)(0.05 * S)], q95 = key[min(S - 1, (int)(0.95 * S))];
+        // average ranks of ties -> normal scores, scattered back to [chain][draw] order
+        for (int e = threadIdx.x; e < S; e += BULK_THREADS) {
+            const double v = key[e];
+            int lo = e, hi = e;
+            while (lo > 0 && key[lo - 1] == v) --lo;
+            while (hi + 1 < S && key[hi + 1] == v) ++hi;
+            const double r = 0.5 * (lo + hi) + 1.0;
+            z[idx[e]] = normcdfinv((r - 0.375) / (S + 0.25));
+        }
+        __syncthreads();
+        double ess_b, rhat_b, ess_lo, ess_hi, dummy;
+        split_ess_block(z, chains, ns, red, mu_s, ess_b, rhat_b);
+        __syncthreads();
+        for (int e = threadIdx.x; e < S; e += BULK_THREADS) { const int c = e / ns, i = e - c * ns; z[e] = (base[((size_t)c * ld_save + n_skip + i) * NQ] <= q05) ? 1.0 : 0.0; }
+        __syncthreads();
+        split_ess_block(z, chains, ns, red, mu_s, ess_lo, dummy);
+        __syncthreads();
+        for (int e = threadIdx.x; e < S; e += BULK_THREADS) { const int c = e / ns, i = e - c * ns; z[e] = (base[((size_t)c * ld_save + n_skip + i) * NQ] <= q95) ? 1.0 : 0.0; }
+        __syncthreads();
+        split_ess_block(z, chains, ns, red, mu_s, ess_hi, dummy);
+        if (threadIdx.x == 0) {
+            out[4 * k] = ess_b; out[4 * k + 1] = rhat_b;
+            out[4 * k + 2] = (ess_lo == ess_lo && ess_hi == ess_hi) ? fmin(ess_lo, ess_hi) : nan("");
+            out[4 * k + 3] = (double)S;
+        }
+    }
+}
+inline size_t bulk_ess_smem_bytes(int S)
+{
+    int S2 = 1;
+    while (S2 < S) S2 <<= 1;
+    return sizeof(double) * ((size_t)S2 + S + (S & 1) + 8 + 64) + sizeof(int) * (size_t)S2;
+}
+
+}  // namespace bsyn

@@ -67,3 +67,19 @@ def bulk_ess_rhat(x):
     r = rankdata(x.reshape(-1), method="average").reshape(x.shape)
     z = norm.ppf((r - 0.375) / (x.size + 0.25))
     return split_ess_rhat(z)
+
+
+def bulk_ess(x):
+    return bulk_ess_rhat(x)[0]
+
+
+def tail_ess(x):
+    """Tail ESS (Vehtari et al. 2021): min over the split-chain ESS of I(x <= q05) and I(x <= q95); the quantiles are
+    the order statistics the device kernel uses (bsyn_post.cuh: bulk_ess_kernel)."""
+    x = np.asarray(x, dtype=np.float64)
+    s = np.sort(x.reshape(-1))
+    S = s.size
+    q05, q95 = s[int(0.05 * S)], s[min(S - 1, int(0.95 * S))]
+    e1, _ = split_ess_rhat((x <= q05).astype(np.float64))
+    e2, _ = split_ess_rhat((x <= q95).astype(np.float64))
+    return float(min(e1, e2)) if e1 == e1 and e2 == e2 else float("nan")

@@ -1,14 +1,18 @@
 #!/usr/bin/env python3
 """bench.py -- the measurement contract for the gp_grid NUTS hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--combos C]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--combos C] [--workload screen|target]
 
 Metric (BASELINE.json): grad evals/sec (value) and ESS/sec per combo (extra keys) of a synergyscreen batch.
 Workload (config.workload): cfg5 of SURVEY.md §8d -- synthetic 10x10-dose-grid x 3-replicate combinations,
-gp_grid with the package-default Matern 3/2 kernel and priors, 4 chains x 2000 iterations (1000 warmup) of
-adaptive NUTS per combination.  A "step" = one full screen (all warmup + sampling iterations of every chain)
-over C combinations per GPU; weak scaling: every rank gets its own C combinations (combination ids are
-disjoint), no collective in the data path, one all_reduce of the timings/counters at the end.
+gp_grid with the package-default Matern 3/2 kernel and priors, 4 chains of adaptive NUTS per combination with
+rstan's 1000 warm-up iterations + 150 sampling iterations (the budget that takes a combination to north_star's
+ESS of 400: `--iter 1150 --warmup-iter 1000`; `--iter 2000` is rstan's default budget).  A "step" = one full
+screen (all warm-up + sampling iterations of every chain) over C combinations per GPU; weak scaling: every rank
+gets its own C combinations (combination ids are disjoint), no collective in the data path, one all_reduce of the
+timings/counters at the end.  The W warm-up steps run the same screen at 1/5 of the iterations (declared in
+config.warmup_steps): they warm the instruction caches, the allocator and the clocks, not a cache of results.
+Both arms (`--impl ours|reference`) print the SAME config; the reference arm's bounded sample is in cpu_baseline.
 
   value : whole-job gradient evaluations per second, problems resident in HBM, device time (CUDA events on the
           launch stream inside the library), max over ranks.
@@ -17,6 +21,10 @@ disjoint), no collective in the data path, one all_reduce of the timings/counter
   roofline : FP64 issue roofline: achieved = evals/s x FLOP per eval, peak = DFMA microbenchmark
           measured live on the same GPU (bsyn_measure_fp64_peak); HBM figures reported alongside.
   cpu_baseline : the oracle's NUTS ("port": the CPU restatement, NOT rstan) on a bounded sample, all host cores.
+
+`--workload target` (north_star's target run): every combination is sampled until its rank-normalised bulk ESS of
+VUS_syn and VUS_ant reaches 400 -- one warm-up + sampling launch, then extension launches over the combinations
+still below the target (chains resume from their adapted state); reports time_to_ess400_all_s.
 """
 import argparse
 import ctypes as C
@@ -36,9 +44,8 @@ sys.path.insert(0, ROOT)
 # per lp+gradient + 920 for the leapfrog / tree bookkeeping (8 D), FMA counted as 2 FLOP.
 SLOTS_PER_EVAL = 26904 + 920
 FLOP_PER_EVAL = 2.0 * SLOTS_PER_EVAL
-# Algorithmic HBM bytes per evaluation for the resident design: state lives on chip; per saved draw the kernel
-# writes 12 generated scalars + 7 sampler params (152 B) and per combination reads ~5.9 KB of inputs once.
 METRIC = "grad_evals_per_sec"
+ESS_TARGET = 400.0
 
 
 def dist_env():
@@ -87,25 +94,48 @@ def h2d_bytes(sds):
     return tot
 
 
-def cpu_leg(n_combos, chains, iters, warmup, threads, seed=1, first_id=10_000_000):
+def iters(args):
+    it = args.iter
+    wu = args.warmup_iter if args.warmup_iter is not None else args.iter // 2
+    return it, wu
+
+
+def workload_config(args):
+    """The SAME dict in both arms: it names the workload, not how large a sample of it an arm timed."""
+    it, wu = iters(args)
+    cfg = {"workload": "cfg5: synthetic gp_grid screen, 10x10 dose grid x 3 replicates (N=363, D=115), Matern 3/2, "
+                       "default priors, heteroscedastic Normal likelihood, adaptive NUTS (diag_e, adapt_delta 0.9, "
+                       "max_treedepth 10)"
+                       + ("; every combination sampled until min(bulk-ESS(VUS_syn), bulk-ESS(VUS_ant)) >= 400"
+                          if args.workload == "target" else ""),
+           "mode": args.workload,
+           "combos_per_gpu_per_step": args.combos, "chains": args.chains, "iter": it, "warmup_iter": wu,
+           "warmup_steps": "same screen at 1/5 of the iterations",
+           "ess_estimator": "rank-normalised split-chain bulk ESS (Vehtari et al. 2021), min over VUS_syn / VUS_ant",
+           "sharding": "combinations across GPUs, no data-path collective",
+           "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+    return cfg
+
+
+def cpu_leg(n_combos, chains, it, wu, threads, seed=1, first_id=10_000_000):
     """Oracle NUTS (CPU restatement) on a bounded sample; returns dict(value, seconds, n_grad, ess_per_sec)."""
     from oracle.c_oracle import Problem, nuts_screen, lib
     from bayesynergy_b200.dataprep import output_names
-    from bayesynergy_b200.diagnostics import split_ess_rhat
+    from bayesynergy_b200.diagnostics import bulk_ess
     sds = make_experiments(first_id, n_combos)
     probs = [Problem(sd) for sd in sds]
     t = time.time()
-    ng, outs, sp = nuts_screen(probs, n_chains=chains, num_warmup=warmup, num_samples=iters - warmup, seed=seed,
+    ng, outs, sp = nuts_screen(probs, n_chains=chains, num_warmup=wu, num_samples=it - wu, seed=seed,
                                nthreads=threads)
     dt = time.time() - t
     names = output_names(sds[0])
     ess = []
     for k in range(n_combos):
-        e1, _ = split_ess_rhat(outs[k, :, :, names.index("VUS_syn")])
-        e2, _ = split_ess_rhat(outs[k, :, :, names.index("VUS_ant")])
+        e1 = bulk_ess(outs[k, :, :, names.index("VUS_syn")])
+        e2 = bulk_ess(outs[k, :, :, names.index("VUS_ant")])
         ess.append(min(e1, e2))
     return dict(value=ng / dt, seconds=dt, n_grad=int(ng), ess_per_sec_per_combo=float(np.nanmean(ess) / dt),
-                total_ess_per_sec=float(np.nansum(ess) / dt),
+                total_ess_per_sec=float(np.nansum(ess) / dt), ess_ge_400_frac=float(np.mean(np.array(ess) >= ESS_TARGET)),
                 cores=threads if threads > 0 else lib().orc_num_threads())
 
 
@@ -115,34 +145,43 @@ def run_reference(args):
         return
     from oracle.c_oracle import lib
     cores = lib().orc_num_threads()
-    n_combos = max(1, cores // args.chains)
-    it, wu = args.ref_iter, args.ref_iter // 2
-    vals, secs = [], []
+    n_combos = max(1, cores // args.chains)      # one chain per host thread
+    it, wu = iters(args)
+    vals, secs, last = [], [], None
     for s in range(args.warmup + args.steps):
-        r = cpu_leg(n_combos, args.chains, it, wu, cores, seed=1 + s)
-        if s >= args.warmup:
-            vals.append(r["value"]); secs.append(r["seconds"])
-    v = float(np.mean(vals))
-    sample = f"{n_combos} cfg5 combinations x {args.chains} chains x {it} iterations ({wu} warmup) per step"
+        warm = s < args.warmup
+        r = cpu_leg(n_combos, args.chains, max(10, it // 5) if warm else it, max(5, wu // 5) if warm else wu, cores,
+                    seed=1 + s, first_id=10_000_000 + s * n_combos)
+        if not warm:
+            vals.append(r["value"]); secs.append(r["seconds"]); last = r
+    v = float(np.sum([x * y for x, y in zip(vals, secs)]) / np.sum(secs))     # total evals / total seconds
+    sample = (f"{n_combos} cfg5 combinations x {args.chains} chains x {it} iterations ({wu} warm-up) per step = one chain "
+              f"per host thread; {args.steps} steps, {np.sum(secs):.1f} s")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "grad evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n_combos, it, wu),
+        "config": workload_config(args),
         "cpu_baseline": {"value": v, "unit": "grad evals/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "oracle/gp_oracle.c NUTS: the CPU restatement, NOT rstan (R/rstan are not in the image)",
-                         "ess_per_sec_per_combo": r["ess_per_sec_per_combo"], "total_ess_per_sec": r["total_ess_per_sec"]},
+                         "ess_per_sec_per_combo": last["ess_per_sec_per_combo"], "total_ess_per_sec": last["total_ess_per_sec"],
+                         "ess_ge_400_frac": last["ess_ge_400_frac"]},
         "e2e": {"value": v, "unit": "grad evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(args, combos, it, wu):
-    return {"workload": "cfg5: synthetic gp_grid screen, 10x10 dose grid x 3 replicates (N=363, D=115), Matern 3/2, "
-                        "default priors, heteroscedastic Normal likelihood, adaptive NUTS (diag_e, adapt_delta 0.9, "
-                        "max_treedepth 10)",
-            "combos_per_gpu_per_step": combos, "chains": args.chains, "iter": it, "warmup_iter": wu,
-            "sharding": "combinations across GPUs, no data-path collective",
-            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+def measured_traffic(args):
+    """DRAM bytes of ONE sampler launch from the committed ncu capture of this command (profiles/r02_traffic.json,
+    written by tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): used only when
+    the capture is of the same workload (combos, iter, warm-up), otherwise null -- never extrapolated."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:
+        return None, None
+    it, wu = iters(args)
+    if (t.get("combos"), t.get("iter"), t.get("warmup_iter"), t.get("chains")) != (args.combos, it, wu, args.chains):
+        return None, None
+    return float(t["dram_bytes_per_launch"]), t.get("source")
 
 
 def run_ours(args):
@@ -158,9 +197,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     from bayesynergy_b200 import _lib
     L = _lib.load()
-    it = args.iter
-    wu = args.warmup_iter if args.warmup_iter is not None else args.iter // 2
+    it, wu = iters(args)
+    t_setup = time.time()
     sds = make_experiments(rank * args.combos, args.combos)
+    t_setup = time.time() - t_setup
 
     def barrier():
         torch.cuda.synchronize()
@@ -172,19 +212,29 @@ def run_ours(args):
     pk = C.c_double()
     L.bsyn_measure_fp64_peak(dev, C.byref(pk))
     b = _lib.Batch(sds, device=dev)
-    launches0 = L.bsyn_launch_count()
+    target = args.workload == "target"
+
+    def one_step(seed, n_it, n_wu):
+        """One pass of the hot path over the resident batch; returns (grad evals, device ms, extra info)."""
+        if target:
+            r = b.sample_to_ess(target=ESS_TARGET, chains=args.chains, warmup=n_wu, block=n_it - n_wu, seed=seed,
+                                max_rounds=args.max_rounds)
+            return r["n_grad"], r["kernel_ms"], r
+        ng, ms = b.sample_device(chains=args.chains, iter=n_it, warmup=n_wu, seed=seed)
+        return ng, ms, None
+
     # ---- device-resident leg -------------------------------------------------------------------
     for s in range(args.warmup):
-        b.sample_device(chains=args.chains, iter=it, warmup=wu, seed=100 + s)
+        one_step(100 + s, max(10, it // 5), max(5, wu // 5))
         flush.fill_(s & 255)
     clocks = ClockSampler(dev)
     clocks.start()
     barrier()
     launches1 = L.bsyn_launch_count()
-    tot_ms, tot_grad = 0.0, 0
+    tot_ms, tot_grad, info = 0.0, 0, None
     t0 = time.time()
     for s in range(args.steps):
-        ng, ms = b.sample_device(chains=args.chains, iter=it, warmup=wu, seed=1000 + s)
+        ng, ms, info = one_step(1000 + s, it, wu)
         tot_ms += ms
         tot_grad += ng
         flush.fill_(s & 255)
@@ -192,18 +242,23 @@ def run_ours(args):
     wall = time.time() - t0
     clocks.stop_flag = True
     launches = L.bsyn_launch_count() - launches1
-    ess_syn, _ = b.ess("VUS_syn")
-    ess_ant, rhat = b.ess("VUS_ant")
-    ess = np.fmin(ess_syn, ess_ant)
-    step_s = tot_ms / args.steps * 1e-3
+    if target:
+        ess, rounds = info["ess"], info["rounds"]
+    else:
+        ess = np.fmin(b.bulk_ess("VUS_syn")[0], b.bulk_ess("VUS_ant")[0])
+        rounds = 1
     # ---- end-to-end leg: host buffers in, summaries out, through the public call --------------------
     b.close()
     e2e_t, e2e_grad = [], []
-    for s in range(1):
+    for s in range(args.e2e_reps):
         barrier()
         t = time.time()
         bb = _lib.Batch(sds, device=dev)
-        res = bb.sample(chains=args.chains, iter=it, warmup=wu, seed=2000 + s, want_qdraws=False, want_sampler_params=False)
+        if target:
+            res = bb.sample_to_ess(target=ESS_TARGET, chains=args.chains, warmup=wu, block=it - wu, seed=2000 + s,
+                                   max_rounds=args.max_rounds, want_summary=True)
+        else:
+            res = bb.sample(chains=args.chains, iter=it, warmup=wu, seed=2000 + s, want_qdraws=False, want_sampler_params=False)
         bb.close()
         torch.cuda.synchronize()
         e2e_t.append(time.time() - t)
@@ -212,7 +267,7 @@ def run_ours(args):
     # ---- reduce over ranks -------------------------------------------------------------------------
     stats = torch.tensor([tot_ms, float(tot_grad), wall, float(np.nansum(ess)), float(np.sum(e2e_grad)),
                           float(np.sum(e2e_t)), float(np.isnan(ess).sum()), float(launches),
-                          float((ess >= 400).sum())], dtype=torch.float64, device="cuda")
+                          float((ess >= ESS_TARGET).sum()), float(rounds)], dtype=torch.float64, device="cuda")
     mx = stats.clone()
     sm = stats.clone()
     if world > 1:
@@ -232,21 +287,24 @@ def run_ours(args):
             pass
         achieved_tflops = value / world * FLOP_PER_EVAL / 1e12
         peak_tflops = 2.0 * pk.value / 1e12
+        traffic, traffic_src = measured_traffic(args)
         out = {
             "metric": METRIC, "value": value, "unit": "grad evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * step_time, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, args.combos, it, wu),
+            "config": workload_config(args),
             "ess_per_sec_per_combo": float(sm[3] / n_combo_total / step_time),
             "total_ess_per_sec": float(sm[3] / step_time),
             "ess_min_syn_ant_mean": float(sm[3] / n_combo_total), "ess_nan_combos": int(sm[6]),
             # time until every combination of the step has ESS >= 400 -- the step itself when all do
             "ess_ge_400_frac": float(sm[8] / n_combo_total),
             "time_to_ess400_all_s": float(step_time) if int(sm[8]) == n_combo_total else None,
+            "sampler_launch_rounds_last_step": int(mx[9]),
             "grad_evals_per_step": sm[1] / args.steps,
             "wall_s_timed_region": float(mx[2]),
+            "setup_s_rank0": {"synthetic data + prepare (host, before any timed region)": t_setup},
             "e2e": {"value": e2e_value, "unit": "grad evals/s", "h2d_bytes_per_step": h2d_bytes(sds),
-                    "d2h_bytes_per_step": d2h, "seconds_per_step": float(mx[5] / len(e2e_t))},
+                    "d2h_bytes_per_step": d2h, "seconds_per_step": float(mx[5] / len(e2e_t)), "reps": len(e2e_t)},
             "gpu_launches": int(mx[7]),
             "clocks": clocks.summary(),
             # the bound of this path is FP64 issue throughput (neither HBM nor tensor cores)
@@ -256,20 +314,16 @@ def run_ours(args):
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          "flop_per_eval": FLOP_PER_EVAL, "per_gpu": True,
                          "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "note": "state is on-chip; HBM is not the bound"},
-                         # DRAM bytes of one sampler launch: 13.3 B per gradient evaluation (dram__bytes_read.sum +
-                         # dram__bytes_write.sum of the ncu --set full capture in profiles/r01_nuts_v6_summary.txt)
-                         # x the evaluations of one launch; the algorithmic figure is ~0 (state is resident)
-                         "traffic": 13.3 * sm[1] / args.steps / world,
-                         "traffic_unit": "bytes per launch (extrapolated from a 444-combination ncu capture)"},
+                         "traffic": traffic, "traffic_source": traffic_src},
         }
         if world == 1 and not args.no_cpu:
             from oracle.c_oracle import lib
             cores = lib().orc_num_threads()
-            nc = max(1, cores // args.chains)
-            r = cpu_leg(nc, args.chains, args.ref_iter, args.ref_iter // 2, cores)
+            nc = max(1, 2 * cores // args.chains)
+            r = cpu_leg(nc, args.chains, it, wu, cores)
             out["cpu_baseline"] = {"value": r["value"], "unit": "grad evals/s", "cores": cores, "kind": "port",
-                                   "sample": f"{nc} cfg5 combinations x {args.chains} chains x {args.ref_iter} iterations "
-                                             f"({args.ref_iter // 2} warmup), {r['seconds']:.1f} s",
+                                   "sample": f"{nc} cfg5 combinations x {args.chains} chains x {it} iterations "
+                                             f"({wu} warm-up), {r['seconds']:.1f} s",
                                    "note": "oracle/gp_oracle.c NUTS: CPU restatement (not rstan)",
                                    "ess_per_sec_per_combo": r["ess_per_sec_per_combo"],
                                    "total_ess_per_sec": r["total_ess_per_sec"]}
@@ -281,18 +335,20 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--combos", type=int, default=int(os.environ.get("BENCH_COMBOS", "1776")),
-                    help="combinations per GPU per step (the full cfg5 screen is 12500 per GPU on 8 GPUs; 1776 = 4 chains "
-                         "per resident warp slot keeps a step at ~30 s so that W + K steps finish within minutes)")
+    ap.add_argument("--workload", default="screen", choices=["screen", "target"])
+    ap.add_argument("--combos", type=int, default=int(os.environ.get("BENCH_COMBOS", "1332")),
+                    help="combinations per GPU per step (the full cfg5 screen is 12500 per GPU on 8 GPUs; 1332 = 3 chains "
+                         "per resident warp slot (148 SMs x 12 warps) keeps the launch tail amortised and a step near 12 s, "
+                         "so that --steps 20 --warmup 5 ends within ~5 minutes)")
     ap.add_argument("--chains", type=int, default=4)
-    ap.add_argument("--iter", type=int, default=2000)
-    ap.add_argument("--warmup-iter", type=int, default=None,
-                    help="warm-up iterations per chain (default iter / 2 as in rstan); e.g. --iter 1150 --warmup-iter 1000 "
-                         "samples just long enough for ESS >= 400 per combination")
-    ap.add_argument("--ref-iter", type=int, default=600, help="iterations per chain in the bounded CPU sample")
+    ap.add_argument("--iter", type=int, default=1150)
+    ap.add_argument("--warmup-iter", type=int, default=1000,
+                    help="warm-up iterations per chain (rstan: 1000); --iter 2000 --warmup-iter 1000 is rstan's default budget")
+    ap.add_argument("--max-rounds", type=int, default=8, help="--workload target: cap on the extension launches")
+    ap.add_argument("--e2e-reps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -191,6 +191,13 @@ int bsyn_sample_device(bsyn_batch *b, const bsyn_sampler_args *args, int64_t *to
  * qdraws of the last sampling call.  ess[n_problems], rhat[n_problems] (may be NULL).  Host pointers. */
 int bsyn_ess(bsyn_batch *b, int32_t q, double *ess, double *rhat);
 
+/* Rank-normalised split-chain bulk ESS and R-hat, and tail ESS (Vehtari et al. 2021: rstan's Bulk_ESS / Tail_ESS; the
+ * estimator SURVEY.md 8(d) defines "ESS per combination" on) of generated scalar `q` for every problem: per problem the
+ * pooled draws of the last sampling call are sorted on the device, replaced by normal scores of their average ranks,
+ * and scored with the estimator of bsyn_ess; tail = min over the 5 % / 95 % quantile indicators.  Up to 8192 pooled
+ * draws per problem.  ess_bulk[n_problems]; rhat, ess_tail may be NULL.  Host pointers. */
+int bsyn_bulk_ess(bsyn_batch *b, int32_t q, double *ess_bulk, double *rhat, double *ess_tail);
+
 /* ---- data preparation in native code: R/bayesynergy.R:129-154 (the step before the path; no GPU involved).
  * y: [n x nrep_in] column-major (replicate r of row i at y[i + r n]), NaN = missing.  x: [n x 2] row-major
  * concentrations (0 = monotherapy).  Outputs (caller-allocated): x1_out[>= n], x2_out[>= n] log10 dose levels,

@@ -1,6 +1,8 @@
 """The reference arm of bench.py runs on host cores only, so its JSON contract can be checked without a GPU."""
 import json
 import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import subprocess
 import sys
 
@@ -9,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--ref-iter", "40"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--warmup", "0", "--iter", "40", "--warmup-iter", "20"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -20,6 +22,11 @@ def test_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms print the SAME config (the reference arm's bounded sample is described in cpu_baseline.sample)
+    import argparse
+    import bench
+    ns = argparse.Namespace(workload="screen", combos=1332, chains=4, iter=40, warmup_iter=20)
+    assert d["config"] == bench.workload_config(ns)
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -6,7 +6,7 @@ import pytest
 
 from bayesynergy_b200 import _lib
 from bayesynergy_b200.dataprep import prepare, output_names
-from bayesynergy_b200.diagnostics import split_ess_rhat, mcse_mean
+from bayesynergy_b200.diagnostics import split_ess_rhat, mcse_mean, bulk_ess_rhat, tail_ess
 from oracle.c_oracle import Problem, nuts_screen
 
 pytestmark = pytest.mark.gpu
@@ -48,6 +48,12 @@ def test_nuts_matches_oracle_mathews(built, datasets):
             ess_h, rhat_h = split_ess_rhat(q[:, :, qi])
             assert abs(ess_d[0] - ess_h) < 1e-6 * ess_h and abs(rhat_d[0] - rhat_h) < 1e-9
             assert rhat_h < 1.05
+            # rank-normalised bulk ESS / R-hat and tail ESS (the estimator of SURVEY 8(d)): device sort vs scipy ranks
+            eb_d, rb_d, et_d = b.bulk_ess(qi)
+            eb_h, rb_h = bulk_ess_rhat(q[:, :, qi])
+            assert abs(eb_d[0] - eb_h) < 1e-6 * eb_h and abs(rb_d[0] - rb_h) < 1e-9, (eb_d[0], eb_h)
+            et_h = tail_ess(q[:, :, qi])
+            assert abs(et_d[0] - et_h) < 1e-6 * et_h, (et_d[0], et_h)
         b.close()
 
 
@@ -184,3 +190,38 @@ def test_oneil_shaped_screen(built, datasets):
     ng, outs, spo = nuts_screen([Problem(sd)], n_chains=4, num_warmup=500, num_samples=500, seed=12)
     _compare(res["qdraws"][0], outs[0], output_names(sd), "oneil_failed:0")
     b.close()
+
+
+def test_cfg3_shape_dense_robust_pcprior_matches_oracle(built):
+    """cfg3 of BASELINE.json on its real shape: O'Neil-shaped 11 x 11 grids (D = 136, 32 observed cells), robust
+    likelihood + PC prior, which makes bayesynergy() select dense_e + stepsize_jitter 0.5 (R/bayesynergy.R:112-115).
+    Device sampler vs the oracle's hmc_nuts_dense_e_adapt restatement on 6 combinations x 4 chains: VUS means within 3
+    MCSE, adapted step size / tree depth distributions agree."""
+    from bayesynergy_b200.dataprep import synthetic_oneil_experiment
+    ncomb, it, wu = 6, 1000, 500
+    sds = [prepare(*synthetic_oneil_experiment(k), robust=True, pcprior=True) for k in range(ncomb)]
+    b = _lib.Batch(sds)
+    res = b.sample(chains=4, iter=it, warmup=wu, seed=51, metric=1, stepsize_jitter=0.5)
+    b.close()
+    assert (res["chain_stats"][:, :, 6] == 0).all()
+    ng, outs, spo = nuts_screen([Problem(sd) for sd in sds], n_chains=4, num_warmup=wu, num_samples=it - wu, seed=53,
+                                metric=1, stepsize_jitter=0.5)
+    names = output_names(sds[0])
+    zs = []
+    for k in range(ncomb):
+        for qn in ("VUS_syn", "VUS_ant", "rVUS_f", "rVUS_p0"):
+            a = res["qdraws"][k][:, :, Q.index(qn)]
+            c = outs[k][:, :, names.index(qn)]
+            se = np.hypot(mcse_mean(a), mcse_mean(c))
+            zs.append((abs(a.mean() - c.mean()) - 1e-6) / se)
+    zs = np.array(zs)
+    # 24 comparisons: every one within 4 MCSE, at most one beyond 3 (P(|z| > 3) = 0.27 % each under agreement)
+    assert zs.max() <= 4.0 and (zs > 3.0).sum() <= 1, zs
+    sp = res["sampler_params"]
+    eps_g, eps_o = np.log(sp[..., 1].mean(axis=2)).ravel(), np.log(spo[..., 1].mean(axis=2)).ravel()
+    dep_g, dep_o = sp[..., 2].mean(axis=2).ravel(), spo[..., 2].mean(axis=2).ravel()
+    se_eps = np.hypot(eps_g.std(ddof=1), eps_o.std(ddof=1)) / np.sqrt(len(eps_g))
+    se_dep = np.hypot(dep_g.std(ddof=1), dep_o.std(ddof=1)) / np.sqrt(len(dep_g))
+    assert abs(eps_g.mean() - eps_o.mean()) < 4 * se_eps + 0.05, (eps_g.mean(), eps_o.mean(), se_eps)
+    assert abs(dep_g.mean() - dep_o.mean()) < 4 * se_dep + 0.15, (dep_g.mean(), dep_o.mean(), se_dep)
+    assert abs(sp[..., 0].mean() - spo[..., 0].mean()) < 0.04
