@@ -19,6 +19,14 @@
 
 using namespace bsyn;
 
+// defaults of the specialised sampler variants (measured: profiles/r02_*)
+#ifndef BSYN_FAST_DEFAULT_NW
+#define BSYN_FAST_DEFAULT_NW 12
+#endif
+#ifndef BSYN_FAST_DEFAULT_TICK
+#define BSYN_FAST_DEFAULT_TICK 1
+#endif
+
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};   // batches on different host threads share it
 
@@ -61,6 +69,7 @@ struct bsyn_batch {
     int *d_ipool = nullptr;
     int *d_tri = nullptr;
     int maxD = 0, maxOut = 0, maxN = 0, max_d_smem = 0, max_i_smem = 0;
+    const VariantOps *fast = nullptr;   // compile-time specialised kernels when the options and every grid match one
     cudaStream_t stream = nullptr;
     int num_sms = 0;
     // buffers of the last sampling call (device)
@@ -68,7 +77,9 @@ struct bsyn_batch {
     double *d_arena = nullptr, *d_dense_L = nullptr, *d_dense_m2 = nullptr, *d_dense_mf = nullptr;
     size_t dense_L_elems = 0, dense_m2_elems = 0, dense_mf_elems = 0;
     size_t qdraws_elems = 0, sp_elems = 0, arena_elems = 0, summary_elems = 0, cs_elems = 0;
-    int last_chains = 0, last_nsave = 0, last_nskip = 0;
+    int last_chains = 0, last_nsave = 0, last_nskip = 0;   // last_nsave: draw slots per chain (the row stride of qdraws)
+    double *d_resume = nullptr; size_t resume_elems = 0;
+    int *d_list = nullptr, *d_nsp = nullptr;
     unsigned long long *d_gradctr = nullptr;
     int *d_workctr = nullptr;
 };
@@ -144,10 +155,17 @@ static const VariantOps *variant(int cpl);
 
 // shared memory layouts.  per_warp_problem: every warp has its own problem block (logp / write_array
 // kernels); otherwise one block per CTA (sampler).
-static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t *bytes, int warps = WPC)
+// the kernels a call uses: the specialised variant when the batch matches one (and the caller can take it), else the
+// runtime-flags variant of the batch's cells-per-lane class
+static const VariantOps *ops_for(const bsyn_batch *b, bool allow_fast = true)
+{
+    return (allow_fast && b->fast) ? b->fast : variant(b->cpl);
+}
+
+static SmemLayout make_layout(const bsyn_batch *b, const VariantOps *ops, bool per_warp_problem, size_t *bytes, int warps = WPC)
 {
     SmemLayout sl;
-    const int tr = variant(b->cpl)->tr;
+    const int tr = ops->tr;
     auto even = [](int v) { return (v + 1) & ~1; };   // LDS.128 / STS.128 need 16-byte aligned double offsets
     sl.tri_off = 0;
     sl.pd_off = even((tr + 1) / 2 + 1);
@@ -156,7 +174,7 @@ static SmemLayout make_layout(const bsyn_batch *b, bool per_warp_problem, size_t
     const int nblk = per_warp_problem ? warps : 1;
     sl.pi_off = sl.pd_off + nblk * sl.pd_stride;
     sl.ws_off = even(sl.pi_off + nblk * sl.pi_stride);
-    sl.park_off = even(sl.ws_off + warps * variant(b->cpl)->ws_doubles);
+    sl.park_off = even(sl.ws_off + warps * ops->ws_doubles);
     *bytes = sizeof(double) * (size_t)(sl.park_off + warps * PARK_DOUBLES);
     return sl;
 }
@@ -199,6 +217,16 @@ extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const 
         if (cpl > 8) { return fail(BSYN_ERR_UNSUPPORTED, "problem " + std::to_string(k) + ": dose grid larger than 16 x 15 is not supported by the compiled kernel variants"); }
     }
     b->cpl = cpl;
+    {   // compile-time specialised kernels (bsyn_f10.cu / bsyn_h10.cu): package-default options on 10 x 10 grids
+        bool all10 = true;
+        for (int k = 0; k < n; ++k) all10 = all10 && problems[k].n1 == 10 && problems[k].n2 == 10;
+        const bool def_lik = F.het == 1 && F.robust == 0 && F.est_la == 1;
+        const char *nf = getenv("BSYN_NO_FAST");
+        if (all10 && def_lik && !(nf && atoi(nf))) {
+            if (F.model == 0 && F.kernel == 2 && F.nu_matern == 2 && F.pcprior == 0 && F.est_alpha == 0) b->fast = bsyn_variant_gp10();
+            if (F.model == 1) b->fast = bsyn_variant_h0_10();
+        }
+    }
     std::vector<double> dpool;
     std::vector<int> ipool;
     b->descs.resize(n);
@@ -307,7 +335,7 @@ extern "C" void bsyn_batch_destroy(bsyn_batch *b)
     cudaSetDevice(b->device);
     cudaFree(b->d_descs); cudaFree(b->d_dpool); cudaFree(b->d_ipool); cudaFree(b->d_tri);
     cudaFree(b->d_qdraws); cudaFree(b->d_sp); cudaFree(b->d_summary); cudaFree(b->d_chain_stats); cudaFree(b->d_arena); cudaFree(b->d_dense_L); cudaFree(b->d_dense_m2); cudaFree(b->d_dense_mf);
-    cudaFree(b->d_gradctr); cudaFree(b->d_workctr);
+    cudaFree(b->d_gradctr); cudaFree(b->d_workctr); cudaFree(b->d_resume); cudaFree(b->d_list); cudaFree(b->d_nsp);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -379,10 +407,11 @@ static int launch_logp(bsyn_batch *b, int B, const int *d_idx, const double *d_u
                        double *d_grad, int *d_status, double *d_dbg, int dbg_stride, cudaStream_t st)
 {
     size_t bytes;
-    SmemLayout sl = make_layout(b, true, &bytes);
+    const VariantOps *ops = ops_for(b);
+    SmemLayout sl = make_layout(b, ops, true, &bytes);
     int grid = std::min((B + WPC - 1) / WPC, b->num_sms * 8);
     if (grid < 1) grid = 1;
-    CK(variant(b->cpl)->logp(d_dbg != nullptr, grid, bytes, st, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B,
+    CK(ops->logp(d_dbg != nullptr, grid, bytes, st, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B,
                              d_idx, d_u, ldu, jac, d_lp, d_grad, d_status, d_dbg, dbg_stride));
     ++g_launches;
     return BSYN_OK;
@@ -443,7 +472,7 @@ extern "C" int bsyn_logp_grad_debug(bsyn_batch *b, int32_t B, const int32_t *pro
 extern "C" int bsyn_debug_layout(const bsyn_batch *b, int32_t *nm, int32_t *nn, int32_t *gm)
 {
     if (!b) return BSYN_ERR_ARG;
-    int NM = variant(b->cpl)->nm;
+    int NM = ops_for(b)->nm;
     *nm = NM; *nn = NM * NM; *gm = 32 * b->cpl;
     return BSYN_OK;
 }
@@ -464,7 +493,7 @@ extern "C" int bsyn_write_array(bsyn_batch *b, int32_t B, const int32_t *prob_id
     CK(cudaMemcpyAsync(d_idx, prob_idx, sizeof(int) * B, cudaMemcpyHostToDevice, b->stream));
     CK(cudaMemcpyAsync(d_u, u, sizeof(double) * (size_t)B * ldu, cudaMemcpyHostToDevice, b->stream));
     size_t bytes;
-    SmemLayout sl = make_layout(b, true, &bytes);
+    SmemLayout sl = make_layout(b, variant(b->cpl), true, &bytes);
     int grid = std::max(1, std::min((B + WPC - 1) / WPC, b->num_sms * 8));
     CK(variant(b->cpl)->write_array(grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sl, B, d_idx,
                                     d_u, ldu, d_out, ldo, seed, d_st));
@@ -534,7 +563,15 @@ static int check_sampler_args(const bsyn_sampler_args *a)
     return BSYN_OK;
 }
 
-static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks &ds, int64_t *total_grad, float *elapsed_ms)
+// how a launch of the sampler sits inside a multi-launch run (bsyn_sample_to_ess); the default is one stand-alone launch
+struct RunPlan {
+    const int *d_list = nullptr; int n_list = 0;   // problems of this launch (device list), null = all
+    int isave0 = 0, ld_save = 0;                   // first draw slot, slots per chain (0: = the draws of this launch)
+    bool resume_in = false, resume_out = false, summary = true;
+};
+
+static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks &ds, int64_t *total_grad, float *elapsed_ms,
+                       const RunPlan &plan = RunPlan())
 {
     if (int rc0 = check_sampler_args(a)) return rc0;
     CK(cudaSetDevice(b->device));
@@ -543,34 +580,49 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     sp.iter = a->iter; sp.warmup = a->warmup; sp.thin = a->thin; sp.max_depth = a->max_treedepth; sp.save_warmup = a->save_warmup;
     const int ns_samp = (a->iter - a->warmup + a->thin - 1) / a->thin, ns_warm = a->save_warmup ? (a->warmup + a->thin - 1) / a->thin : 0;
     sp.n_save = ns_samp + ns_warm;
+    sp.ld_save = plan.ld_save ? plan.ld_save : sp.n_save;
+    sp.isave0 = plan.isave0; sp.prob_list = plan.d_list; sp.n_list = plan.n_list;
+    sp.resume_in = plan.resume_in; sp.resume_out = plan.resume_out;
+    if (sp.isave0 + sp.n_save > sp.ld_save) return fail(BSYN_ERR_ARG, "bsyn_sample: draws of this launch do not fit behind isave0");
+    if ((plan.resume_in || plan.resume_out) && a->metric != 0) return fail(BSYN_ERR_UNSUPPORTED, "resuming chains needs metric = diag_e");
     sp.init_r = a->init_r; sp.delta = a->adapt_delta; sp.stepsize0 = a->stepsize; sp.jitter = a->stepsize_jitter;
     sp.gamma = a->adapt_gamma; sp.kappa = a->adapt_kappa; sp.t0 = a->adapt_t0;
     sp.init_buffer = a->adapt_init_buffer; sp.term_buffer = a->adapt_term_buffer; sp.window = a->adapt_window;
     sp.seed = a->seed; sp.jacobian = 1; sp.metric = a->metric;
-    const size_t nrows = (size_t)b->n * a->chains * sp.n_save;
+    const size_t nrows = (size_t)b->n * a->chains * sp.ld_save;
+    const bool first = plan.isave0 == 0 && !plan.resume_in;    // later launches of a run keep the earlier draws
     int rc;
     if ((rc = ensure(&b->d_qdraws, &b->qdraws_elems, nrows * BSYN_NQ))) return rc;
     if ((rc = ensure(&b->d_sp, &b->sp_elems, nrows * BSYN_NSP))) return rc;
     if ((rc = ensure(&b->d_chain_stats, &b->cs_elems, (size_t)b->n * a->chains * 8))) return rc;
     if ((rc = ensure(&b->d_summary, &b->summary_elems, (size_t)b->n * BSYN_NQ * 2))) return rc;
-    b->last_chains = a->chains; b->last_nsave = sp.n_save; b->last_nskip = ns_warm;
+    b->last_chains = a->chains; b->last_nsave = sp.ld_save; b->last_nskip = ns_warm;
     sp.qdraws = b->d_qdraws; sp.sp = b->d_sp; sp.chain_stats = b->d_chain_stats;
     sp.draws = ds.draws; sp.ld_draws = ds.ld_draws; sp.udraws = ds.udraws; sp.ld_u = ds.ld_u;
     sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im;
-    // warps per CTA: the largest compiled variant (12, 6, 4, 1) whose shared memory fits on an SM
+    // warps per CTA: the largest compiled variant (12, 6, 4, 1) whose shared memory fits on an SM.  A batch that
+    // matches a compile-time specialisation (diag_e only) uses it: 12 or 16 warps per SM, with or without the tick barrier
+    // (BSYN_NUTS_NW / BSYN_NUTS_TICK override the defaults for A/B measurements).
     size_t bytes = 0;
     int nw = 0, per_sm = 0;
+    const VariantOps *ops = ops_for(b, a->metric == 0);
     const int want = getenv("BSYN_NUTS_NW") ? atoi(getenv("BSYN_NUTS_NW")) : 0;
-    for (int cand : {12, 6, 4, 1}) {
+    const bool fast = ops != variant(b->cpl);
+    int tick = 1;
+    if (fast) tick = getenv("BSYN_NUTS_TICK") ? atoi(getenv("BSYN_NUTS_TICK")) : BSYN_FAST_DEFAULT_TICK;
+    for (int cand : {16, 12, 6, 4, 1}) {
         if (want && cand != want) continue;
+        if (fast && cand != 12 && cand != 16) continue;
+        if (fast && !want && cand != BSYN_FAST_DEFAULT_NW) continue;
+        if (!fast && cand == 16) continue;
         if (a->metric == 1 && cand != 12 && cand != 4) continue;
-        sp.sl = make_layout(b, true, &bytes, cand);
+        sp.sl = make_layout(b, ops, true, &bytes, cand);
         if (bytes > 227 * 1024) continue;
-        if (variant(b->cpl)->nuts_occupancy(cand, a->metric, bytes, &per_sm) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (ops->nuts_occupancy(cand, a->metric, tick, bytes, &per_sm) != cudaSuccess) { cudaGetLastError(); continue; }
         if (per_sm >= 1) { nw = cand; break; }
     }
     if (!nw) return fail(BSYN_ERR_UNSUPPORTED, "sampler kernel does not fit on an SM");
-    const int n_items = b->n * a->chains;
+    const int n_items = (plan.d_list ? plan.n_list : b->n) * a->chains;
     const int grid = std::max(1, std::min((n_items + nw - 1) / nw, per_sm * b->num_sms));
     const int VS = (b->cpl + 1) * 32;
     sp.arena_stride = (long long)arena_vectors(a->max_treedepth) * VS * (a->metric == 1 ? 2 : 1);
@@ -584,21 +636,30 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
         sp.dense_L = b->d_dense_L; sp.dense_m2 = b->d_dense_m2; sp.dense_minv = reinterpret_cast<float *>(b->d_dense_mf);
     }
     sp.arena = b->d_arena;
+    if (plan.resume_in || plan.resume_out) {
+        sp.resume_stride = 2LL * VS + 32;
+        if (plan.resume_in && b->resume_elems < (size_t)b->n * a->chains * sp.resume_stride) return fail(BSYN_ERR_ARG, "no chain state to resume from");
+        if ((rc = ensure(&b->d_resume, &b->resume_elems, (size_t)b->n * a->chains * sp.resume_stride))) return rc;
+        sp.resume = b->d_resume;
+    }
     sp.grad_counter = b->d_gradctr; sp.work_counter = b->d_workctr;
     CK(cudaMemsetAsync(b->d_gradctr, 0, sizeof(unsigned long long), b->stream));
     CK(cudaMemsetAsync(b->d_workctr, 0, sizeof(int), b->stream));
-    CK(cudaMemsetAsync(b->d_qdraws, 0, sizeof(double) * nrows * BSYN_NQ, b->stream));
-    CK(cudaMemsetAsync(b->d_sp, 0, sizeof(double) * nrows * BSYN_NSP, b->stream));
-    CK(cudaMemsetAsync(b->d_chain_stats, 0, sizeof(double) * (size_t)b->n * a->chains * 8, b->stream));
+    if (first) {
+        CK(cudaMemsetAsync(b->d_qdraws, 0, sizeof(double) * nrows * BSYN_NQ, b->stream));
+        CK(cudaMemsetAsync(b->d_sp, 0, sizeof(double) * nrows * BSYN_NSP, b->stream));
+        CK(cudaMemsetAsync(b->d_chain_stats, 0, sizeof(double) * (size_t)b->n * a->chains * 8, b->stream));
+    }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, b->stream));
-    CK(variant(b->cpl)->nuts(nw, grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sp));
+    CK(ops->nuts(nw, tick, grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sp));
     ++g_launches;
     // per-problem posterior summaries (mean, sd over all chains and saved sampling draws)
-    {
+    if (plan.summary) {
         const int g2 = std::max(1, std::min((b->n + WPC - 1) / WPC, b->num_sms * 8));
-        summary_kernel<<<g2, 32 * WPC, 0, b->stream>>>(b->d_qdraws, b->n, a->chains, sp.n_save, ns_warm, b->d_summary);
+        summary_kernel<<<g2, 32 * WPC, 0, b->stream>>>(b->d_qdraws, b->n, a->chains, sp.ld_save, ns_warm, sp.n_save - ns_warm, nullptr,
+                                                       b->d_summary);
         ++g_launches;
         CK(cudaGetLastError());
     }
@@ -719,7 +780,7 @@ extern "C" int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *a, const bsyn_advi
     vp.adapt_engaged = a->adapt_engaged; vp.adapt_iter = a->adapt_iter; vp.output_samples = a->output_samples;
     vp.cb_size = cb_size; vp.eta = a->eta; vp.tol_rel_obj = a->tol_rel_obj; vp.init_r = a->init_r; vp.seed = a->seed;
     size_t bytes = 0;
-    vp.sl = make_layout(b, true, &bytes, ADVI_NW);
+    vp.sl = make_layout(b, variant(b->cpl), true, &bytes, ADVI_NW);
     int per_sm = 0;
     if (bytes > 227 * 1024 || variant(b->cpl)->advi_occupancy(bytes, &per_sm) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
@@ -771,7 +832,7 @@ extern "C" int bsyn_advi(bsyn_batch *b, const bsyn_advi_args *a, const bsyn_advi
     }
     if (e == cudaSuccess && ns > 0) {
         const int g2 = std::max(1, std::min((b->n + WPC - 1) / WPC, b->num_sms * 8));
-        summary_kernel<<<g2, 32 * WPC, 0, b->stream>>>(b->d_qdraws, b->n, 1, a->output_samples, 0, b->d_summary);
+        summary_kernel<<<g2, 32 * WPC, 0, b->stream>>>(b->d_qdraws, b->n, 1, a->output_samples, 0, a->output_samples, nullptr, b->d_summary);
         ++g_launches;
         e = cudaGetLastError();
     }

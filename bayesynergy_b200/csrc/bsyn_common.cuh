@@ -45,10 +45,50 @@ struct ProbDesc {
     int n_i_smem;            // ints copied to shared memory (cstart only, and only if robust)
 };
 
-template <int CPL> struct Cfg {
-    static constexpr int NM = (CPL <= 2) ? 8 : (CPL == 4) ? 12 : 16;   // max dose levels per axis (multiple of 4)
+// ---- compile-time specialisation of the model options -------------------------------------
+// The kernels are templates over a SPEC type.  SpecRT reads every option from the runtime Flags (the fallback that
+// covers all 5 kernels x 4 likelihoods x both models in one instruction stream); SpecCT<...> fixes them at compile
+// time, so the instruction stream of a launch carries exactly one kernel function, one likelihood, one model -- and,
+// with NF > 0, a fixed NF x NF dose grid with exact loop bounds and buffer strides.  OptV<SP> is the view the model
+// code queries: `O.het()` folds to a constant under SpecCT and reads F.het under SpecRT.
+struct SpecRT {
+    static constexpr bool fixed = false;
+    static constexpr int NF = 0;
+};
+template <int MODEL, int KERNEL, int NU, int HET, int ROBUST, int ESTLA, int PCP, int NF_> struct SpecCT {
+    static constexpr bool fixed = true;
+    static constexpr int model = MODEL, kernel = KERNEL, nu_matern = NU, het = HET, robust = ROBUST, est_la = ESTLA,
+                         pcprior = PCP, est_alpha = (KERNEL == 3) ? 1 : 0;
+    static constexpr int NF = NF_;   // 0: grid sizes are runtime values
+    static constexpr unsigned active_mask =
+        (ESTLA ? ((1u << SL_LA1) | (1u << SL_LA2)) : 0u) | (1u << SL_M1) | (1u << SL_M2) | (1u << SL_TH1) | (1u << SL_TH2) |
+        (1u << SL_SL1) | (1u << SL_SL2) |
+        (MODEL == 0 ? ((1u << SL_B1) | (1u << SL_B2) | (1u << SL_ELL) | (1u << SL_SIGF) | (KERNEL == 3 ? (1u << SL_ALPHA) : 0u)) : 0u) |
+        (1u << SL_S) | (1u << SL_S21) | (1u << SL_S22);
+};
+template <class SP> struct OptV {
+    const Flags &F;
+    __device__ __forceinline__ explicit OptV(const Flags &f) : F(f) {}
+#define BSYN_OPT(name)                                                                                                     \
+    __device__ __forceinline__ int name() const                                                                            \
+    {                                                                                                                      \
+        if constexpr (SP::fixed) return SP::name; else return F.name;                                                      \
+    }
+    BSYN_OPT(model) BSYN_OPT(kernel) BSYN_OPT(nu_matern) BSYN_OPT(het) BSYN_OPT(robust) BSYN_OPT(est_la) BSYN_OPT(pcprior)
+    BSYN_OPT(est_alpha)
+#undef BSYN_OPT
+    __device__ __forceinline__ unsigned active_mask() const
+    {
+        if constexpr (SP::fixed) return SP::active_mask; else return F.active_mask;
+    }
+};
+
+template <int CPL, class SP = SpecRT> struct Cfg {
+    // max dose levels per axis: a multiple of 4 for the runtime-size kernels (4-row strips), the exact size rounded up
+    // to even (LDS.128 alignment of a column) for a fixed grid
+    static constexpr int NM = SP::NF ? ((SP::NF + 1) & ~1) : ((CPL <= 2) ? 8 : (CPL == 4) ? 12 : 16);
     static constexpr int NN = NM * NM;
-    static constexpr int NS = NM / 4;                   // 4-row strips per column
+    static constexpr int NS = (NM + 3) / 4;             // 4-row strips per column
     static constexpr int GM = 32 * CPL;                 // max GP cells
     static constexpr int PK = NM * (NM - 1);            // max off-diagonal pairs, both axes
     static constexpr int TR = NM * (NM + 1) / 2;        // packed lower-triangular entries of one matrix

@@ -7,7 +7,7 @@
 namespace bsyn {
 
 // stand-alone log_prob / grad_log_prob and write_array kernels: one warp per evaluation point
-template <int CPL, bool DBG>
+template <int CPL, bool DBG, class SP = SpecRT>
 __global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const ProbDesc *__restrict__ descs,
                                                         const double *__restrict__ dpool, const int *__restrict__ ipool,
                                                         const int *__restrict__ tri_tab, const SmemLayout sl, const int B,
@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const Pro
                                                         double *__restrict__ grad, int *__restrict__ status,
                                                         double *__restrict__ dbg, const int dbg_stride)
 {
-    using C = Cfg<CPL>;
+    using C = Cfg<CPL, SP>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s_tri = 2 * sl.tri_off;
     for (int e = threadIdx.x; e < C::TR; e += blockDim.x) SMI(s_tri + e) = tri_tab[e];
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const Pro
             for (int e = lane; e < pd.n_i_smem; e += 32) SMI(s_pi + e) = ipool[pd.off_i + e];
             __syncwarp();
             bind_problem(P, pd, s_pd, s_pi, s_tri);
-            make_cells<CPL>(F, P, cell);
+            make_cells<CPL, SP>(F, P, cell);
             loaded = ip;
         }
         WVec<CPL> q, g;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(32 * WPC) logp_kernel(const Flags F, const Pro
         double lpv;
         GQ gq{};
         gq.on = false; gq.so = 0; gq.fwd = (grad == nullptr) && !DBG;   // value-only calls (log_prob(upar, jacobian, gradient = FALSE)) skip the reverse sweep
-        const bool ok = warp_logp_grad<CPL, DBG>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr, gq);
+        const bool ok = warp_logp_grad<CPL, DBG, SP>(F, P, ws, cell, q, jacobian, lpv, g, DBG ? dbg + (size_t)pt * dbg_stride : nullptr, gq);
         if (!ok) {
             lpv = -INFINITY;
 #pragma unroll
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(32 * WPC) write_array_kernel(const Flags F, co
 }
 
 
-template <int CPL> struct VariantImpl {
+template <int CPL, class SP = SpecRT> struct VariantImpl {
     static cudaError_t logp(bool dbg, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                             const double *dpool, const int *ipool, const int *tri, SmemLayout sl, int B, const int *idx,
                             const double *u, int ldu, int jac, double *lp, double *grad, int *status, double *dbgbuf,
@@ -119,15 +119,15 @@ template <int CPL> struct VariantImpl {
     {
         cudaError_t e;
         if (dbg) {
-            e = cudaFuncSetAttribute(logp_kernel<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            e = cudaFuncSetAttribute(logp_kernel<CPL, true, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
             if (e != cudaSuccess) return e;
-            logp_kernel<CPL, true><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, jac, lp, grad,
-                                                                status, dbgbuf, dbg_stride);
+            logp_kernel<CPL, true, SP><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, jac, lp, grad,
+                                                                    status, dbgbuf, dbg_stride);
         } else {
-            e = cudaFuncSetAttribute(logp_kernel<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            e = cudaFuncSetAttribute(logp_kernel<CPL, false, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
             if (e != cudaSuccess) return e;
-            logp_kernel<CPL, false><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, jac, lp, grad,
-                                                                 status, nullptr, 0);
+            logp_kernel<CPL, false, SP><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, jac, lp, grad,
+                                                                     status, nullptr, 0);
         }
         return cudaGetLastError();
     }
@@ -141,43 +141,61 @@ template <int CPL> struct VariantImpl {
         write_array_kernel<CPL><<<grid, 32 * WPC, bytes, st>>>(F, descs, dpool, ipool, tri, sl, B, idx, u, ldu, out, ldo, seed, status);
         return cudaGetLastError();
     }
-    // sampler instantiations <warps per CTA, register cap, dense metric>: 12 warps per SM as 1 x 12, 2 x 6, 3 x 4 or
-    // 12 x 1 CTAs for diag_e; dense_e (robust models, R/bayesynergy.R:112-115) as 1 x 12
-    template <int NW, int MINB, bool DENSE>
+    // sampler instantiations <warps per CTA, register cap, dense metric, spec, tick barrier>.
+    // SpecRT: 12 warps per SM as 1 x 12, 2 x 6, 3 x 4 or 12 x 1 CTAs for diag_e; dense_e (robust models,
+    // R/bayesynergy.R:112-115) as 1 x 12 or 3 x 4.  Specialised (SpecCT) variants: 12 x 168 registers and 16 x 128
+    // registers, each with and without the tick barrier (`tick` = 0: free-running warps), diag_e only.
+    template <int NW, int MINB, bool DENSE, bool TICK>
     static cudaError_t nuts_launch(int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                                    const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
     {
-        nuts_kernel<CPL, NW, MINB, DENSE><<<grid, 32 * NW, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
+        nuts_kernel<CPL, NW, MINB, DENSE, SP, TICK><<<grid, 32 * NW, bytes, st>>>(F, descs, dpool, ipool, tri, sp);
         return cudaGetLastError();
     }
-    template <int NW, int MINB, bool DENSE> static cudaError_t nuts_occ(size_t bytes, int *per_sm)
+    template <int NW, int MINB, bool DENSE, bool TICK> static cudaError_t nuts_occ(size_t bytes, int *per_sm)
     {
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NW, MINB, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<CPL, NW, MINB, DENSE, SP, TICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NW, MINB, DENSE>, 32 * NW, bytes);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, nuts_kernel<CPL, NW, MINB, DENSE, SP, TICK>, 32 * NW, bytes);
     }
-    static cudaError_t nuts(int nw, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
+    // one table for launch and occupancy query: op = 0 launch, 1 occupancy
+    static cudaError_t nuts_do(int op, int nw, int metric, int tick, int grid, size_t bytes, cudaStream_t st, const Flags *F,
+                               const ProbDesc *descs, const double *dpool, const int *ipool, const int *tri,
+                               const SamplerParams *sp, int *per_sm)
+    {
+#define BSYN_NUTS_CASE(NW_, MINB_, DENSE_, TICK_)                                                                          \
+    return op == 0 ? nuts_launch<NW_, MINB_, DENSE_, TICK_>(grid, bytes, st, *F, descs, dpool, ipool, tri, *sp)            \
+                   : nuts_occ<NW_, MINB_, DENSE_, TICK_>(bytes, per_sm)
+        if constexpr (SP::fixed) {
+            if (metric == 1) return cudaErrorInvalidValue;
+            if (nw == 12 && tick) { BSYN_NUTS_CASE(12, 168, false, true); }
+            if (nw == 12 && !tick) { BSYN_NUTS_CASE(12, 168, false, false); }
+            if (nw == 16 && tick) { BSYN_NUTS_CASE(16, 128, false, true); }
+            if (nw == 16 && !tick) { BSYN_NUTS_CASE(16, 128, false, false); }
+            return cudaErrorInvalidValue;
+        } else {
+            if (!tick) return cudaErrorInvalidValue;
+            if (metric == 1) {
+                if (nw == 12) { BSYN_NUTS_CASE(12, 168, true, true); }
+                if (nw == 4) { BSYN_NUTS_CASE(4, 168, true, true); }
+                return cudaErrorInvalidValue;
+            }
+            if (nw == 12) { BSYN_NUTS_CASE(12, 168, false, true); }
+            if (nw == 6) { BSYN_NUTS_CASE(6, 168, false, true); }
+            if (nw == 4) { BSYN_NUTS_CASE(4, 168, false, true); }
+            if (nw == 1) { BSYN_NUTS_CASE(1, 168, false, true); }
+            return cudaErrorInvalidValue;
+        }
+#undef BSYN_NUTS_CASE
+    }
+    static cudaError_t nuts(int nw, int tick, int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
                             const double *dpool, const int *ipool, const int *tri, const SamplerParams &sp)
     {
-        if (sp.metric == 1) {
-            if (nw == 12) return nuts_launch<12, 168, true>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-            return nuts_launch<4, 168, true>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        }
-        if (nw == 12) return nuts_launch<12, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        if (nw == 6) return nuts_launch<6, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        if (nw == 4) return nuts_launch<4, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
-        return nuts_launch<1, 168, false>(grid, bytes, st, F, descs, dpool, ipool, tri, sp);
+        return nuts_do(0, nw, sp.metric, tick, grid, bytes, st, &F, descs, dpool, ipool, tri, &sp, nullptr);
     }
-    static cudaError_t nuts_occupancy(int nw, int metric, size_t bytes, int *per_sm)
+    static cudaError_t nuts_occupancy(int nw, int metric, int tick, size_t bytes, int *per_sm)
     {
-        if (metric == 1) {
-            if (nw == 12) return nuts_occ<12, 168, true>(bytes, per_sm);
-            return nuts_occ<4, 168, true>(bytes, per_sm);
-        }
-        if (nw == 12) return nuts_occ<12, 168, false>(bytes, per_sm);
-        if (nw == 6) return nuts_occ<6, 168, false>(bytes, per_sm);
-        if (nw == 4) return nuts_occ<4, 168, false>(bytes, per_sm);
-        return nuts_occ<1, 168, false>(bytes, per_sm);
+        return nuts_do(1, nw, metric, tick, 0, bytes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, per_sm);
     }
     // full-rank ADVI: ADVI_NW warps (problems) per CTA, one CTA per SM
     static cudaError_t advi(int grid, size_t bytes, cudaStream_t st, const Flags &F, const ProbDesc *descs,
@@ -194,9 +212,15 @@ template <int CPL> struct VariantImpl {
     }
     static const VariantOps *ops()
     {
-        static const VariantOps o = {CPL, Cfg<CPL>::WS_DOUBLES, Cfg<CPL>::TR, Cfg<CPL>::NM, &logp, &write_array, &nuts, &nuts_occupancy,
-                                     &advi, &advi_occupancy};
-        return &o;
+        if constexpr (SP::fixed) {   // specialised variants carry the lp+gradient kernel and the sampler only
+            static const VariantOps o = {CPL, Cfg<CPL, SP>::WS_DOUBLES, Cfg<CPL, SP>::TR, Cfg<CPL, SP>::NM, &logp, nullptr, &nuts,
+                                         &nuts_occupancy, nullptr, nullptr};
+            return &o;
+        } else {
+            static const VariantOps o = {CPL, Cfg<CPL>::WS_DOUBLES, Cfg<CPL>::TR, Cfg<CPL>::NM, &logp, &write_array, &nuts,
+                                         &nuts_occupancy, &advi, &advi_occupancy};
+            return &o;
+        }
     }
 };
 

@@ -35,42 +35,46 @@ template <int CPL> struct WVec {
 };
 
 // cell descriptor per lane slot t: i | j<<8 | valid<<16 | (valid && z is a parameter)<<17
-template <int CPL> __device__ __forceinline__ void make_cells(const Flags &F, const ProbS &P, int (&cell)[CPL])
+template <int CPL, class SP = SpecRT>
+__device__ __forceinline__ void make_cells(const Flags &F, const ProbS &P, int (&cell)[CPL])
 {
+    const OptV<SP> O(F);
     const int lane = threadIdx.x & 31;
+    const int n2 = SP::NF ? SP::NF : P.n2, G = SP::NF ? SP::NF * SP::NF : P.G;
 #pragma unroll
     for (int t = 0; t < CPL; ++t) {
         int c = lane + 32 * t;
-        int valid = c < P.G;
+        int valid = c < G;
         int cc = valid ? c : 0;
-        int j = cc / P.n2, i = cc - j * P.n2;
-        cell[t] = i | (j << 8) | (valid << 16) | ((valid && F.model == 0) << 17);
+        int j = cc / n2, i = cc - j * n2;
+        cell[t] = i | (j << 8) | (valid << 16) | ((valid && O.model() == 0) << 17);
     }
 }
 
 // kernel value from the stored exponential (and, for the backward pass, its partials)
-__device__ __forceinline__ double kern_arg(const Flags &F, double d, double iell, double alpha)
+template <class OV> __device__ __forceinline__ double kern_arg(const OV &F, double d, double iell, double alpha)
 {
     // argument x of ev = fast_exp(x) (RQ: ev = fast_exp(-alpha*log1p(w)) handled by the caller)
-    if (F.kernel == 1) return -0.5 * d * d * iell * iell;
-    if (F.nu_matern == 1) return -d * iell;
-    if (F.nu_matern == 2) return -BSYN_SQRT3 * d * iell;
+    if (F.kernel() == 1) return -0.5 * d * d * iell * iell;
+    if (F.nu_matern() == 1) return -d * iell;
+    if (F.nu_matern() == 2) return -BSYN_SQRT3 * d * iell;
     return -BSYN_SQRT5 * d * iell;
 }
-__device__ __forceinline__ double kern_val(const Flags &F, double d, double iell, double ev)
+template <class OV> __device__ __forceinline__ double kern_val(const OV &F, double d, double iell, double ev)
 {
-    if (F.kernel == 2 && F.nu_matern == 2) { double r = BSYN_SQRT3 * d * iell; return (1.0 + r) * ev; }
-    if (F.kernel == 2 && F.nu_matern == 3) { double r = BSYN_SQRT5 * d * iell; return (1.0 + r + r * r * (1.0 / 3.0)) * ev; }
+    if (F.kernel() == 2 && F.nu_matern() == 2) { double r = BSYN_SQRT3 * d * iell; return (1.0 + r) * ev; }
+    if (F.kernel() == 2 && F.nu_matern() == 3) { double r = BSYN_SQRT5 * d * iell; return (1.0 + r + r * r * (1.0 / 3.0)) * ev; }
     return ev;
 }
-__device__ __forceinline__ void kern_partials(const Flags &F, double d, double iell, double alpha, double ev,
+template <class OV>
+__device__ __forceinline__ void kern_partials(const OV &F, double d, double iell, double alpha, double ev,
                                               double &kv, double &dk, double &da)
 {
     da = 0.0;
-    if (F.kernel == 1) { kv = ev; dk = ev * d * d * iell * iell * iell; }
-    else if (F.kernel == 2) {
-        if (F.nu_matern == 1) { kv = ev; dk = ev * d * iell * iell; }
-        else if (F.nu_matern == 2) { double r = BSYN_SQRT3 * d * iell; kv = (1.0 + r) * ev; dk = r * r * ev * iell; }
+    if (F.kernel() == 1) { kv = ev; dk = ev * d * d * iell * iell * iell; }
+    else if (F.kernel() == 2) {
+        if (F.nu_matern() == 1) { kv = ev; dk = ev * d * iell * iell; }
+        else if (F.nu_matern() == 2) { double r = BSYN_SQRT3 * d * iell; kv = (1.0 + r) * ev; dk = r * r * ev * iell; }
         else { double r = BSYN_SQRT5 * d * iell; kv = (1.0 + r + r * r * (1.0 / 3.0)) * ev; dk = r * r * (1.0 / 3.0) * (1.0 + r) * ev * iell; }
     } else {
         double w = d * d * iell * iell / (2.0 * alpha);
@@ -85,31 +89,63 @@ __device__ __forceinline__ void kern_partials(const Flags &F, double d, double i
 // Strip product: the one matrix-product shape every Kronecker / adjoint product is reduced to.
 //   Out[r0..r0+3, c] = sum_{m < nm} A[r0..r0+3 + m*NM] * B[c*SBC + m*SBM]        (c < C)
 // A lane owns a 4-row strip of one output column: per m it issues 2 LDS.128 (A) + 1 LDS.64 (B, shared by the
-// strip) for 4 DFMA; rows r0..r0+3 beyond the valid size only ever produce values in padding rows.
-template <int NM, int SBC, int SBM, class Epi>
+// strip) for 4 DFMA; rows r0..r0+3 beyond the valid size only ever produce values in padding rows (NM a multiple of
+// 4), or are dropped by the st4 / st4t stores of the epilogue (fixed grids: NM = the even grid size).
+// CF / KF > 0: compile-time column and term counts (fixed grids): the whole product is one predicated, fully unrolled
+// pass, every load address an immediate offset.
+template <int NM, int SBC, int SBM, int CF, int KF, class Epi>
 __device__ __forceinline__ void strip_product(const double *A, const double *B, const int C, const int nm, Epi &&epi)
 {
-    constexpr int NS = NM / 4;
+    constexpr int NS = (NM + 3) / 4;
     const int lane = threadIdx.x & 31;
-    for (int s = lane; s < NS * C; s += 32) {
+    if constexpr (CF > 0 && KF > 0 && NS * CF <= 32) {
+        const int s = lane < NS * CF ? lane : 0;      // idle lanes recompute item 0 and do not store
         const int c = s / NS, r0 = 4 * (s - c * NS);
         const double2 *Ap = reinterpret_cast<const double2 *>(A + r0);
         const double *Bp = B + c * SBC;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 2
-        for (int m = 0; m < nm; ++m) {
+#pragma unroll
+        for (int m = 0; m < KF; ++m) {
             const double2 x = Ap[m * (NM / 2)], y = Ap[m * (NM / 2) + 1];
             const double bv = Bp[m * SBM];
             a0 = fma(x.x, bv, a0); a1 = fma(x.y, bv, a1); a2 = fma(y.x, bv, a2); a3 = fma(y.y, bv, a3);
         }
-        epi(r0, c, a0, a1, a2, a3);
+        if (lane < NS * CF) epi(r0, c, a0, a1, a2, a3);
+    } else {
+        const int Cn = CF > 0 ? CF : C, nmn = KF > 0 ? KF : nm;
+        for (int s = lane; s < NS * Cn; s += 32) {
+            const int c = s / NS, r0 = 4 * (s - c * NS);
+            const double2 *Ap = reinterpret_cast<const double2 *>(A + r0);
+            const double *Bp = B + c * SBC;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+            for (int m = 0; m < nmn; ++m) {
+                const double2 x = Ap[m * (NM / 2)], y = Ap[m * (NM / 2) + 1];
+                const double bv = Bp[m * SBM];
+                a0 = fma(x.x, bv, a0); a1 = fma(x.y, bv, a1); a2 = fma(y.x, bv, a2); a3 = fma(y.y, bv, a3);
+            }
+            epi(r0, c, a0, a1, a2, a3);
+        }
     }
 }
 __device__ __forceinline__ void st2(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
-
-template <int CPL> __device__ __forceinline__ int zoff(const int cell)   // cell -> offset in a grid-shaped buffer
+// store the 4 strip values at p[0..3] (rows r0..r0+3 of a column of length NM); the upper pair is dropped when the
+// column ends at r0 + 2 (NM not a multiple of 4)
+template <int NM> __device__ __forceinline__ void st4(double *p, int r0, double a0, double a1, double a2, double a3)
 {
-    return (cell & 255) + ((cell >> 8) & 255) * Cfg<CPL>::NM;
+    st2(p, a0, a1);
+    if ((NM & 3) == 0 || r0 + 2 < NM) st2(p + 2, a2, a3);
+}
+// transposed store: element (r0 + e) goes to p[e * NM]
+template <int NM> __device__ __forceinline__ void st4t(double *p, int r0, double a0, double a1, double a2, double a3)
+{
+    p[0] = a0; p[NM] = a1;
+    if ((NM & 3) == 0 || r0 + 2 < NM) { p[2 * NM] = a2; p[3 * NM] = a3; }
+}
+
+template <int CPL, class SP = SpecRT> __device__ __forceinline__ int zoff(const int cell)   // cell -> offset in a grid-shaped buffer
+{
+    return (cell & 255) + ((cell >> 8) & 255) * Cfg<CPL, SP>::NM;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -118,14 +154,14 @@ template <int CPL> __device__ __forceinline__ int zoff(const int cell)   // cell
 // shuffle, column k is published to the column-major factor in shared memory and read back (broadcast LDS.128)
 // for the trailing update.  Leaves in scratch: L1r, L2r (row-major), L2c (column-major), invd (1/diag), exv
 // (exp table), Zs = Z, Ts = T = L2*Z, Tt = T^T, Gs = GP.  Returns GP of this lane's cells in Gv.
-template <int CPL>
-__device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const int ws, const int (&cell)[CPL],
+template <int CPL, class SP>
+__device__ __forceinline__ bool gp_forward(const OptV<SP> &F, const ProbS &P, const int ws, const int (&cell)[CPL],
                                            const double (&z)[CPL], double (&Gv)[CPL])
 {
-    using C = Cfg<CPL>;
-    constexpr int NM = C::NM;
+    using C = Cfg<CPL, SP>;
+    constexpr int NM = C::NM, NF = SP::NF;
     const int lane = threadIdx.x & 31;
-    const int n1 = P.n1, n2 = P.n2;
+    const int n1 = NF ? NF : P.n1, n2 = NF ? NF : P.n2;
     double *const th = smem + ws + C::OFF_TH;
     double *const invd = smem + ws + C::OFF_INVD, *const L1r = smem + ws + C::OFF_L1R, *const L2r = smem + ws + C::OFF_L2R,
                  *const L2c = smem + ws + C::OFF_L2C, *const L1c = smem + ws + C::OFF_WS;
@@ -133,13 +169,13 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const
                  *const Gs = smem + ws + C::OFF_GS, *const exv = smem + ws + C::OFF_EX;
     const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA];
     const double iell = fast_rcp(th[SL_ELL]);
-    const int P1 = P.P1, Pn = P.P1 + P.P2;
+    const int P1 = NF ? NF * (NF - 1) / 2 : P.P1, Pn = NF ? NF * (NF - 1) : P.P1 + P.P2;
 #pragma unroll 3
     for (int e0 = lane; e0 < Pn; e0 += 32) {
         const double d = smem[P.dist + e0];
         const int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
         double ev;
-        if (F.kernel == 3) {
+        if (F.kernel() == 3) {
             const double w = d * d * iell * iell / (2.0 * alpha);
             ev = fast_exp(-alpha * log1p(w));
         } else {
@@ -195,19 +231,19 @@ __device__ __forceinline__ bool gp_forward(const Flags &F, const ProbS &P, const
     // Z -> Zs ; T = L2*Z -> Ts, Tt ; G = T*L1^T -> Gs
 #pragma unroll
     for (int t = 0; t < CPL; ++t)
-        if (cell[t] >> 16) Zs[zoff<CPL>(cell[t])] = z[t];
+        if (cell[t] >> 16) Zs[zoff<CPL, SP>(cell[t])] = z[t];
     __syncwarp();
-    strip_product<NM, NM, 1>(L2c, Zs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-        st2(Ts + r0 + c * NM, a0, a1); st2(Ts + r0 + c * NM + 2, a2, a3);
-        Tt[c + r0 * NM] = a0; Tt[c + (r0 + 1) * NM] = a1; Tt[c + (r0 + 2) * NM] = a2; Tt[c + (r0 + 3) * NM] = a3;
+    strip_product<NM, NM, 1, NF, NF>(L2c, Zs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+        st4<NM>(Ts + r0 + c * NM, r0, a0, a1, a2, a3);
+        st4t<NM>(Tt + c + r0 * NM, r0, a0, a1, a2, a3);
     });
     __syncwarp();
-    strip_product<NM, NM, 1>(Ts, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-        st2(Gs + r0 + c * NM, a0, a1); st2(Gs + r0 + c * NM + 2, a2, a3);
+    strip_product<NM, NM, 1, NF, NF>(Ts, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+        st4<NM>(Gs + r0 + c * NM, r0, a0, a1, a2, a3);
     });
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < CPL; ++t) Gv[t] = (cell[t] >> 16) ? Gs[zoff<CPL>(cell[t])] : 0.0;
+    for (int t = 0; t < CPL; ++t) Gv[t] = (cell[t] >> 16) ? Gs[zoff<CPL, SP>(cell[t])] : 0.0;
     return ok;
 }
 
@@ -232,10 +268,11 @@ template <int NM> __device__ __forceinline__ void solve_LT(const double *Lr, con
 // Constrain this lane's scalar slot (h:1086-1215, Stan Math lub_constrain/lb_constrain semantics) and
 // publish th[16] / ur[16] to the warp scratch.  Returns the constrained value; e = fast_exp(x) where
 // x = -|u| (la slots) or u (lb slots).
-__device__ __forceinline__ double constrain_slot(const Flags &F, double u, const int th, const int ur, double &e)
+template <class OV>
+__device__ __forceinline__ double constrain_slot(const OV &F, double u, const int th, const int ur, double &e)
 {
     const int lane = threadIdx.x & 31;
-    const bool act = (F.active_mask >> lane) & 1u;
+    const bool act = (F.active_mask() >> lane) & 1u;
     const bool is_la = lane < 2, is_lb = (lane >= SL_SL1) && (lane < SL_COUNT);
     e = exp(is_la ? -fabs(u) : u);   // exact exp here: exp(u) = inf must propagate (the reference rejects it)
     double thv;
@@ -259,14 +296,16 @@ __device__ __forceinline__ double constrain_slot(const Flags &F, double u, const
 // The per-observation constants  -log(2pi)/2 - log(s)  are added once per evaluation by the caller, and the
 // heteroscedastic  -n/2 log(f + lambda)  terms of all cells of a lane are folded into ONE logarithm:
 // vprod accumulates prod (f+lambda)^n (n <= 4 replicates; otherwise the log is taken directly).
-__device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int fc, double f, double s, double is2,
+template <class OV>
+__device__ __forceinline__ double lik_cell(const OV &O, const ProbS &P, int fc, double f, double s, double is2,
                                            double &lpl, double &slogbar, double &vprod, bool &ok)
 {
+    const Flags &F = O.F;
     const double n = smem[P.cnt + fc];
     if (n == 0.0) return 0.0;
     double fbar;
     double iv = 0.0;
-    if (F.het) {
+    if (O.het()) {
         const double v = f + F.lambda;
         if (!(v > 0.0)) { ok = false; return 0.0; }
         iv = fast_rcp(v);
@@ -277,10 +316,10 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
             lpl += -0.5 * n * cold_log(v);
         }
     }
-    if (!F.robust) {
+    if (!O.robust()) {
         const double d = smem[P.ybar + fc] - f;
         const double Q = fma(n * d, d, smem[P.ss + fc]);
-        if (F.het) {
+        if (O.het()) {
             lpl += -0.5 * Q * is2 * iv;
             fbar = iv * (-0.5 * n + is2 * (n * d + 0.5 * Q * iv));
             slogbar += -n + Q * is2 * iv;
@@ -291,7 +330,7 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
         }
     } else {
         double isd = fast_rcp(s);
-        if (F.het) isd *= sqrt(iv);
+        if (O.het()) isd *= sqrt(iv);
         fbar = -0.5 * n * iv;
         const int o1 = SMI(P.cstart + fc + 1);
         for (int o = SMI(P.cstart + fc); o < o1; ++o) {
@@ -316,13 +355,15 @@ __device__ __forceinline__ double lik_cell(const Flags &F, const ProbS &P, int f
 
 // Branch-free version for the Normal likelihoods: an unobserved (or masked: live = false) cell has n = 0 and
 // every term vanishes, so the four cells of a lane are straight-line code the scheduler can interleave.
-__device__ __forceinline__ double lik_cell_normal(const Flags &F, const ProbS &P, int fc, double f, double is2, bool live,
+template <class OV>
+__device__ __forceinline__ double lik_cell_normal(const OV &O, const ProbS &P, int fc, double f, double is2, bool live,
                                                   double &lpl, double &slogbar, double &vprod, bool &ok)
 {
+    const Flags &F = O.F;
     const double n = live ? smem[P.cnt + fc] : 0.0;
     const double d = smem[P.ybar + fc] - f;
     const double Q = fma(n * d, d, (n > 0.0) ? smem[P.ss + fc] : 0.0);
-    if (F.het) {
+    if (O.het()) {
         const double v = f + F.lambda;
         ok = ok && ((v > 0.0) || (n == 0.0));
         const double iv = fast_rcp(v);
@@ -379,34 +420,35 @@ __device__ __forceinline__ int gq_D(const GQ &gq) { return SMI(2 * (gq.so + GQS_
 // lp(u) and d lp / d u for one (problem, point), cooperatively on one warp.
 // q / g are in lane layout.  Returns false where the reference would throw (reject): lp/g undefined.
 // dbg (DBG only): global scratch for intermediate dumps (tests).
-template <int CPL, bool DBG>
+template <int CPL, bool DBG, class SP = SpecRT>
 __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, const int ws, const int (&cell)[CPL],
                                                const WVec<CPL> &q, const int jacobian, double &lp_out, WVec<CPL> &g,
                                                double *dbg, const GQ &gq)
 {
-    using C = Cfg<CPL>;
-    constexpr int NM = C::NM;
+    using C = Cfg<CPL, SP>;
+    constexpr int NM = C::NM, NF = SP::NF;
+    const OptV<SP> O(F);
     const int lane = threadIdx.x & 31;
-    const int n1 = P.n1, n2 = P.n2, nm = n1 + n2;
+    const int n1 = NF ? NF : P.n1, n2 = NF ? NF : P.n2, nm = n1 + n2;
     double *const th = smem + ws + C::OFF_TH, *const ur = smem + ws + C::OFF_UR, *const pm = smem + ws + C::OFF_PM;
     double *const invd = smem + ws + C::OFF_INVD, *const L1r = smem + ws + C::OFF_L1R, *const L2r = smem + ws + C::OFF_L2R;
     double *const Zs = smem + ws + C::OFF_ZS, *const Ts = smem + ws + C::OFF_TS, *const Tt = smem + ws + C::OFF_TT,
                  *const Gs = smem + ws + C::OFF_GS, *const Ws = smem + ws + C::OFF_WS;
     double *const Lb1 = smem + ws + C::OFF_LB1, *const Lb2 = smem + ws + C::OFF_LB2, *const exv = smem + ws + C::OFF_EX;
-    const bool gp = (F.model == 0);
+    const bool gp = (O.model() == 0);
     const double J = jacobian ? 1.0 : 0.0;
-    const bool act = (F.active_mask >> lane) & 1u;
+    const bool act = (O.active_mask() >> lane) & 1u;
     const bool is_la = lane < 2, is_lb = (lane >= SL_SL1) && (lane < SL_COUNT);
 
     __syncwarp();   // previous users of the scratch are done
     // ---- 1. scalars: constrain, Jacobian, priors (gp_grid.stan:177-209) -----------------------------
     const double u = q.s;
     double e;
-    const double thv = constrain_slot(F, u, ws + C::OFF_TH, ws + C::OFF_UR, e);
-    const int npre = 2 * F.est_la + 6 + (gp ? 4 + F.est_alpha : 0);
+    const double thv = constrain_slot(O, u, ws + C::OFF_TH, ws + C::OFF_UR, e);
+    const int npre = 2 * O.est_la() + 6 + (gp ? 4 + O.est_alpha() : 0);
     if (gq.on && act) {   // constrained parameters in declaration order
         double *const row = gq_ptr<double>(gq, GQS_ROW);
-        const int pos = (lane < SL_M1) ? lane : (lane <= SL_ALPHA) ? lane - (F.est_la ? 0 : 2) : gq_D(gq) - 3 + (lane - SL_S);
+        const int pos = (lane < SL_M1) ? lane : (lane <= SL_ALPHA) ? lane - (O.est_la() ? 0 : 2) : gq_D(gq) - 3 + (lane - SL_S);
         if (row) row[pos] = thv;
     }
     double lpl = 0.0;   // lane-local part of lp
@@ -442,10 +484,10 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
                 lpl += -BSYN_LOG_2PI_HALF - BSYN_LOG_0_1 - 0.5 * rr * rr + J * u;
                 tb += -(thv - 1.0) * 100.0;
             } else if (lane == SL_ELL) {
-                if (F.pcprior) { lpl += F.log_lam12 - 2.0 * u - F.lam1 * ie + J * u; tb += -2.0 * ie + F.lam1 * ie * ie; }
+                if (O.pcprior()) { lpl += F.log_lam12 - 2.0 * u - F.lam1 * ie + J * u; tb += -2.0 * ie + F.lam1 * ie * ie; }
                 else { lpl += BSYN_IG55_C - 6.0 * u - 5.0 * ie + J * u; tb += -6.0 * ie + 5.0 * ie * ie; }
             } else if (lane == SL_SIGF) {
-                if (F.pcprior) { const double sq = sqrt(thv); lpl += -F.lam2 * sq - 0.5 * u + J * u; tb += -0.5 * F.lam2 * sq * ie - 0.5 * ie; }
+                if (O.pcprior()) { const double sq = sqrt(thv); lpl += -F.lam2 * sq - 0.5 * u + J * u; tb += -0.5 * F.lam2 * sq * ie - 0.5 * ie; }
                 else { lpl += -BSYN_LOG_2PI_HALF - u - 0.5 * (u - 1.0) * (u - 1.0) + J * u; tb += -u * ie; }
             } else if (lane == SL_ALPHA) {
                 lpl += -thv + J * u;
@@ -464,7 +506,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     // ---- 2-4. GP forward -----------------------------------------------------------------------------
     double Gv[CPL];
     bool ok = true;
-    if (gp) ok = gp_forward<CPL>(F, P, ws, cell, q.z, Gv);
+    if (gp) ok = gp_forward<CPL, SP>(O, P, ws, cell, q.z, Gv);
     // ---- 5. monotherapy curves (gp_grid.stan:154-157) ---------------------------------------------
     // gfin: the reference's reverse sweep yields NaN (0 * inf) exactly where 10^(...) overflows or where the Bliss
     // product rounds to 0 or 1 (log(p0 / (1 - p0)) = +-inf); value and lp stay finite there.  The formulas below have
@@ -491,7 +533,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     const double b1 = th[SL_B1], b2 = th[SL_B2];
     double b1bar = 0.0, b2bar = 0.0, slogbar = 0.0, vprod = 1.0;
     // generated quantities (only when gq.on): output offsets, VUS accumulators, f on its (n2+1) x (n1+1) grid
-    const int G = P.G;
+    const int G = NF ? NF * NF : P.G;
     // row layout: [params D][p0 G][p01 n1][p02 n2][Delta G][GP G][ec50 2][CPO N][dss 2][VUS 2 (+3)]
     double *const fg = Lb1;   // (n2+1)(n1+1) <= 2 NN doubles: spans Lb1..Lb2, both free until the adjoint products
     double vus[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -537,9 +579,9 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
             if (row) row[gq_D(gq) + lane + 32 * t] = p0;
         }
         double fbar;
-        if (!F.robust) fbar = lik_cell_normal(F, P, fc, f, is2, live, lpl, slogbar, vprod, ok);
-        else fbar = live ? lik_cell(F, P, fc, f, s, is2, lpl, slogbar, vprod, ok) : 0.0;
-        if (gp && live) Gs[zoff<CPL>(cell[t])] = fbar * dfdG;   // Gbar, in place of G
+        if (!O.robust()) fbar = lik_cell_normal(O, P, fc, f, is2, live, lpl, slogbar, vprod, ok);
+        else fbar = live ? lik_cell(O, P, fc, f, s, is2, lpl, slogbar, vprod, ok) : 0.0;
+        if (gp && live) Gs[zoff<CPL, SP>(cell[t])] = fbar * dfdG;   // Gbar, in place of G
         b1bar = fma(fbar, dfdb1, b1bar);
         b2bar = fma(fbar, dfdb2, b2bar);
         if (live) Ws[lane + 32 * t] = fbar * dfdp0;   // p0bar, packed cell index i + j*n2
@@ -548,14 +590,14 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     double pmbar = 0.0;
     if (lane <= nm) {
         const int fc = lane < n1 ? (lane + 1) * (n2 + 1) : (lane < nm ? lane - n1 + 1 : 0);
-        pmbar = lik_cell(F, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, vprod, ok);
+        pmbar = lik_cell(O, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, vprod, ok);
         if (gq.on) {
             fg[fc] = lane < nm ? pmv : 1.0;
             double *const row = gq_ptr<double>(gq, GQS_ROW);
             if (row && lane < nm) row[gq_D(gq) + G + lane] = pmv;   // p01 then p02 are contiguous
         }
     }
-    if (F.het) lpl += -0.5 * fast_log(vprod);
+    if (O.het()) lpl += -0.5 * fast_log(vprod);
     if (gq.on) {
         __syncwarp();
         double *const row = gq_ptr<double>(gq, GQS_ROW), *const qout = gq_ptr<double>(gq, GQS_QOUT);
@@ -571,7 +613,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         if (row || cpo_acc) {
             for (int n = lane; n < P.N; n += 32) {
                 const double fv = fg[iiglob[n]];
-                const double sd = F.het ? s * sqrt(fv + F.lambda) : s;
+                const double sd = O.het() ? s * sqrt(fv + F.lambda) : s;
                 const double r = (yglob[n] - fv) / sd;
                 const double cpo = cold_exp(BSYN_LOG_2PI_HALF + cold_log(sd) + 0.5 * r * r);
                 if (row) row[o_cpo + n] = cpo;
@@ -619,7 +661,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
                 if (cell[t] >> 16) lpl = fma(-0.5 * q.z[t], q.z[t], lpl);
         }
         double lpf = warp_sum(lpl) - (double)P.N * (BSYN_LOG_2PI_HALF + ur[SL_S]);
-        if (gp) lpf += -(double)P.G * BSYN_LOG_2PI_HALF;
+        if (gp) lpf += -(double)G * BSYN_LOG_2PI_HALF;
         lp_out = lpf;
         ok = ok && (lpf == lpf);
         return __all_sync(FULL, ok);
@@ -629,8 +671,14 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         double v8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (lane < nm) {
             const bool d1 = lane < n1;
-            if (d1) { for (int i = 0; i < n2; ++i) pmbar = fma(Ws[i + lane * n2], pm[n1 + i], pmbar); }
-            else { const int i = lane - n1; for (int j = 0; j < n1; ++j) pmbar = fma(Ws[i + j * n2], pm[j], pmbar); }
+            if (d1) {
+#pragma unroll
+                for (int i = 0; i < n2; ++i) pmbar = fma(Ws[i + lane * n2], pm[n1 + i], pmbar);
+            } else {
+                const int i = lane - n1;
+#pragma unroll
+                for (int j = 0; j < n1; ++j) pmbar = fma(Ws[i + j * n2], pm[j], pmbar);
+            }
             const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
             const double c = pmbar * (1.0 - lam) * BSYN_LN10 * (1.0 - om) * om;   // (1-la) E ln10/(1+E)^2
             const double dla = pmbar * (1.0 - om);            // d/d la = E/(1+E)
@@ -649,44 +697,44 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     if (gp) {
         __syncwarp();   // p0bar (in Ws) has been consumed
         // W = Gbar * L1 -> Ws            W[i,l] = sum_j Gbar[i,j] L1[j,l]
-        strip_product<NM, 1, NM>(Gs, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st2(Ws + r0 + c * NM, a0, a1); st2(Ws + r0 + c * NM + 2, a2, a3);
+        strip_product<NM, 1, NM, NF, NF>(Gs, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st4<NM>(Ws + r0 + c * NM, r0, a0, a1, a2, a3);
         });
         // L1bar = tril(Gbar^T T) -> Lb1 row-major: strip rows l of column j hold L1bar[j,l], kept for l <= j
-        strip_product<NM, NM, 1>(Tt, Gs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st2(Lb1 + r0 + c * NM, (r0 <= c) ? a0 : 0.0, (r0 + 1 <= c) ? a1 : 0.0);
-            st2(Lb1 + r0 + c * NM + 2, (r0 + 2 <= c) ? a2 : 0.0, (r0 + 3 <= c) ? a3 : 0.0);
+        strip_product<NM, NM, 1, NF, NF>(Tt, Gs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st4<NM>(Lb1 + r0 + c * NM, r0, (r0 <= c) ? a0 : 0.0, (r0 + 1 <= c) ? a1 : 0.0, (r0 + 2 <= c) ? a2 : 0.0,
+                    (r0 + 3 <= c) ? a3 : 0.0);
         });
         __syncwarp();
         // L2bar = tril(W Z^T) -> Lb2 col-major [i + k*NM], kept for i >= k
-        strip_product<NM, 1, NM>(Ws, Zs, n2, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st2(Lb2 + r0 + c * NM, (r0 >= c) ? a0 : 0.0, (r0 + 1 >= c) ? a1 : 0.0);
-            st2(Lb2 + r0 + c * NM + 2, (r0 + 2 >= c) ? a2 : 0.0, (r0 + 3 >= c) ? a3 : 0.0);
+        strip_product<NM, 1, NM, NF, NF>(Ws, Zs, n2, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st4<NM>(Lb2 + r0 + c * NM, r0, (r0 >= c) ? a0 : 0.0, (r0 + 1 >= c) ? a1 : 0.0, (r0 + 2 >= c) ? a2 : 0.0,
+                    (r0 + 3 >= c) ? a3 : 0.0);
         });
         if (DBG) {
 #pragma unroll
             for (int t = 0; t < CPL; ++t)
-                if (cell[t] >> 16) dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gs[zoff<CPL>(cell[t])];
+                if (cell[t] >> 16) dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gs[zoff<CPL, SP>(cell[t])];
         }
         __syncwarp();
         // Zbar = L2^T W -> Gs            Zbar[k,l] = sum_i L2[i,k] W[i,l]
-        strip_product<NM, NM, 1>(L2r, Ws, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st2(Gs + r0 + c * NM, a0, a1); st2(Gs + r0 + c * NM + 2, a2, a3);
+        strip_product<NM, NM, 1, NF, NF>(L2r, Ws, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st4<NM>(Gs + r0 + c * NM, r0, a0, a1, a2, a3);
         });
         // Cholesky adjoint (Murray 2016): Xfull = L^-T (Phi + Phi^T) L^-1, Phi = tril(L^T Lbar), diag halved.
         // Stage A: P = L^T Lbar (only its lower triangle is used) -> S1 (over Zs), S2 (over Ts)
-        strip_product<NM, 1, NM>(L1r, Lb1, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st2(Zs + r0 + c * NM, a0, a1); st2(Zs + r0 + c * NM + 2, a2, a3);
+        strip_product<NM, 1, NM, NF, NF>(L1r, Lb1, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st4<NM>(Zs + r0 + c * NM, r0, a0, a1, a2, a3);
         });
-        strip_product<NM, NM, 1>(L2r, Lb2, n2, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st2(Ts + r0 + c * NM, a0, a1); st2(Ts + r0 + c * NM + 2, a2, a3);
+        strip_product<NM, NM, 1, NF, NF>(L2r, Lb2, n2, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st4<NM>(Ts + r0 + c * NM, r0, a0, a1, a2, a3);
         });
         __syncwarp();
         // Zbar is complete: gradient wrt z (+ its N(0,1) prior)
 #pragma unroll
         for (int t = 0; t < CPL; ++t) {
             const bool v = cell[t] >> 16;
-            const double zb = v ? Gs[zoff<CPL>(cell[t])] : 0.0;
+            const double zb = v ? Gs[zoff<CPL, SP>(cell[t])] : 0.0;
             g.z[t] = v ? zb - q.z[t] : 0.0;
             if (v) lpl = fma(-0.5 * q.z[t], q.z[t], lpl);
             if (DBG && v) dbg[2 * C::NN + 3 * C::GM + lane + 32 * t] = zb;
@@ -730,14 +778,14 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         // contraction with d cov / d(ell, sigma_f, alpha): sum over all (a,b) of Sbar_sym * dcov
         //   = sum_{a>b} Xfull[a,b] * dcov[a,b] + 1/2 sum_a Xfull[a,a] * dcov[a,a]
         const double sigf = th[SL_SIGF], alpha = th[SL_ALPHA], iell = fast_rcp(th[SL_ELL]);
-        const int P1 = P.P1, Pn = P.P1 + P.P2;
+        const int P1 = NF ? NF * (NF - 1) / 2 : P.P1, Pn = NF ? NF * (NF - 1) : P.P1 + P.P2;
 #pragma unroll 3
         for (int e0 = lane; e0 < Pn; e0 += 32) {
             const bool m1 = e0 < P1;
             const int ab = SMI(P.pr + e0), a = ab >> 8, b = ab & 255;
             const double X = (m1 ? Lb1 : Lb2)[a * NM + b];
             double kv, dk, da;
-            kern_partials(F, smem[P.dist + e0], iell, alpha, exv[e0], kv, dk, da);
+            kern_partials(O, smem[P.dist + e0], iell, alpha, exv[e0], kv, dk, da);
             const double sc = m1 ? sigf : 1.0;
             ellbar = fma(X * sc, dk, ellbar);
             alphabar = fma(X * sc, da, alphabar);
@@ -757,7 +805,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         if (lane >= SL_B1 && lane <= SL_ALPHA) tb += rsum;
         lp = __shfl_sync(FULL, rsum, 6);
         lp += -(double)P.N * (BSYN_LOG_2PI_HALF + ur[SL_S]);
-        if (gp) lp += -(double)P.G * BSYN_LOG_2PI_HALF;
+        if (gp) lp += -(double)G * BSYN_LOG_2PI_HALF;
         double gs;
         if (is_la) gs = tb * thv * (1.0 - thv) + J * (1.0 - 2.0 * thv);
         else if (is_lb) gs = tb * thv + J;

@@ -46,6 +46,12 @@ struct SamplerParams {
     // (double, column-major lower) and the Welford cross-product accumulator (double)
     int metric;
     float *dense_minv; double *dense_L, *dense_m2; long long dense_stride;
+    // extension launches (bsyn_sample_to_ess): the chains of the listed problems resume from their adapted state and
+    // append their draws behind the ones already saved
+    const int *prob_list; int n_list;      // null / 0: every problem of the batch
+    int isave0, ld_save;                   // first draw slot written by this launch, draw slots per chain in the sinks
+    double *resume; long long resume_stride;   // [n_problems * chains][q (VS), M^-1 diagonal (VS), step size]
+    int resume_in, resume_out;
     // work
     double *arena; long long arena_stride;
     unsigned long long *grad_counter;
@@ -233,15 +239,19 @@ struct TransInfo {
 enum Phase { PH_FETCH = 0, PH_INIT, PH_ISTEP, PH_TREE, PH_GQ, PH_DONE };
 enum Next { N_NONE = 0, N_ENDTRANS, N_ITER, N_TRANS, N_DOUBLE };
 
-template <int CPL, int NW, int MINB, bool DENSE>
+// Template parameters: CPL cells per lane; NW warps per CTA; MINB register cap per thread; DENSE dense_e metric;
+// SP the compile-time model specialisation (SpecRT = every option read from F); TICK = the barrier-aligned tick
+// described above (false: warps free-run -- only sensible when the specialised instruction stream is small).
+template <int CPL, int NW, int MINB, bool DENSE, class SP = SpecRT, bool TICK = true>
 __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const Flags F, const ProbDesc *__restrict__ descs,
                                                          const double *__restrict__ dpool, const int *__restrict__ ipool,
                                                          const int *__restrict__ tri_tab, const SamplerParams sp)
 {
-    using C = Cfg<CPL>;
+    using C = Cfg<CPL, SP>;
+    const OptV<SP> O(F);
     constexpr int VS = (CPL + 1) * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = sp.n_problems * sp.chains;
+    const int n_items = (sp.prob_list ? sp.n_list : sp.n_problems) * sp.chains;
     const int s_tri = 2 * sp.sl.tri_off;
     const int s_pd = pin_uniform(sp.sl.pd_off + warp * sp.sl.pd_stride);
     const int s_pi = pin_uniform(2 * (sp.sl.pi_off + warp * sp.sl.pi_stride));
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     double *const Lc = DENSE ? sp.dense_L + (long long)(blockIdx.x * NW + warp) * sp.dense_stride : nullptr;
     double *const M2 = DENSE ? sp.dense_m2 + (long long)(blockIdx.x * NW + warp) * sp.dense_stride : nullptr;
     double *const pv = smem + ws + C::OFF_ZS;           // DI <= 2 NN doubles: spans Zs..Ts, free outside the evaluation
-    const bool lane_active = (F.active_mask >> lane) & 1u;
+    const bool lane_active = (O.active_mask() >> lane) & 1u;
     const double l08 = -0.22314355131420976;   // log(0.8)
     // warm-up schedule (windowed_adaptation), identical for every chain
     const int nw = sp.warmup;
@@ -317,7 +327,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
 #pragma unroll
             for (int t = 0; t < CPL; ++t) y.z[t] = 0.0;
             y.s = 0.0;
-            const int nz = (F.model == 0) ? P.G : 0;
+            const int nz = (O.model() == 0) ? P.G : 0;
 #pragma unroll 4
             for (int gg = 0; gg < nz; ++gg) {
                 const double xg = pv[gg];
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 y.s = fma((double)col[CPL * 32], xg, y.s);
             }
             for (int sidx = 0; sidx < SL_COUNT; ++sidx) {
-                if (!((F.active_mask >> sidx) & 1u)) continue;
+                if (!((O.active_mask() >> sidx) & 1u)) continue;
                 const double xg = pv[CPL * 32 + sidx];
                 const float *col = Mf + (size_t)(CPL * 32 + sidx) * DI + lane;
 #pragma unroll
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
         if constexpr (DENSE) vstore<CPL>(A + (long long)(slot + SOFF) * VS, psv);
     };
     auto slot_active = [&](int f) -> bool {   // is internal slot f a parameter?
-        return f < CPL * 32 ? (F.model == 0 && f < P.G) : ((f - CPL * 32) < SL_COUNT && ((F.active_mask >> (f - CPL * 32)) & 1u));
+        return f < CPL * 32 ? (O.model() == 0 && f < P.G) : ((f - CPL * 32) < SL_COUNT && ((O.active_mask() >> (f - CPL * 32)) & 1u));
     };
     auto sample_momentum = [&](uint32_t tag, uint32_t iter, uint32_t idx0) {
         // diag_e_metric::sample_p: p_i = N(0,1) / sqrt(minv_i);  dense_e_metric::sample_p: p = L^-T z, M^-1 = L L^T
@@ -415,8 +425,13 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
         step = eps_try;
     };
 
+    if constexpr (!TICK) __syncthreads();   // the tri table is complete (the tick barrier covers it otherwise)
     for (;;) {
-        if (__syncthreads_and(phase == PH_DONE)) break;
+        if constexpr (TICK) {
+            if (__syncthreads_and(phase == PH_DONE)) break;
+        } else {
+            if (phase == PH_DONE) break;
+        }
         // ---- fetch the next chain -----------------------------------------------------------------------
         if (phase == PH_FETCH) {
             int item = 0;
@@ -425,15 +440,16 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             if (item >= n_items) {
                 phase = PH_DONE;
             } else {
-                const int ip = item / sp.chains;
-                cg = item;
+                const int ipl = item / sp.chains;
+                const int ip = sp.prob_list ? sp.prob_list[ipl] : ipl;
+                cg = (long long)ip * sp.chains + (item - ipl * sp.chains);
                 pd = descs[ip];
                 __syncwarp();
                 for (int e = lane; e < pd.n_d_smem; e += 32) smem[s_pd + e] = dpool[pd.off_d + e];
                 for (int e = lane; e < pd.n_i_smem; e += 32) SMI(s_pi + e) = ipool[pd.off_i + e];
                 __syncwarp();
                 bind_problem(P, pd, s_pd, s_pi, s_tri);
-                make_cells<CPL>(F, P, cell);
+                make_cells<CPL, SP>(F, P, cell);
                 rk.k0 = (uint32_t)sp.seed; rk.k1 = (uint32_t)(sp.seed >> 32); rk.chain = (uint32_t)cg;
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) minv.z[t] = ((cell[t] >> 17) & 1) ? 1.0 : 0.0;
@@ -456,9 +472,14 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 yglob = dpool + pd.off_d + pool_y_off(pd);
                 iiglob = ipool + pd.off_i + pool_ii_off(pd);
                 cpo_acc = sp.cpo_acc ? sp.cpo_acc + cg * sp.ld_cpo : nullptr;
-                if (cpo_acc) for (int e = lane; e < pd.N; e += 32) cpo_acc[e] = 0.0;
+                if (cpo_acc && !sp.resume_in) for (int e = lane; e < pd.N; e += 32) cpo_acc[e] = 0.0;
                 init_try = 0;
                 draw_init(0);
+                if (sp.resume_in) {   // continue a finished chain: its last position and adapted (diagonal) metric
+                    const double *R = sp.resume + cg * sp.resume_stride;
+                    vload<CPL>(R, q);
+                    if constexpr (!DENSE) vload<CPL>(R + VS, minv);
+                }
                 phase = PH_INIT;
             }
         }
@@ -487,7 +508,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             gq.on = (phase == PH_GQ);
             gq.so = s_park + PARK_GQ; gq.fwd = false;
             if (gq.on) {
-                const long long rowi = cg * sp.n_save + isave;
+                const long long rowi = cg * sp.ld_save + sp.isave0 + isave;
                 double uz[4];
                 rng_u2(rk, RT_GQ, 0xFFu, it, 0, uz[0], uz[1]);
                 rng_u2(rk, RT_GQ, 0xFFu, it, 1, uz[2], uz[3]);
@@ -525,7 +546,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             if constexpr (!DENSE) vstore<CPL>(A + A_PARK_MINV * VS, minv);
             else vstore<CPL>(A + A_PARK_YV * VS, yv_keep);
             double lp;
-            const bool okv = warp_logp_grad<CPL, false>(F, P, ws, cell, q, sp.jacobian, lp, g, nullptr, gq);
+            const bool okv = warp_logp_grad<CPL, false, SP>(F, P, ws, cell, q, sp.jacobian, lp, g, nullptr, gq);
             vload<CPL>(A + A_PARK_S * VS, S); vload<CPL>(A + A_PARK_PREV * VS, pprev); vload<CPL>(A + A_PARK_P * VS, p);
             if constexpr (!DENSE) vload<CPL>(A + A_PARK_MINV * VS, minv);
             else vload<CPL>(A + A_PARK_YV * VS, yv_keep);
@@ -586,6 +607,10 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             if (__all_sync(FULL, fin)) {
                 eps = sp.stepsize0;
                 need_istep = true;            // base_hmc::init_stepsize runs before the first transition ...
+                if (sp.resume_in && init_try == 0) {   // ... unless the chain resumes with its adapted step size
+                    eps = sp.resume[cg * sp.resume_stride + 2 * VS];
+                    need_istep = false;
+                }
                 istep_tag = 0xFFFFFF00u;
                 mu = 0.0; sbar = 0.0; xbar = 0.0; cnt = 0.0; wn = 0.0;
                 win_size = base_window; win_end = init_buffer + base_window - 1;
@@ -745,7 +770,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             }
         } else if (phase == PH_GQ) {
             // the saved draw's generated quantities have just been written by the evaluation
-            const long long rowi = cg * sp.n_save + isave;
+            const long long rowi = cg * sp.ld_save + sp.isave0 + isave;
             if (sp.qdraws && lane == 0) { double *qo = sp.qdraws + rowi * 12; qo[10] = -V; qo[11] = 0.0; }
             ++isave;
             ++it;
@@ -885,7 +910,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             const int base = warm ? 0 : nw;
             const bool save = (!warm || sp.save_warmup) && ((it - base) % sp.thin == 0) && isave < sp.n_save;
             if (save) {
-                const long long rowi = cg * sp.n_save + isave;
+                const long long rowi = cg * sp.ld_save + sp.isave0 + isave;
                 if (sp.udraws) store_user_vec<CPL>(F, pd, cell, q, sp.udraws + rowi * sp.ld_u);
                 if (sp.sp && lane == 0) {
                     double *o = sp.sp + rowi * 7;
@@ -910,8 +935,20 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
         if (next == N_ITER) {
             if (it >= sp.iter) {   // chain finished
                 if (cs && lane == 0) {
-                    cs[0] = eps; cs[1] = n_div; cs[2] = n_maxd; cs[3] = nleap_tot; cs[4] = nleap_samp;
-                    cs[5] = n_samp_it > 0 ? acc_sum / n_samp_it : 0.0; cs[6] = 0.0; cs[7] = (double)isave;
+                    if (sp.resume_in) {   // an extension launch adds to the statistics of the chain's earlier launches
+                        const double n_old = cs[7], n_new = n_old + (double)isave;
+                        cs[0] = eps; cs[1] += n_div; cs[2] += n_maxd; cs[3] += nleap_tot; cs[4] += nleap_samp;
+                        cs[5] = n_new > 0 ? (cs[5] * n_old + acc_sum) / n_new : 0.0; cs[7] = n_new;
+                    } else {
+                        cs[0] = eps; cs[1] = n_div; cs[2] = n_maxd; cs[3] = nleap_tot; cs[4] = nleap_samp;
+                        cs[5] = n_samp_it > 0 ? acc_sum / n_samp_it : 0.0; cs[6] = 0.0; cs[7] = (double)isave;
+                    }
+                }
+                if (sp.resume_out) {
+                    double *R = sp.resume + cg * sp.resume_stride;
+                    vstore<CPL>(R, q);
+                    if constexpr (!DENSE) vstore<CPL>(R + VS, minv);
+                    if (lane == 0) R[2 * VS] = eps;
                 }
                 if (sp.inv_metric) {
                     if constexpr (DENSE) {   // the sink is a D-vector: the diagonal of the adapted dense M^-1

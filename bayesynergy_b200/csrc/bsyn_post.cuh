@@ -9,28 +9,30 @@ namespace bsyn {
 
 constexpr int NQ = 12;
 
-// one warp per problem; qdraws[(k*chains + c)*n_save + i][NQ]; the first n_skip saved draws of every chain
-// (saved warmup) are skipped.  summary[k][NQ][2] = mean, sd (n-1 denominator over all chains pooled).
+// one warp per problem; qdraws[(k*chains + c)*ld_save + i][NQ]; the first n_skip saved draws of every chain
+// (saved warmup) are skipped, the next ns (= ns_p[k] when ns_p != nullptr, problems sampled for different lengths,
+// else ns_all) are used.  summary[k][NQ][2] = mean, sd (n-1 denominator over all chains pooled).
 __global__ void summary_kernel(const double *__restrict__ qdraws, const int n_problems, const int chains,
-                               const int n_save, const int n_skip, double *__restrict__ summary)
+                               const int ld_save, const int n_skip, const int ns_all, const int *__restrict__ ns_p,
+                               double *__restrict__ summary)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int ns = n_save - n_skip;
-    const long long tot = (long long)chains * ns;
     for (int k = warp; k < n_problems; k += nwarps) {
-        const double *base = qdraws + (size_t)k * chains * n_save * NQ;
+        const int ns = ns_p ? ns_p[k] : ns_all;
+        const long long tot = (long long)chains * ns;
+        const double *base = qdraws + (size_t)k * chains * ld_save * NQ;
         for (int q = 0; q < NQ; ++q) {
             double s = 0.0;
             for (long long r = lane; r < tot; r += 32) {
                 const int c = (int)(r / ns), i = (int)(r - (long long)c * ns) + n_skip;
-                s += base[((size_t)c * n_save + i) * NQ + q];
+                s += base[((size_t)c * ld_save + i) * NQ + q];
             }
             const double mean = warp_sum(s) / (double)tot;
             double v = 0.0;
             for (long long r = lane; r < tot; r += 32) {
                 const int c = (int)(r / ns), i = (int)(r - (long long)c * ns) + n_skip;
-                const double d = base[((size_t)c * n_save + i) * NQ + q] - mean;
+                const double d = base[((size_t)c * ld_save + i) * NQ + q] - mean;
                 v = fma(d, d, v);
             }
             v = warp_sum(v);
