@@ -23,7 +23,7 @@ EXPORTS = [
     "bsyn_batch_create", "bsyn_batch_destroy", "bsyn_last_error", "bsyn_version", "bsyn_num_params",
     "bsyn_num_outputs", "bsyn_max_params", "bsyn_max_outputs", "bsyn_num_problems", "bsyn_logp_grad",
     "bsyn_logp_grad_device", "bsyn_write_array", "bsyn_unconstrain", "bsyn_sampler_defaults", "bsyn_sample",
-    "bsyn_sample_device", "bsyn_ess", "bsyn_bulk_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare", "bsyn_output_name",
+    "bsyn_sample_device", "bsyn_ess", "bsyn_bulk_ess", "bsyn_sample_to_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare", "bsyn_output_name",
 ]
 VI_NAMES = ["status", "eta", "iterations", "elbo", "converged", "n_grad", "n_lp", "_reserved"]
 
@@ -112,6 +112,9 @@ def load():
                                      C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.bsyn_ess.argtypes = [vp, C.c_int32, dp, dp]
     L.bsyn_bulk_ess.argtypes = [vp, C.c_int32, dp, dp, dp]
+    L.bsyn_sample_to_ess.argtypes = [vp, C.POINTER(BsynSamplerArgs), C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                                     C.POINTER(BsynSinks), dp, ip, C.POINTER(C.c_int64), C.POINTER(C.c_float),
+                                     C.POINTER(C.c_int32)]
     i32p = C.POINTER(C.c_int32)
     L.bsyn_prepare.argtypes = [dp, dp, C.c_int32, C.c_int32, dp, i32p, dp, i32p, dp, ip, i32p, i32p, i32p]
     L.bsyn_output_name.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
@@ -360,6 +363,35 @@ class Batch:
         _check(load().bsyn_sample_device(self.h, C.byref(a), C.byref(ng), C.byref(ms), None, None, None),
                "bsyn_sample_device")
         return ng.value, ms.value
+
+    def sample_to_ess(self, target=400.0, q=("VUS_syn", "VUS_ant"), block=150, max_rounds=8, want_summary=False,
+                      want_qdraws=False, **kw):
+        """Sample every experiment until min over `q` of its rank-normalised bulk ESS reaches `target`
+        (bsyn_sample_to_ess): warm-up + `block` draws per chain, then extension launches of `block` draws over the
+        experiments still below the target.  kw: sampler arguments (chains, warmup, seed, adapt_delta ...)."""
+        kw = dict(kw)
+        kw["iter"] = kw.get("warmup", 1000) + block
+        kw.setdefault("warmup", 1000)
+        a = self.sampler_args(**kw)
+        n, ch, ld = self.n, a.chains, block * max_rounds
+        s = BsynSinks()
+        res = {}
+        if want_summary:
+            res["summary"] = np.zeros((n, BSYN_NQ, 2))
+            s.summary = _dp(res["summary"])
+            res["chain_stats"] = np.zeros((n, ch, 8))
+            s.chain_stats = _dp(res["chain_stats"])
+        if want_qdraws:
+            res["qdraws"] = np.zeros((n, ch, ld, BSYN_NQ))
+            s.qdraws = _dp(res["qdraws"])
+        ess = np.empty(n)
+        nd = np.empty(n, dtype=np.int32)
+        ng, ms, rounds = C.c_int64(), C.c_float(), C.c_int32()
+        qi = [Q_NAMES.index(x) if isinstance(x, str) else int(x) for x in q]
+        _check(load().bsyn_sample_to_ess(self.h, C.byref(a), float(target), qi[0], qi[1], max_rounds, C.byref(s), _dp(ess),
+                                         _ip(nd), C.byref(ng), C.byref(ms), C.byref(rounds)), "bsyn_sample_to_ess")
+        res.update(ess=ess, draws_per_chain=nd, n_grad=ng.value, kernel_ms=ms.value, rounds=rounds.value)
+        return res
 
     def bulk_ess(self, q):
         """Rank-normalised bulk ESS, R-hat and tail ESS per experiment, on the device (bsyn_bulk_ess)."""

@@ -23,6 +23,9 @@ using namespace bsyn;
 #ifndef BSYN_FAST_DEFAULT_NW
 #define BSYN_FAST_DEFAULT_NW 12
 #endif
+#ifndef BSYN_DEFAULT_TICK_PERIOD
+#define BSYN_DEFAULT_TICK_PERIOD 2
+#endif
 #ifndef BSYN_FAST_DEFAULT_TICK
 #define BSYN_FAST_DEFAULT_TICK 1
 #endif
@@ -80,6 +83,7 @@ struct bsyn_batch {
     int last_chains = 0, last_nsave = 0, last_nskip = 0;   // last_nsave: draw slots per chain (the row stride of qdraws)
     double *d_resume = nullptr; size_t resume_elems = 0;
     int *d_list = nullptr, *d_nsp = nullptr;
+    bool last_var_ns = false;   // the last run left a different number of draws per problem (d_nsp)
     unsigned long long *d_gradctr = nullptr;
     int *d_workctr = nullptr;
 };
@@ -596,7 +600,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     if ((rc = ensure(&b->d_sp, &b->sp_elems, nrows * BSYN_NSP))) return rc;
     if ((rc = ensure(&b->d_chain_stats, &b->cs_elems, (size_t)b->n * a->chains * 8))) return rc;
     if ((rc = ensure(&b->d_summary, &b->summary_elems, (size_t)b->n * BSYN_NQ * 2))) return rc;
-    b->last_chains = a->chains; b->last_nsave = sp.ld_save; b->last_nskip = ns_warm;
+    b->last_chains = a->chains; b->last_nsave = sp.ld_save; b->last_nskip = ns_warm; b->last_var_ns = false;
     sp.qdraws = b->d_qdraws; sp.sp = b->d_sp; sp.chain_stats = b->d_chain_stats;
     sp.draws = ds.draws; sp.ld_draws = ds.ld_draws; sp.udraws = ds.udraws; sp.ld_u = ds.ld_u;
     sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im;
@@ -610,11 +614,12 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     const bool fast = ops != variant(b->cpl);
     int tick = 1;
     if (fast) tick = getenv("BSYN_NUTS_TICK") ? atoi(getenv("BSYN_NUTS_TICK")) : BSYN_FAST_DEFAULT_TICK;
-    for (int cand : {16, 12, 6, 4, 1}) {
+    sp.tick_period = std::max(1, getenv("BSYN_TICK_PERIOD") ? atoi(getenv("BSYN_TICK_PERIOD")) : BSYN_DEFAULT_TICK_PERIOD);
+    for (int cand : {16, 14, 12, 6, 4, 1}) {
         if (want && cand != want) continue;
-        if (fast && cand != 12 && cand != 16) continue;
+        if (fast && cand != 12 && cand != 14 && cand != 16) continue;
         if (fast && !want && cand != BSYN_FAST_DEFAULT_NW) continue;
-        if (!fast && cand == 16) continue;
+        if (!fast && (cand == 16 || cand == 14)) continue;
         if (a->metric == 1 && cand != 12 && cand != 4) continue;
         sp.sl = make_layout(b, ops, true, &bytes, cand);
         if (bytes > 227 * 1024) continue;
@@ -871,6 +876,7 @@ extern "C" int bsyn_ess(bsyn_batch *b, int32_t q, double *ess, double *rhat)
 {
     if (!b || q < 0 || q >= BSYN_NQ || !ess) return fail(BSYN_ERR_ARG, "bsyn_ess: bad argument");
     if (!b->d_qdraws || b->last_nsave - b->last_nskip < 8) return fail(BSYN_ERR_ARG, "bsyn_ess: no draws from a previous bsyn_sample call");
+    if (b->last_var_ns) return fail(BSYN_ERR_UNSUPPORTED, "bsyn_ess: after bsyn_sample_to_ess use bsyn_bulk_ess (per-problem draw counts)");
     CK(cudaSetDevice(b->device));
     double *d_out = nullptr;
     CK(cudaMalloc(&d_out, sizeof(double) * 2 * b->n));
@@ -901,7 +907,7 @@ extern "C" int bsyn_bulk_ess(bsyn_batch *b, int32_t q, double *ess_bulk, double 
     CK(cudaFuncSetAttribute(bulk_ess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const int grid = std::max(1, std::min(b->n, b->num_sms * 4));
     bulk_ess_kernel<<<grid, BULK_THREADS, bytes, b->stream>>>(b->d_qdraws, b->n, nullptr, b->last_chains, b->last_nsave,
-                                                              b->last_nskip, ns, nullptr, q, d_out);
+                                                              b->last_nskip, ns, b->last_var_ns ? b->d_nsp : nullptr, q, d_out);
     ++g_launches;
     CK(cudaGetLastError());
     std::vector<double> tmp(4 * (size_t)b->n);
@@ -912,5 +918,118 @@ extern "C" int bsyn_bulk_ess(bsyn_batch *b, int32_t q, double *ess_bulk, double 
         if (rhat) rhat[k] = tmp[4 * k + 1];
         if (ess_tail) ess_tail[k] = tmp[4 * k + 2];
     }
+    return BSYN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ESS-target control (north_star: "sampled to an ESS of 400 per combination"): one warm-up + sampling launch over
+// the whole batch, then extension launches over the problems whose rank-normalised bulk ESS (min over the two scalars
+// q1, q2) is still below the target -- their chains resume from the adapted state and append `block` draws.
+static __global__ void select_below_kernel(const double *__restrict__ e1, const double *__restrict__ e2, const int n_list,
+                                           const int *__restrict__ list_in, const double target, const int ns_now,
+                                           double *__restrict__ ess, int *__restrict__ ns_p, int *__restrict__ list_out,
+                                           int *__restrict__ n_out)
+{
+    for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n_list; li += gridDim.x * blockDim.x) {
+        const int k = list_in ? list_in[li] : li;
+        const double a = e1[4 * k], c = e2[4 * k];
+        const double m = (a == a && c == c) ? fmin(a, c) : nan("");
+        ess[k] = m;
+        ns_p[k] = ns_now;
+        if (!(m >= target)) list_out[atomicAdd(n_out, 1)] = k;
+    }
+}
+
+extern "C" int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, double target_ess, int32_t q1, int32_t q2,
+                                  int32_t max_rounds, const bsyn_sample_sinks *sinks, double *ess, int32_t *draws_per_chain,
+                                  int64_t *total_grad_evals, float *elapsed_ms, int32_t *rounds)
+{
+    if (!b || !args) return fail(BSYN_ERR_ARG, "bsyn_sample_to_ess: null argument");
+    if (int rc0 = check_sampler_args(args)) return rc0;
+    const int block = args->iter - args->warmup;
+    if (args->thin != 1 || args->save_warmup || block < 8 || max_rounds < 1 || q1 < 0 || q1 >= BSYN_NQ || q2 < 0 || q2 >= BSYN_NQ ||
+        !(target_ess > 0))
+        return fail(BSYN_ERR_ARG, "bsyn_sample_to_ess: needs thin = 1, save_warmup = 0, iter - warmup >= 8, max_rounds >= 1");
+    if ((long long)block * max_rounds * args->chains > BULK_MAX_DRAWS)
+        return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample_to_ess: chains x (iter - warmup) x max_rounds exceeds 8192 pooled draws");
+    if (sinks && (sinks->draws || sinks->udraws || sinks->cpo_mean || sinks->inv_metric))
+        return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample_to_ess: only the qdraws / sampler_params / summary / chain_stats sinks");
+    CK(cudaSetDevice(b->device));
+    const int n = b->n, ld_save = block * max_rounds;
+    DevBuf<double> d_e1, d_e2, d_ess;
+    DevBuf<int> d_lists, d_cnt;
+    CK(d_e1.alloc(4 * (size_t)n)); CK(d_e2.alloc(4 * (size_t)n)); CK(d_ess.alloc(n));
+    CK(d_lists.alloc(2 * (size_t)n)); CK(d_cnt.alloc(1));
+    if (!b->d_nsp) CK(cudaMalloc(&b->d_nsp, sizeof(int) * n));
+    const size_t ebytes = bulk_ess_smem_bytes(block * max_rounds * args->chains);
+    CK(cudaFuncSetAttribute(bulk_ess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ebytes));
+    DevSinks ds;
+    int64_t tot_grad = 0;
+    float tot_ms = 0.f;
+    int n_active = n, r = 0;
+    const int *list = nullptr;       // device list of the active problems (null = all)
+    for (;; ++r) {
+        bsyn_sampler_args a = *args;
+        RunPlan plan;
+        plan.ld_save = ld_save; plan.isave0 = r * block; plan.resume_out = (r + 1 < max_rounds); plan.summary = false;
+        if (r > 0) {
+            a.warmup = 0; a.iter = block; a.seed = args->seed + 0x9E3779B97F4A7C15ull * (uint64_t)r;
+            plan.resume_in = true; plan.d_list = list; plan.n_list = n_active;
+        }
+        int64_t ng = 0;
+        float ms = 0.f;
+        int rc = run_sampler(b, &a, ds, &ng, &ms, plan);
+        if (rc) return rc;
+        tot_grad += ng;
+        // rank-normalised bulk ESS of q1 and q2 over the (r + 1) * block draws of the active problems
+        const int ns_now = (r + 1) * block;
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, b->stream));
+        const int grid = std::max(1, std::min(n_active, b->num_sms * 4));
+        const size_t eb = bulk_ess_smem_bytes(ns_now * args->chains);
+        bulk_ess_kernel<<<grid, BULK_THREADS, eb, b->stream>>>(b->d_qdraws, n_active, list, args->chains, ld_save, 0, ns_now, nullptr, q1, d_e1);
+        bulk_ess_kernel<<<grid, BULK_THREADS, eb, b->stream>>>(b->d_qdraws, n_active, list, args->chains, ld_save, 0, ns_now, nullptr, q2, d_e2);
+        CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), b->stream));
+        int *list_out = d_lists.p + (size_t)((r & 1) ? n : 0);
+        select_below_kernel<<<std::max(1, std::min((n_active + 255) / 256, 1024)), 256, 0, b->stream>>>(d_e1, d_e2, n_active, list, target_ess, ns_now, d_ess,
+                                                                                                       b->d_nsp, list_out, d_cnt);
+        g_launches += 3;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, b->stream));
+        int n_next = 0;
+        CK(cudaMemcpyAsync(&n_next, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        float ms2 = 0.f;
+        CK(cudaEventElapsedTime(&ms2, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        tot_ms += ms + ms2;
+        if (n_next == 0 || r + 1 >= max_rounds) { ++r; break; }
+        list = list_out; n_active = n_next;
+    }
+    b->last_chains = args->chains; b->last_nsave = ld_save; b->last_nskip = 0; b->last_var_ns = true;
+    {   // summaries over each problem's own number of draws
+        int rc;
+        if ((rc = ensure(&b->d_summary, &b->summary_elems, (size_t)n * BSYN_NQ * 2))) return rc;
+        const int g2 = std::max(1, std::min((n + WPC - 1) / WPC, b->num_sms * 8));
+        summary_kernel<<<g2, 32 * WPC, 0, b->stream>>>(b->d_qdraws, n, args->chains, ld_save, 0, 0, b->d_nsp, b->d_summary);
+        ++g_launches;
+        CK(cudaGetLastError());
+    }
+    std::vector<int> nsp(n);
+    CK(cudaMemcpyAsync(nsp.data(), b->d_nsp, sizeof(int) * n, cudaMemcpyDeviceToHost, b->stream));
+    if (ess) CK(cudaMemcpyAsync(ess, d_ess, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+    if (sinks) {
+        const size_t nrows = (size_t)n * args->chains * ld_save, nch = (size_t)n * args->chains;
+        if (sinks->qdraws) CK(cudaMemcpyAsync(sinks->qdraws, b->d_qdraws, sizeof(double) * nrows * BSYN_NQ, cudaMemcpyDeviceToHost, b->stream));
+        if (sinks->sampler_params) CK(cudaMemcpyAsync(sinks->sampler_params, b->d_sp, sizeof(double) * nrows * BSYN_NSP, cudaMemcpyDeviceToHost, b->stream));
+        if (sinks->summary) CK(cudaMemcpyAsync(sinks->summary, b->d_summary, sizeof(double) * (size_t)n * BSYN_NQ * 2, cudaMemcpyDeviceToHost, b->stream));
+        if (sinks->chain_stats) CK(cudaMemcpyAsync(sinks->chain_stats, b->d_chain_stats, sizeof(double) * nch * 8, cudaMemcpyDeviceToHost, b->stream));
+    }
+    CK(cudaStreamSynchronize(b->stream));
+    if (draws_per_chain) for (int k = 0; k < n; ++k) draws_per_chain[k] = nsp[k];
+    if (total_grad_evals) *total_grad_evals = tot_grad;
+    if (elapsed_ms) *elapsed_ms = tot_ms;
+    if (rounds) *rounds = r;
     return BSYN_OK;
 }

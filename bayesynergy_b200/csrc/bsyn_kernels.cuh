@@ -170,8 +170,8 @@ template <int CPL, class SP = SpecRT> struct VariantImpl {
             if (metric == 1) return cudaErrorInvalidValue;
             if (nw == 12 && tick) { BSYN_NUTS_CASE(12, 168, false, true); }
             if (nw == 12 && !tick) { BSYN_NUTS_CASE(12, 168, false, false); }
+            if (nw == 14 && tick) { BSYN_NUTS_CASE(14, 144, false, true); }
             if (nw == 16 && tick) { BSYN_NUTS_CASE(16, 128, false, true); }
-            if (nw == 16 && !tick) { BSYN_NUTS_CASE(16, 128, false, false); }
             return cudaErrorInvalidValue;
         } else {
             if (!tick) return cudaErrorInvalidValue;

@@ -367,10 +367,16 @@ __device__ __forceinline__ double lik_cell_normal(const OV &O, const ProbS &P, i
         const double v = f + F.lambda;
         ok = ok && ((v > 0.0) || (n == 0.0));
         const double iv = fast_rcp(v);
-        const double v2 = v * v;
-        const bool fold = v >= BSYN_VPROD_MIN;
-        vprod *= (n == 0.0 || !fold) ? 1.0 : (n == 1.0) ? v : (n == 2.0) ? v2 : (n == 3.0) ? v2 * v : (n == 4.0) ? v2 * v2 : 1.0;
-        if ((n > 4.0 || !fold) && n > 0.0) lpl += -0.5 * n * cold_log(v);
+        // v^n for n <= 4 by selects over unconditionally computed powers (the nested conditional products compile to
+        // a chain of branches otherwise)
+        const double v2 = v * v, v3 = v2 * v, v4 = v2 * v2;
+        const bool fold = (v >= BSYN_VPROD_MIN) && (n <= 4.0);
+        double pw = (n == 1.0) ? v : 1.0;
+        pw = (n == 2.0) ? v2 : pw;
+        pw = (n == 3.0) ? v3 : pw;
+        pw = (n == 4.0) ? v4 : pw;
+        vprod *= fold ? pw : 1.0;
+        if (!fold && n > 0.0) lpl += -0.5 * n * cold_log(v);
         const double qi = Q * is2 * iv;
         lpl = fma(-0.5, qi, lpl);
         slogbar += qi - n;

@@ -52,6 +52,7 @@ struct SamplerParams {
     int isave0, ld_save;                   // first draw slot written by this launch, draw slots per chain in the sinks
     double *resume; long long resume_stride;   // [n_problems * chains][q (VS), M^-1 diagonal (VS), step size]
     int resume_in, resume_out;
+    int tick_period;   // the CTA barrier of the tick state machine is taken every tick_period-th tick (>= 1)
     // work
     double *arena; long long arena_stride;
     unsigned long long *grad_counter;
@@ -426,9 +427,11 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
     };
 
     if constexpr (!TICK) __syncthreads();   // the tri table is complete (the tick barrier covers it otherwise)
+    int tickn = 0;
     for (;;) {
         if constexpr (TICK) {
-            if (__syncthreads_and(phase == PH_DONE)) break;
+            if (tickn == 0 && __syncthreads_and(phase == PH_DONE)) break;
+            if (++tickn >= sp.tick_period) tickn = 0;
         } else {
             if (phase == PH_DONE) break;
         }

@@ -225,3 +225,44 @@ def test_cfg3_shape_dense_robust_pcprior_matches_oracle(built):
     assert abs(eps_g.mean() - eps_o.mean()) < 4 * se_eps + 0.05, (eps_g.mean(), eps_o.mean(), se_eps)
     assert abs(dep_g.mean() - dep_o.mean()) < 4 * se_dep + 0.15, (dep_g.mean(), dep_o.mean(), se_dep)
     assert abs(sp[..., 0].mean() - spo[..., 0].mean()) < 0.04
+
+
+def test_sample_to_ess_extends_only_what_is_below_target(built):
+    """ESS-target control (north_star: every combination sampled to an ESS of 400): warm-up + 150 draws, then extension
+    launches over the combinations still below the target, chains resuming from their adapted state."""
+    from bayesynergy_b200.dataprep import synthetic_experiment
+    from bayesynergy_b200.diagnostics import bulk_ess
+    n = 48
+    sds = [prepare(*synthetic_experiment(1000 + k)) for k in range(n)]
+    b = _lib.Batch(sds)
+    block, rounds_max = 150, 6
+    r = b.sample_to_ess(target=400.0, block=block, max_rounds=rounds_max, chains=4, warmup=300, seed=5, want_summary=True,
+                        want_qdraws=True)
+    nd, ess = r["draws_per_chain"], r["ess"]
+    assert r["rounds"] >= 1 and (nd % block == 0).all() and nd.min() >= block and nd.max() <= block * rounds_max
+    assert nd.max() == block * r["rounds"]
+    assert ((ess >= 400.0) | (nd == block * rounds_max)).all()
+    assert (nd > block).any() and (nd == block).any()          # some combinations were extended, some were not
+    q = r["qdraws"]
+    for k in range(n):
+        # the device ESS that stopped the combination = the host estimator on exactly its draws
+        e = min(bulk_ess(q[k, :, :nd[k], Q.index("VUS_syn")]), bulk_ess(q[k, :, :nd[k], Q.index("VUS_ant")]))
+        assert abs(e - ess[k]) < 1e-6 * max(1.0, e), (k, e, ess[k])
+        assert (q[k, :, nd[k]:, :] == 0).all()                  # nothing written behind the last block
+        m = q[k, :, :nd[k], Q.index("rVUS_f")].mean()
+        assert abs(r["summary"][k, Q.index("rVUS_f"), 0] - m) < 1e-9 * max(1.0, abs(m))
+    # rank-normalised ESS after the run uses each combination's own draw count
+    eb, _, _ = b.bulk_ess("VUS_syn")
+    k = int(np.argmax(nd))
+    assert abs(eb[k] - bulk_ess(q[k, :, :nd[k], Q.index("VUS_syn")])) < 1e-6 * eb[k]
+    # an extended run samples the same posterior as one long run: VUS means within 4 MCSE on the extended combinations
+    long = b.sample(chains=4, iter=300 + block * rounds_max, warmup=300, seed=77)
+    b.close()
+    zs = []
+    for k in np.where(nd > block)[0][:12]:
+        for qn in ("VUS_syn", "VUS_ant", "rVUS_f"):
+            a = q[k, :, :nd[k], Q.index(qn)]
+            c = long["qdraws"][k][:, :, Q.index(qn)]
+            zs.append(abs(a.mean() - c.mean()) / (np.hypot(mcse_mean(a), mcse_mean(c)) + 1e-9))
+    zs = np.array(zs)
+    assert zs.max() < 4.5 and (zs > 3.0).sum() <= 2, zs
