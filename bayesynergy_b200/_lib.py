@@ -21,7 +21,7 @@ SP_NAMES = ["accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "diver
 
 EXPORTS = [
     "bsyn_batch_create", "bsyn_batch_destroy", "bsyn_last_error", "bsyn_version", "bsyn_num_params",
-    "bsyn_num_outputs", "bsyn_max_params", "bsyn_max_outputs", "bsyn_num_problems", "bsyn_logp_grad",
+    "bsyn_num_outputs", "bsyn_num_param_blocks", "bsyn_param_block", "bsyn_max_params", "bsyn_max_outputs", "bsyn_num_problems", "bsyn_logp_grad",
     "bsyn_logp_grad_device", "bsyn_write_array", "bsyn_unconstrain", "bsyn_sampler_defaults", "bsyn_sample",
     "bsyn_sample_device", "bsyn_ess", "bsyn_bulk_ess", "bsyn_sample_to_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare", "bsyn_output_name",
 ]
@@ -55,7 +55,8 @@ class BsynSinks(C.Structure):
                 ("udraws", C.POINTER(C.c_double)), ("ld_udraws", C.c_int64),
                 ("qdraws", C.POINTER(C.c_double)), ("sampler_params", C.POINTER(C.c_double)),
                 ("summary", C.POINTER(C.c_double)), ("cpo_mean", C.POINTER(C.c_double)), ("ld_cpo", C.c_int64),
-                ("chain_stats", C.POINTER(C.c_double)), ("inv_metric", C.POINTER(C.c_double))]
+                ("chain_stats", C.POINTER(C.c_double)), ("inv_metric", C.POINTER(C.c_double)),
+                ("init_u", C.POINTER(C.c_double)), ("elapsed_ms", C.POINTER(C.c_float))]
 
 
 class BsynAdviArgs(C.Structure):
@@ -118,6 +119,8 @@ def load():
     i32p = C.POINTER(C.c_int32)
     L.bsyn_prepare.argtypes = [dp, dp, C.c_int32, C.c_int32, dp, i32p, dp, i32p, dp, ip, i32p, i32p, i32p]
     L.bsyn_output_name.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+    L.bsyn_num_param_blocks.argtypes = [vp]
+    L.bsyn_param_block.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, i32p, i32p, i32p]
     L.bsyn_advi_defaults.argtypes = [C.POINTER(BsynAdviArgs)]
     L.bsyn_advi_defaults.restype = None
     L.bsyn_advi.argtypes = [vp, C.POINTER(BsynAdviArgs), C.POINTER(BsynAdviSinks), C.POINTER(C.c_int64),
@@ -288,8 +291,18 @@ class Batch:
             setattr(a, k, v)
         return a
 
+    def param_blocks(self, k=0):
+        """[(name, dims, flat_offset)]: what param_names() / param_dims() of the rstan module report."""
+        L = load()
+        out, buf = [], C.create_string_buffer(48)
+        nd, off, dims = C.c_int32(), C.c_int32(), (C.c_int32 * 2)()
+        for i in range(L.bsyn_num_param_blocks(self.h)):
+            _check(L.bsyn_param_block(self.h, k, i, buf, 48, C.byref(nd), dims, C.byref(off)), "bsyn_param_block")
+            out.append((buf.value.decode(), [dims[j] for j in range(nd.value)], off.value))
+        return out
+
     def sample(self, want_draws=False, want_udraws=False, want_qdraws=True, want_sampler_params=True,
-               want_cpo=False, want_inv_metric=False, **kw):
+               want_cpo=False, want_inv_metric=False, want_inits=False, **kw):
         """Run adaptive NUTS for every experiment x chain in one launch.  Returns a dict of numpy arrays."""
         a = self.sampler_args(**kw)
         ns = (a.iter - a.warmup + a.thin - 1) // a.thin + ((a.warmup + a.thin - 1) // a.thin if a.save_warmup else 0)
@@ -319,10 +332,16 @@ class Batch:
         if want_inv_metric:
             res["inv_metric"] = np.zeros((n, ch, self.max_params))
             s.inv_metric = _dp(res["inv_metric"])
+        if want_inits:
+            res["init_u"] = np.zeros((n, ch, self.max_params))
+            s.init_u = _dp(res["init_u"])
+        ems = C.c_float()
+        s.elapsed_ms = C.pointer(ems)
         ng = C.c_int64()
         _check(load().bsyn_sample(self.h, C.byref(a), C.byref(s), C.byref(ng)), "bsyn_sample")
         res["n_grad"] = ng.value
         res["n_save"] = ns
+        res["kernel_ms"] = ems.value
         return res
 
     def advi(self, want_draws=False, want_udraws=False, want_qdraws=True, want_cpo=False, **kw):

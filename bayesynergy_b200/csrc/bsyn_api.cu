@@ -166,7 +166,10 @@ static const VariantOps *ops_for(const bsyn_batch *b, bool allow_fast = true)
     return (allow_fast && b->fast) ? b->fast : variant(b->cpl);
 }
 
-static SmemLayout make_layout(const bsyn_batch *b, const VariantOps *ops, bool per_warp_problem, size_t *bytes, int warps = WPC)
+// vpark_vs > 0 (sampler): also reserve 3 D-vectors of vpark_vs doubles per warp for parking S, p_prev and p across an
+// evaluation -- when that still fits in the 227 KB of an SM; otherwise vpark_off = -1 and the arena is used
+static SmemLayout make_layout(const bsyn_batch *b, const VariantOps *ops, bool per_warp_problem, size_t *bytes, int warps = WPC,
+                              int vpark_vs = 0)
 {
     SmemLayout sl;
     const int tr = ops->tr;
@@ -179,7 +182,13 @@ static SmemLayout make_layout(const bsyn_batch *b, const VariantOps *ops, bool p
     sl.pi_off = sl.pd_off + nblk * sl.pd_stride;
     sl.ws_off = even(sl.pi_off + nblk * sl.pi_stride);
     sl.park_off = even(sl.ws_off + warps * ops->ws_doubles);
-    *bytes = sizeof(double) * (size_t)(sl.park_off + warps * PARK_DOUBLES);
+    size_t tot = (size_t)(sl.park_off + warps * PARK_DOUBLES);
+    sl.vpark_off = -1;
+    if (vpark_vs > 0 && sizeof(double) * (tot + (size_t)warps * 3 * vpark_vs) <= 227 * 1024) {
+        sl.vpark_off = (int)tot;
+        tot += (size_t)warps * 3 * vpark_vs;
+    }
+    *bytes = sizeof(double) * tot;
     return sl;
 }
 
@@ -393,6 +402,53 @@ extern "C" int bsyn_output_name(const bsyn_batch *b, int32_t k, int32_t index, c
     return put(tail[i], 0, 0);
 }
 
+// Parameter blocks = what param_names() / param_dims() of the module report (get_param_names / get_dims,
+// src/stanExports_gp_grid.h:1588-1704; nointeraction: :966-1040): every declared name with its dimensions, including the
+// zero-length la_1 / la_2 / alpha vectors when they are not estimated, then "lp__".
+struct BlockDef { const char *name; int kind; };   // kind: 0 scalar, 1 [est_la], 2 [est_alpha], 3 [n2,n1], 4 [n1], 5 [n2], 6 [N]
+static const BlockDef g_blocks_gp[] = {
+    {"la_1", 1}, {"la_2", 1}, {"log10_ec50_1", 0}, {"log10_ec50_2", 0}, {"theta_1", 0}, {"theta_2", 0}, {"slope_1", 0}, {"slope_2", 0},
+    {"b1", 0}, {"b2", 0}, {"ell", 0}, {"sigma_f", 0}, {"alpha", 2}, {"z", 3}, {"s", 0}, {"s2_log10_ec50_1", 0}, {"s2_log10_ec50_2", 0},
+    {"p0", 3}, {"p01", 4}, {"p02", 5}, {"Delta", 3}, {"GP", 3}, {"ec50_1", 0}, {"ec50_2", 0}, {"CPO", 6}, {"dss_1", 0}, {"dss_2", 0},
+    {"rVUS_f", 0}, {"rVUS_p0", 0}, {"VUS_Delta", 0}, {"VUS_syn", 0}, {"VUS_ant", 0}, {"lp__", 0}};
+static const BlockDef g_blocks_h0[] = {
+    {"la_1", 1}, {"la_2", 1}, {"log10_ec50_1", 0}, {"log10_ec50_2", 0}, {"theta_1", 0}, {"theta_2", 0}, {"slope_1", 0}, {"slope_2", 0},
+    {"s", 0}, {"s2_log10_ec50_1", 0}, {"s2_log10_ec50_2", 0}, {"p0", 3}, {"p01", 4}, {"p02", 5}, {"ec50_1", 0}, {"ec50_2", 0}, {"CPO", 6},
+    {"dss_1", 0}, {"dss_2", 0}, {"rVUS_f", 0}, {"rVUS_p0", 0}, {"lp__", 0}};
+
+extern "C" int32_t bsyn_num_param_blocks(const bsyn_batch *b)
+{
+    if (!b) return -1;
+    return b->opts.model == BSYN_MODEL_GP_GRID ? (int)(sizeof g_blocks_gp / sizeof g_blocks_gp[0]) : (int)(sizeof g_blocks_h0 / sizeof g_blocks_h0[0]);
+}
+extern "C" int bsyn_param_block(const bsyn_batch *b, int32_t k, int32_t block, char *name, int32_t buflen, int32_t *ndims,
+                                int32_t *dims, int32_t *flat_offset)
+{
+    if (!b || k < 0 || k >= b->n || block < 0 || block >= bsyn_num_param_blocks(b) || !name || buflen < 2 || !ndims || !dims || !flat_offset)
+        return fail(BSYN_ERR_ARG, "bsyn_param_block: bad argument");
+    const BlockDef *tab = b->opts.model == BSYN_MODEL_GP_GRID ? g_blocks_gp : g_blocks_h0;
+    const ProbDesc &d = b->descs[k];
+    int off = 0;
+    for (int i = 0;; ++i) {
+        int nd = 0, dm[2] = {0, 0}, len = 1;
+        switch (tab[i].kind) {
+            case 1: nd = 1; dm[0] = b->opts.est_la ? 1 : 0; len = dm[0]; break;
+            case 2: nd = 1; dm[0] = b->opts.est_alpha ? 1 : 0; len = dm[0]; break;
+            case 3: nd = 2; dm[0] = d.n2; dm[1] = d.n1; len = d.n1 * d.n2; break;
+            case 4: nd = 1; dm[0] = d.n1; len = d.n1; break;
+            case 5: nd = 1; dm[0] = d.n2; len = d.n2; break;
+            case 6: nd = 1; dm[0] = d.N; len = d.N; break;
+            default: break;
+        }
+        if (i == block) {
+            snprintf(name, (size_t)buflen, "%s", tab[i].name);
+            *ndims = nd; dims[0] = dm[0]; dims[1] = dm[1]; *flat_offset = off;   // lp__ sits behind the write_array row
+            return BSYN_OK;
+        }
+        off += len;
+    }
+}
+
 extern "C" int32_t bsyn_max_params(const bsyn_batch *b) { return b ? b->maxD : -1; }
 extern "C" int32_t bsyn_max_outputs(const bsyn_batch *b) { return b ? b->maxOut : -1; }
 extern "C" int32_t bsyn_num_problems(const bsyn_batch *b) { return b ? b->n : -1; }
@@ -554,7 +610,7 @@ static int ensure(double **p, size_t *have, size_t need)
 }
 
 struct DevSinks {
-    double *draws = nullptr, *udraws = nullptr, *cpo = nullptr, *inv_metric = nullptr;
+    double *draws = nullptr, *udraws = nullptr, *cpo = nullptr, *inv_metric = nullptr, *init_u = nullptr;
     long long ld_draws = 0, ld_u = 0;
     int ld_cpo = 0, ld_im = 0;
 };
@@ -603,7 +659,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     b->last_chains = a->chains; b->last_nsave = sp.ld_save; b->last_nskip = ns_warm; b->last_var_ns = false;
     sp.qdraws = b->d_qdraws; sp.sp = b->d_sp; sp.chain_stats = b->d_chain_stats;
     sp.draws = ds.draws; sp.ld_draws = ds.ld_draws; sp.udraws = ds.udraws; sp.ld_u = ds.ld_u;
-    sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im;
+    sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im; sp.init_u = ds.init_u;
     // warps per CTA: the largest compiled variant (12, 6, 4, 1) whose shared memory fits on an SM.  A batch that
     // matches a compile-time specialisation (diag_e only) uses it: 12 or 16 warps per SM, with or without the tick barrier
     // (BSYN_NUTS_NW / BSYN_NUTS_TICK override the defaults for A/B measurements).
@@ -621,7 +677,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
         if (fast && !want && cand != BSYN_FAST_DEFAULT_NW) continue;
         if (!fast && (cand == 16 || cand == 14)) continue;
         if (a->metric == 1 && cand != 12 && cand != 4) continue;
-        sp.sl = make_layout(b, ops, true, &bytes, cand);
+        sp.sl = make_layout(b, ops, true, &bytes, cand, (b->cpl + 1) * 32);
         if (bytes > 227 * 1024) continue;
         if (ops->nuts_occupancy(cand, a->metric, tick, bytes, &per_sm) != cudaSuccess) { cudaGetLastError(); continue; }
         if (per_sm >= 1) { nw = cand; break; }
@@ -729,7 +785,13 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
         if (cudaMalloc(&ds.inv_metric, sizeof(double) * nch * ds.ld_im) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); return fail(BSYN_ERR_ALLOC, "inv_metric buffer"); }
         cudaMemsetAsync(ds.inv_metric, 0, sizeof(double) * nch * ds.ld_im, b->stream);
     }
-    rc = run_sampler(b, args, ds, total_grad_evals, nullptr);
+    if (sinks->init_u) {
+        ds.ld_im = b->maxD;
+        if (cudaMalloc(&ds.init_u, sizeof(double) * nch * b->maxD) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); return fail(BSYN_ERR_ALLOC, "init_u buffer"); }
+        cudaMemsetAsync(ds.init_u, 0, sizeof(double) * nch * b->maxD, b->stream);
+    }
+    float ms_total = 0.f;
+    rc = run_sampler(b, args, ds, total_grad_evals, &ms_total);
     if (rc == BSYN_OK) {
         cudaError_t e = cudaSuccess;
         if (sinks->draws) e = cudaMemcpy(sinks->draws, ds.draws, sizeof(double) * nrows * ds.ld_draws, cudaMemcpyDeviceToHost);
@@ -739,6 +801,8 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
         if (e == cudaSuccess && sinks->summary) e = cudaMemcpy(sinks->summary, b->d_summary, sizeof(double) * (size_t)b->n * BSYN_NQ * 2, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && sinks->chain_stats) e = cudaMemcpy(sinks->chain_stats, b->d_chain_stats, sizeof(double) * nch * 8, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && sinks->inv_metric) e = cudaMemcpy(sinks->inv_metric, ds.inv_metric, sizeof(double) * nch * ds.ld_im, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sinks->init_u) e = cudaMemcpy(sinks->init_u, ds.init_u, sizeof(double) * nch * b->maxD, cudaMemcpyDeviceToHost);
+        if (sinks->elapsed_ms) *sinks->elapsed_ms = ms_total;
         if (e == cudaSuccess && sinks->cpo_mean) {
             // mean over chains and sampling draws of CPO_n
             std::vector<double> tmp(nch * std::max(1, ds.ld_cpo));
@@ -756,7 +820,7 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
         }
         if (e != cudaSuccess) rc = fail(BSYN_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
     }
-    cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric);
+    cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); cudaFree(ds.init_u);
     return rc;
 }
 

@@ -101,14 +101,16 @@ template <int CPL, class SP = SpecRT> struct Cfg {
     static constexpr int OFF_ITH = 96;                  // 16 per-slot reciprocals (1/theta, 1/(1-la), 1/(1+s^2))
     static constexpr int OFF_L1R = 112;                 // L1 row-major  [j*NM + l]
     static constexpr int OFF_L2R = OFF_L1R + NN;        // L2 row-major  [i*NM + k]
-    static constexpr int OFF_L2C = OFF_L2R + NN;        // L2 col-major  [k*NM + i]
-    static constexpr int OFF_ZS = OFF_L2C + NN;         // Z           ; later S1 = L1^T L1bar
+    static constexpr int OFF_ZS = OFF_L2R + NN;         // Z           ; later S1 = L1^T L1bar
     static constexpr int OFF_TS = OFF_ZS + NN;          // T = L2 Z    ; later S2 = L2^T L2bar
     static constexpr int OFF_TT = OFF_TS + NN;          // T^T         ; later Y1 transpose
     static constexpr int OFF_GS = OFF_TT + NN;          // G -> Gbar (in place) -> Zbar
     static constexpr int OFF_WS = OFF_GS + NN;          // L1 col-major (Cholesky) ; p0bar ; W = Gbar L1 ; later Y2 transpose
     static constexpr int OFF_LB1 = OFF_WS + NN;         // L1bar row-major [j*NM + l] ; later X1
-    static constexpr int OFF_LB2 = OFF_LB1 + NN;        // L2bar col-major [i + k*NM] ; later X2
+    // L2 col-major [k*NM + i] is dead after T = L2 Z, before L2bar is formed: one buffer serves both (the Cholesky
+    // publishes whole columns, zeros above the diagonal, so X2 left over from the previous evaluation does no harm)
+    static constexpr int OFF_L2C = OFF_LB1 + NN;
+    static constexpr int OFF_LB2 = OFF_L2C;             // L2bar col-major [i + k*NM] ; later X2
     static constexpr int OFF_EX = OFF_LB2 + NN;         // exp table per pair
     static constexpr int WS_DOUBLES = OFF_EX + PK + (PK & 1);
 };

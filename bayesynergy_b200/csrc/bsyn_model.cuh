@@ -206,7 +206,7 @@ __device__ __forceinline__ bool gp_forward(const OptV<SP> &F, const ProbS &P, co
             const double inv = fast_rsqrt(dkk);
             a[k] *= inv;
             if (r == k) invd[h * 16 + k] = inv;
-            if (r >= k && r < NM) Lc[k * NM + r] = a[k];   // publish column k
+            if (r < NM) Lc[k * NM + r] = (r >= k) ? a[k] : 0.0;   // publish column k (zeros above the diagonal)
             __syncwarp();
             // trailing update a[j] -= L[r][k] * L[j][k], j > k.  Entries j > r (upper triangle) are updated too:
             // they are never read (masked to zero when the row is stored).
@@ -541,7 +541,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     // generated quantities (only when gq.on): output offsets, VUS accumulators, f on its (n2+1) x (n1+1) grid
     const int G = NF ? NF * NF : P.G;
     // row layout: [params D][p0 G][p01 n1][p02 n2][Delta G][GP G][ec50 2][CPO N][dss 2][VUS 2 (+3)]
-    double *const fg = Lb1;   // (n2+1)(n1+1) <= 2 NN doubles: spans Lb1..Lb2, both free until the adjoint products
+    double *const fg = Lb1;   // (n2+1)(n1+1) <= 2 NN doubles: spans Lb1..Lb2 (= L2c, dead by now), free until the adjoint products
     double vus[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int t = 0; t < CPL; ++t) {

@@ -21,11 +21,12 @@ namespace bsyn {
 // shared-memory layout (offsets in doubles), computed on the host from the batch maxima
 struct SmemLayout {
     int tri_off, pd_off, pi_off, ws_off, pd_stride, pi_stride;   // *_stride: per-warp problem blocks (logp kernel)
-    int park_off;                                                // sampler: per-warp parking area (PARK_DOUBLES each)
+    int park_off;                                                // sampler: per-warp chain-state block (PARK_DOUBLES each)
+    int vpark_off;                                               // sampler: per-warp vector parking (3 D-vectors), or -1
 };
-// per-warp parking area: warp-uniform chain state parked during an evaluation (34 doubles, then up to 32 ints), and
-// the generated-quantities sink block (GQ_DOUBLES) read by the evaluation when gq.on
-constexpr int PARK_INTS = 34, PARK_GQ = 50, PARK_DOUBLES = 60;
+// per-warp chain-state block: the warp-uniform chain state (struct ChainSt, <= PARK_GQ doubles) lives here for the
+// whole life of a chain, followed by the generated-quantities sink block (GQ_DOUBLES) the evaluation reads when gq.on
+constexpr int PARK_GQ = 52, PARK_DOUBLES = 62;
 
 struct SamplerParams {
     int n_problems, chains;
@@ -41,6 +42,7 @@ struct SamplerParams {
     double *sp;
     double *chain_stats;
     double *inv_metric; int ld_im;
+    double *init_u;                  // [n_problems][chains][ld_im]: the initial point of every chain (unconstrained)
     double *cpo_acc; int ld_cpo;     // [n_problems][chains][ld_cpo]
     // dense_e metric (metric == 1): per resident warp  M^-1 (float, column-major DI x DI),  its Cholesky factor
     // (double, column-major lower) and the Welford cross-product accumulator (double)
@@ -237,6 +239,27 @@ struct TransInfo {
     double accept, energy;
     int depth, nleap, divergent;
 };
+// Warp-uniform state of one chain, resident in shared memory (every lane stores the same value to the same address).
+// Only what the evaluation itself touches lives in registers; the bookkeeping after an evaluation loads what it needs
+// where it needs it.  (Round 1 kept all of this in registers and parked it with 25 STS.128 + 25 LDS.128 around every
+// evaluation; the bulk reload then spilled to local memory: 74 LDL + 45 STL per evaluation, profiles/r02_nuts_v1*.)
+struct ChainSt {
+    double eps, mu, sbar, xbar, cnt, wn, n_div, n_maxd, nleap_tot, nleap_samp, acc_sum, n_samp_it;      // chain level
+    double is_H0, is_V0, eps_try;                                                                       // init_stepsize
+    double e_used, H0, otherV, sampleV, sampleH, proposeV, proposeH, lsw, summetro, lsw_sub, u_leaf;    // transition
+    TransInfo info;
+    long long cg;
+    unsigned long long ngrad;
+    double *cs, *cpo_acc;
+    const double *yglob;
+    const int *iiglob;
+    int it, isave, win_size, win_end, init_try, is_it, is_dir, curdir, depth, nleap, k, nleaf;
+    int need_istep, divergent;
+    uint32_t istep_tag;
+    int pad_;
+    ProbDesc pd;
+};
+static_assert(sizeof(ChainSt) <= PARK_GQ * sizeof(double), "ChainSt must fit in front of the GQ sink block");
 enum Phase { PH_FETCH = 0, PH_INIT, PH_ISTEP, PH_TREE, PH_GQ, PH_DONE };
 enum Next { N_NONE = 0, N_ENDTRANS, N_ITER, N_TRANS, N_DOUBLE };
 
@@ -278,39 +301,44 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
         init_buffer = (int)(0.15 * nw); term_buffer = (int)(0.1 * nw);
         base_window = nw - (init_buffer + term_buffer);
     }
-    // ---- chain state (registers; warp-uniform unless it is a WVec) ----
+    // ---- chain state: D-vectors and what the evaluation touches in registers, everything warp-uniform in ChainSt ----
     int phase = PH_FETCH;
     ProbS P;
-    ProbDesc pd;
     int cell[CPL];
     RngKey rk;
-    long long cg = 0;
     WVec<CPL> q, p, g, minv, S, pprev;
     // dense_e: M^-1 p and M^-1 g of the state in registers, so that a leapfrog costs ONE matrix-vector product:
     // M^-1 (p + e/2 g) = M^-1 p + e/2 M^-1 g before the evaluation, and the same update with the new g after it
     WVec<CPL> ps_c, mg_c, yv_keep;
     bool sharp_valid = false;
     double V = 0.0, step = 0.0;
-    unsigned long long ngrad = 0;
-    // chain level
-    int it = 0, isave = 0, win_size = 0, win_end = 0, init_try = 0;
-    double eps = 0.0, mu = 0.0, sbar = 0.0, xbar = 0.0, cnt = 0.0, wn = 0.0;
-    bool need_istep = false;
-    uint32_t istep_tag = 0;
-    double n_div = 0.0, n_maxd = 0.0, nleap_tot = 0.0, nleap_samp = 0.0, acc_sum = 0.0, n_samp_it = 0.0;
-    // init_stepsize level
-    int is_it = 0, is_dir = 0;
-    double is_H0 = 0.0, is_V0 = 0.0, eps_try = 0.0;
-    // transition level
-    double e_used = 0.0, H0 = 0.0, otherV = 0.0, sampleV = 0.0, sampleH = 0.0, proposeV = 0.0, proposeH = 0.0;
-    double lsw = 0.0, summetro = 0.0, lsw_sub = 0.0;
-    int curdir = 1, depth = 0, nleap = 0, k = 0, nleaf = 1;
-    bool divergent = false;
-    double u_leaf = 0.5;
-    TransInfo info{};
-    const double *yglob = nullptr;
-    const int *iiglob = nullptr;
-    double *cpo_acc = nullptr, *cs = nullptr;
+    ChainSt &st = *reinterpret_cast<ChainSt *>(smem + s_park);
+    ProbDesc &pd = st.pd;
+    long long &cg = st.cg;
+    unsigned long long &ngrad = st.ngrad;
+    int &it = st.it, &isave = st.isave, &win_size = st.win_size, &win_end = st.win_end, &init_try = st.init_try;
+    double &eps = st.eps, &mu = st.mu, &sbar = st.sbar, &xbar = st.xbar, &cnt = st.cnt, &wn = st.wn;
+    int &need_istep = st.need_istep;
+    uint32_t &istep_tag = st.istep_tag;
+    double &n_div = st.n_div, &n_maxd = st.n_maxd, &nleap_tot = st.nleap_tot, &nleap_samp = st.nleap_samp,
+           &acc_sum = st.acc_sum, &n_samp_it = st.n_samp_it;
+    int &is_it = st.is_it, &is_dir = st.is_dir;
+    double &is_H0 = st.is_H0, &is_V0 = st.is_V0, &eps_try = st.eps_try;
+    double &e_used = st.e_used, &H0 = st.H0, &otherV = st.otherV, &sampleV = st.sampleV, &sampleH = st.sampleH,
+           &proposeV = st.proposeV, &proposeH = st.proposeH;
+    double &lsw = st.lsw, &summetro = st.summetro, &lsw_sub = st.lsw_sub;
+    int &curdir = st.curdir, &depth = st.depth, &nleap = st.nleap, &k = st.k, &nleaf = st.nleaf;
+    int &divergent = st.divergent;
+    double &u_leaf = st.u_leaf;
+    TransInfo &info = st.info;
+    const double *&yglob = st.yglob;
+    const int *&iiglob = st.iiglob;
+    double *&cpo_acc = st.cpo_acc, *&cs = st.cs;
+    if (lane == 0) { st.ngrad = 0; st.cg = 0; }
+    __syncwarp();
+    // vectors parked across the evaluation: in shared memory when the layout has room for them (sl.vpark_off >= 0),
+    // else as coalesced rows of the arena
+    const int s_vp = pin_uniform(sp.sl.vpark_off >= 0 ? sp.sl.vpark_off + warp * 3 * VS : -1);
 
     // y = M^-1 x.  diag_e: elementwise; dense_e: column sweep over the active slots, x broadcast from shared memory,
     // M^-1 read coalesced (column g, 32 consecutive rows per load) from the per-warp float matrix.
@@ -483,6 +511,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                     vload<CPL>(R, q);
                     if constexpr (!DENSE) vload<CPL>(R + VS, minv);
                 }
+                if constexpr (!DENSE) vstore<CPL>(A + A_PARK_MINV * VS, minv);
                 phase = PH_INIT;
             }
         }
@@ -518,60 +547,24 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 gq_publish(gq.so, pd.D, yglob, iiglob, uz, sp.draws ? sp.draws + rowi * sp.ld_draws : nullptr,
                            sp.qdraws ? sp.qdraws + rowi * 12 : nullptr, (it >= nw) ? cpo_acc : nullptr);
             }
-            // Warp-uniform chain scalars (60+ registers replicated in every lane) go to shared memory for the
-            // duration of the evaluation, whose schedule is register-starved otherwise (profiles/: the same kernel
-            // with 255 registers runs each warp 1.45x faster).
-#define BSYN_PARK_D2(X) X(eps, mu) X(sbar, xbar) X(cnt, wn) X(n_div, n_maxd) X(nleap_tot, nleap_samp) X(acc_sum, n_samp_it)      \
-    X(is_H0, is_V0) X(eps_try, e_used) X(H0, otherV) X(sampleV, sampleH) X(proposeV, proposeH) X(lsw, summetro)                 \
-    X(lsw_sub, u_leaf) X(info.accept, info.energy)
-#define BSYN_PARK_P2(X) X(cg, ngrad) X(cs, cpo_acc) X(yglob, iiglob)          /* 64-bit integers / pointers */
-#define BSYN_PARK_I4(X) X(it, isave, win_size, win_end) X(init_try, is_it, is_dir, curdir) X(depth, nleap, k, nleaf)           \
-    X(info.depth, info.nleap, info.divergent, pd.n1) X(pd.n2, pd.N, pd.G, pd.ncf) X(pd.D, pd.n_out, pd.off_d, pd.off_i)        \
-    X(pd.n_d_smem, pd.n_i_smem, flag_istep, flag_div)
-            {   // 128-bit stores: 14 + 3 + 7 STS.128 (every lane writes the same values to the same addresses)
-                int flag_istep = (int)need_istep, flag_div = (int)divergent;
-                double2 *pk = reinterpret_cast<double2 *>(smem + s_park);
-#define BSYN_ST(a, b) *pk++ = make_double2(a, b);
-                BSYN_PARK_D2(BSYN_ST)
-#undef BSYN_ST
-#define BSYN_ST(a, b) *pk++ = make_double2(__longlong_as_double((long long)a), __longlong_as_double((long long)b));
-                BSYN_PARK_P2(BSYN_ST)
-#undef BSYN_ST
-                int4 *pi = reinterpret_cast<int4 *>(smem + s_park + PARK_INTS);
-#define BSYN_ST(a, b, c, d) *pi++ = make_int4(a, b, c, d);
-                BSYN_PARK_I4(BSYN_ST)
-#undef BSYN_ST
-                SMI(2 * (s_park + PARK_INTS) + 28) = (int)istep_tag;
+            // The evaluation needs every register it can get; S, pprev and p are dead weight across it: they are parked
+            // in shared memory (or, when it has no room, in the arena: L2-resident, coalesced).  M^-1 only changes at a
+            // metric update, where it is written to its arena row; it is re-read after the evaluation.
+            if (s_vp >= 0) {
+                vstore<CPL>(smem + s_vp, S); vstore<CPL>(smem + s_vp + VS, pprev); vstore<CPL>(smem + s_vp + 2 * VS, p);
+            } else {
+                vstore<CPL>(A + A_PARK_S * VS, S); vstore<CPL>(A + A_PARK_PREV * VS, pprev); vstore<CPL>(A + A_PARK_P * VS, p);
             }
-            // The evaluation needs every register it can get; S, pprev, p and minv are dead weight across it.  Parking
-            // them in the arena (L2-resident, coalesced) beats the compiler's choice of what to spill.
-            vstore<CPL>(A + A_PARK_S * VS, S); vstore<CPL>(A + A_PARK_PREV * VS, pprev); vstore<CPL>(A + A_PARK_P * VS, p);
-            if constexpr (!DENSE) vstore<CPL>(A + A_PARK_MINV * VS, minv);
-            else vstore<CPL>(A + A_PARK_YV * VS, yv_keep);
+            if constexpr (DENSE) vstore<CPL>(A + A_PARK_YV * VS, yv_keep);
             double lp;
             const bool okv = warp_logp_grad<CPL, false, SP>(F, P, ws, cell, q, sp.jacobian, lp, g, nullptr, gq);
-            vload<CPL>(A + A_PARK_S * VS, S); vload<CPL>(A + A_PARK_PREV * VS, pprev); vload<CPL>(A + A_PARK_P * VS, p);
+            if (s_vp >= 0) {
+                vload<CPL>(smem + s_vp, S); vload<CPL>(smem + s_vp + VS, pprev); vload<CPL>(smem + s_vp + 2 * VS, p);
+            } else {
+                vload<CPL>(A + A_PARK_S * VS, S); vload<CPL>(A + A_PARK_PREV * VS, pprev); vload<CPL>(A + A_PARK_P * VS, p);
+            }
             if constexpr (!DENSE) vload<CPL>(A + A_PARK_MINV * VS, minv);
             else vload<CPL>(A + A_PARK_YV * VS, yv_keep);
-            {
-                int flag_istep, flag_div;
-                const double2 *pk = reinterpret_cast<const double2 *>(smem + s_park);
-#define BSYN_LD(a, b) { const double2 t2 = *pk++; a = t2.x; b = t2.y; }
-                BSYN_PARK_D2(BSYN_LD)
-#undef BSYN_LD
-#define BSYN_LD(a, b) { const double2 t2 = *pk++; a = (decltype(a))__double_as_longlong(t2.x); b = (decltype(b))__double_as_longlong(t2.y); }
-                BSYN_PARK_P2(BSYN_LD)
-#undef BSYN_LD
-                const int4 *pi = reinterpret_cast<const int4 *>(smem + s_park + PARK_INTS);
-#define BSYN_LD(a, b, c, d) { const int4 t4 = *pi++; a = t4.x; b = t4.y; c = t4.z; d = t4.w; }
-                BSYN_PARK_I4(BSYN_LD)
-#undef BSYN_LD
-                need_istep = flag_istep != 0; divergent = flag_div != 0;
-                istep_tag = (uint32_t)SMI(2 * (s_park + PARK_INTS) + 28);
-            }
-#undef BSYN_PARK_D2
-#undef BSYN_PARK_P2
-#undef BSYN_PARK_I4
             rk.k0 = (uint32_t)sp.seed; rk.k1 = (uint32_t)(sp.seed >> 32); rk.chain = (uint32_t)cg;
             if (!gq.on) ++ngrad;
             if (!okv || !(fabs(lp) < INFINITY)) {   // domain error in the reference => infinite potential
@@ -609,10 +602,11 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             for (int t = 0; t < CPL; ++t) fin = fin && fabs(g.z[t]) < INFINITY;
             if (__all_sync(FULL, fin)) {
                 eps = sp.stepsize0;
-                need_istep = true;            // base_hmc::init_stepsize runs before the first transition ...
+                need_istep = 1;            // base_hmc::init_stepsize runs before the first transition ...
+                if (sp.init_u) store_user_vec<CPL>(F, pd, cell, q, sp.init_u + cg * sp.ld_im);
                 if (sp.resume_in && init_try == 0) {   // ... unless the chain resumes with its adapted step size
                     eps = sp.resume[cg * sp.resume_stride + 2 * VS];
-                    need_istep = false;
+                    need_istep = 0;
                 }
                 istep_tag = 0xFFFFFF00u;
                 mu = 0.0; sbar = 0.0; xbar = 0.0; cnt = 0.0; wn = 0.0;
@@ -653,7 +647,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 vload<CPL>(A + A_SQ * VS, q); vload<CPL>(A + A_SG * VS, g); V = is_V0;
                 eps = eps_try;
                 mu = log(10.0 * eps); sbar = 0.0; xbar = 0.0; cnt = 0.0;
-                need_istep = false;
+                need_istep = 0;
                 next = N_TRANS;
             }
         } else if (phase == PH_TREE) {
@@ -662,7 +656,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             double h = V + kinetic();
             if (!(h == h)) h = INFINITY;
             const double w = H0 - h;
-            if (h - H0 > 1000.0) divergent = true;
+            if (h - H0 > 1000.0) divergent = 1;
             lsw_sub = log_add_exp(lsw_sub, w);
             summetro += (w > 0.0) ? 1.0 : fast_exp(w);
             bool valid = !divergent;
@@ -839,6 +833,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                             for (int t = 0; t < CPL; ++t)
                                 if ((cell[t] >> 17) & 1) minv.z[t] = fma(aa, m2.z[t] * inm1, bb);
                             if (lane_active) minv.s = fma(aa, m2.s * inm1, bb);
+                            vstore<CPL>(A + A_PARK_MINV * VS, minv);
                         } else {
                             // M^-1 = n/(n+5) cov + 1e-3 5/(n+5) I, symmetrised from the lower triangle, rounded to float;
                             // L = chol(M^-1) of exactly that rounded matrix (column-major lower, right-looking, in place)
@@ -900,7 +895,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                                 if (next_boundary >= nw - term_buffer) win_end = nw - term_buffer - 1;
                             }
                         }
-                        need_istep = true;   // ... and after every metric update (restart of the dual averaging)
+                        need_istep = 1;   // ... and after every metric update (restart of the dual averaging)
                         istep_tag = 0xFFFF0000u + (uint32_t)it;
                     }
                     vstore<CPL>(A + A_WM * VS, m); vstore<CPL>(A + A_WM2 * VS, m2);
@@ -988,7 +983,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             vstore<CPL>(A + A_SQ * VS, q); vstore<CPL>(A + A_SG * VS, g);
             vstore<CPL>(A + A_RHO_OLD * VS, p);
             otherV = V; sampleV = V; sampleH = H0; proposeV = V; proposeH = H0;
-            curdir = 1; lsw = 0.0; summetro = 0.0; depth = 0; nleap = 0; divergent = false;
+            curdir = 1; lsw = 0.0; summetro = 0.0; depth = 0; nleap = 0; divergent = 0;
             next = N_DOUBLE;
         }
         if (next == N_DOUBLE) {

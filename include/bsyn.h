@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BSYN_VERSION 100
+#define BSYN_VERSION 200
 
 enum {
     BSYN_OK = 0,
@@ -79,6 +79,14 @@ int32_t bsyn_num_outputs(const bsyn_batch *b, int32_t problem);    /* one write_
  * param_names / param_fnames_oi (cc:16-18) report, in the declaration order of src/stanExports_gp_grid.h:2256-2402.
  * The first bsyn_num_params entries are the parameters.  Host-only (no GPU involved). */
 int bsyn_output_name(const bsyn_batch *b, int32_t problem, int32_t index, char *buf, int32_t buflen);
+/* Parameter blocks: the declared names and dimensions param_names() / param_dims() report (cc:16, 19;
+ * get_param_names / get_dims, src/stanExports_gp_grid.h:1588-1704), zero-length la_1 / la_2 / alpha included, "lp__"
+ * last.  block i of `problem`: name, ndims (0 scalar, 1 vector, 2 matrix), dims[2], and the offset of its first element
+ * in a write_array row (matrices column-major).  update_param_oi / param_oi_tidx / param_fnames_oi are bookkeeping over
+ * these blocks and stay on the R side of the binding. */
+int32_t bsyn_num_param_blocks(const bsyn_batch *b);
+int bsyn_param_block(const bsyn_batch *b, int32_t problem, int32_t block, char *name, int32_t buflen, int32_t *ndims,
+                     int32_t *dims, int32_t *flat_offset);
 int32_t bsyn_max_params(const bsyn_batch *b);
 int32_t bsyn_max_outputs(const bsyn_batch *b);
 int32_t bsyn_num_problems(const bsyn_batch *b);
@@ -169,8 +177,15 @@ typedef struct bsyn_sample_sinks {
     /* per problem x chain: [n_problems][chains][8] = stepsize, n_divergent, n_max_treedepth, n_leapfrog_total
      * (warmup+sampling), n_leapfrog_sampling, mean accept_stat (sampling), init_failed, reserved */
     double *chain_stats;
-    /* adapted diagonal inverse metric [n_problems][chains][ld_udraws'] -- uses bsyn_max_params() stride */
+    /* adapted inverse metric [n_problems][chains][bsyn_max_params()]: the diagonal M^-1 of diag_e, the diagonal of the
+     * dense M^-1 of dense_e (the device keeps the dense matrix rounded to float for the M^-1 p products; its exact Cholesky
+     * factor is used for the momentum draws, so the sampler stays a valid HMC: a narrower arithmetic than the reference's) */
     double *inv_metric;
+    /* the initial point of every chain on the unconstrained scale [n_problems][chains][bsyn_max_params()] (what rstan
+     * reports, constrained, as attr "inits"; constrain it with bsyn_write_array) */
+    double *init_u;
+    /* device time of the sampling launch in ms (attr "elapsed_time" is this, split by the leapfrog counts of chain_stats) */
+    float *elapsed_ms;
 } bsyn_sample_sinks;
 
 /* Runs the whole screen.  total_grad_evals (may be NULL) receives the number of log-density gradient
