@@ -56,7 +56,8 @@ class BsynSinks(C.Structure):
                 ("qdraws", C.POINTER(C.c_double)), ("sampler_params", C.POINTER(C.c_double)),
                 ("summary", C.POINTER(C.c_double)), ("cpo_mean", C.POINTER(C.c_double)), ("ld_cpo", C.c_int64),
                 ("chain_stats", C.POINTER(C.c_double)), ("inv_metric", C.POINTER(C.c_double)),
-                ("init_u", C.POINTER(C.c_double)), ("elapsed_ms", C.POINTER(C.c_float))]
+                ("init_u", C.POINTER(C.c_double)), ("f_mean", C.POINTER(C.c_double)), ("ld_f", C.c_int64),
+                ("surfaces", C.POINTER(C.c_double)), ("lpml", C.POINTER(C.c_double)), ("elapsed_ms", C.POINTER(C.c_float))]
 
 
 class BsynAdviArgs(C.Structure):
@@ -209,6 +210,7 @@ class Batch:
         self.max_outputs = L.bsyn_max_outputs(h)
         self.dims = [L.bsyn_num_params(h, k) for k in range(n)] if n <= 4096 else None
         self.n_obs = [int(np.asarray(sd.y).shape[0]) for sd in stan_data_list]
+        self.n_cells = [(sd.n1 + 1) * (sd.n2 + 1) for sd in stan_data_list]
 
     def close(self):
         if getattr(self, "h", None):
@@ -302,7 +304,7 @@ class Batch:
         return out
 
     def sample(self, want_draws=False, want_udraws=False, want_qdraws=True, want_sampler_params=True,
-               want_cpo=False, want_inv_metric=False, want_inits=False, **kw):
+               want_cpo=False, want_inv_metric=False, want_inits=False, want_f_mean=False, want_surfaces=False, **kw):
         """Run adaptive NUTS for every experiment x chain in one launch.  Returns a dict of numpy arrays."""
         a = self.sampler_args(**kw)
         ns = (a.iter - a.warmup + a.thin - 1) // a.thin + ((a.warmup + a.thin - 1) // a.thin if a.save_warmup else 0)
@@ -335,6 +337,15 @@ class Batch:
         if want_inits:
             res["init_u"] = np.zeros((n, ch, self.max_params))
             s.init_u = _dp(res["init_u"])
+        if want_f_mean or want_surfaces:
+            s.ld_f = max(self.n_cells)
+        if want_f_mean:
+            res["f_mean"] = np.zeros((n, s.ld_f))
+            s.f_mean = _dp(res["f_mean"])
+        if want_surfaces:          # f (mean / median if robust), p0 (median), Delta (median) per grid cell, and LPML
+            res["surfaces"] = np.zeros((n, 3, s.ld_f))
+            res["lpml"] = np.zeros(n)
+            s.surfaces, s.lpml = _dp(res["surfaces"]), _dp(res["lpml"])
         ems = C.c_float()
         s.elapsed_ms = C.pointer(ems)
         ng = C.c_int64()

@@ -90,6 +90,90 @@ def _diagnose(sp, chain_stats, qdraws, max_treedepth):
     return msgs, ndiv
 
 
+def _posterior_from_draws(sd, draws, lp, model="gp_grid"):
+    """rstan::extract(fit) from the write_array rows draws[chains, n_save, n_out] (chains pooled, as extract does)."""
+    names = output_names(sd, model)
+    flat = draws[:, :, :len(names)].reshape(-1, len(names))
+    n_save = flat.shape[0]
+    col = {nm: i for i, nm in enumerate(names)}
+    n1, n2, N = sd.n1, sd.n2, sd.N
+
+    def block(first, count):
+        return flat[:, col[first]:col[first] + count]
+
+    def grid(first):
+        return block(first, n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
+
+    posterior = {}
+    for nm in param_names(sd, model):
+        base = nm.split("[")[0]
+        if base != "z":
+            posterior.setdefault(base, flat[:, col[nm]])
+    posterior["p0"] = grid("p0[1,1]")
+    posterior["p01"] = block("p01[1]", n1)
+    posterior["p02"] = block("p02[1]", n2)
+    if model == "gp_grid":
+        posterior["z"] = grid("z[1,1]")
+        posterior["Delta"] = grid("Delta[1,1]")
+        posterior["GP"] = grid("GP[1,1]")
+    posterior["CPO"] = block("CPO[1]", N)
+    for nm in ("ec50_1", "ec50_2", "dss_1", "dss_2", "rVUS_f", "rVUS_p0", "VUS_Delta", "VUS_syn", "VUS_ant"):
+        if nm in col:
+            posterior[nm] = flat[:, col[nm]]
+    posterior["lp__"] = lp
+    return posterior
+
+
+def _surface_grids(sd, surfaces_k):
+    """[3, ld_f] device surfaces -> f, p0, Delta as (n2+1) x (n1+1) matrices (cells are column-major on the device)."""
+    ncf = (sd.n1 + 1) * (sd.n2 + 1)
+    return tuple(surfaces_k[i, :ncf].reshape(sd.n1 + 1, sd.n2 + 1).T.copy() for i in range(3))
+
+
+def _outlier_message(sd, f_cells, s_mean, lambda_):
+    """The residual rule of R/bayesynergy.R:305-314 on the posterior surface of f (column-major cell vector)."""
+    fo = f_cells[sd.ii_obs - 1]
+    resid = sd.y - fo
+    point_sd = np.sqrt(s_mean ** 2 * (fo + lambda_))
+    if (np.abs(resid) > 3 * point_sd).any():
+        return (f"Largest residuals from posterior median is {resid.max():.4g}, which is more than three times the "
+                "observation noise. This could indicate the presence of an outlier.")
+    return None
+
+
+def _assemble_object(sd, meta, posterior, surfaces_k, lpml, sp, chain_stats, qdraws, options, max_treedepth):
+    """The fields of the reference's `bayesynergy` object (R/bayesynergy.R:244-343) for one experiment.  The posterior
+    surfaces (mean / median per dose-grid cell) and LPML come reduced from the device (bsyn_sample's `surfaces` / `lpml`
+    sinks), not from the draws on the host."""
+    f_mean, p0_mean, Delta_mean = _surface_grids(sd, surfaces_k)
+    skip = {"z", "p0", "p01", "p02", "Delta", "CPO", "lp__"}
+    posterior_mean = {k: (float(v.mean()) if v.ndim == 1 else v.mean(axis=0)) for k, v in posterior.items() if k not in skip}
+    posterior_mean.update(f=f_mean, p0=p0_mean, Delta=Delta_mean)
+    if options["method"] == "sampling":
+        messages, ndiv = _diagnose(sp, chain_stats, qdraws, max_treedepth)
+    else:
+        messages, ndiv = [], float("nan")
+    returnCode = 1 if messages else 0
+    msg = _outlier_message(sd, f_mean.T.reshape(-1), posterior_mean["s"], options["lambda_"])
+    if msg:
+        warnings.warn(msg)
+        returnCode = 1
+        messages.append(msg)
+    model = dict(type=options["type"], lower_asymptotes=options["lower_asymptotes"], method=options["method"],
+                 bayes_factor=options["bayes_factor"], heteroscedastic=options["heteroscedastic"],
+                 robust=options["robust"], pcprior=options["pcprior"], lambda_=options["lambda_"])
+    if options["type"] == 3:
+        model.update(nu=options["nu"], pcprior_hypers=tuple(options["pcprior_hypers"]))
+    obj = dict(posterior=posterior, posterior_mean=posterior_mean,
+               data=dict(y=meta["y"], x=meta["x"], drug_names=meta["drug_names"], experiment_ID=meta["experiment_ID"],
+                         units=meta["units"], indices=sd.ii_obs),
+               model=model, returnCode=returnCode, LPML=float(lpml), divergent=float("nan"))
+    if returnCode:
+        obj["messages"] = messages
+        obj["divergent"] = ndiv
+    return obj
+
+
 def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, lower_asymptotes=True,
                 heteroscedastic=True, bayes_factor=False, robust=False, rho=0.90, pcprior=False,
                 pcprior_hypers=(1, 0.1, 1, 0.2), lambda_=0.005, nu=1.5, method="sampling", control=None,
@@ -109,10 +193,13 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
                  bayes_factor=bayes_factor, method=method, native=True)
     control = _control_defaults(type, robust, control)
     kw = _sampler_kwargs(control, chains, iter, warmup, thin, seed)
-    drug_names = list(drug_names) if drug_names is not None else ["Drug1", "Drug2"]
-    experiment_ID = experiment_ID if experiment_ID is not None else "Experiment"
-    units = list(units) if units is not None else ["conc.", "conc."]
-
+    meta = dict(y=np.asarray(y), x=np.asarray(x),
+                drug_names=list(drug_names) if drug_names is not None else ["Drug1", "Drug2"],
+                experiment_ID=experiment_ID if experiment_ID is not None else "Experiment",
+                units=list(units) if units is not None else ["conc.", "conc."])
+    options = dict(type=type, lower_asymptotes=lower_asymptotes, method=method, bayes_factor=bayes_factor,
+                   heteroscedastic=heteroscedastic, robust=robust, pcprior=pcprior, lambda_=lambda_, nu=nu,
+                   pcprior_hypers=pcprior_hypers)
     b = _lib.Batch([sd], model="gp_grid", device=device)
     try:
         if method == "vb":
@@ -121,93 +208,49 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
             if st != 0:
                 raise RuntimeError("variational inference failed: " + _VB_ERRORS.get(st, f"status {st}"))
         else:
-            res = b.sample(want_draws=True, want_udraws=bool(bayes_factor), want_cpo=True, **kw)
+            res = b.sample(want_draws=True, want_udraws=bool(bayes_factor), want_surfaces=True, **kw)
     finally:
         b.close()
-    names = output_names(sd)
-    draws = res["draws"][0][:, :, :len(names)]                   # [chains, n_save, n_out]
-    flat = draws.reshape(-1, draws.shape[-1])
-    n_save = flat.shape[0]
-    col = {nm: i for i, nm in enumerate(names)}
-    n1, n2, N = sd.n1, sd.n2, sd.N
-
-    def block(first, count):
-        return flat[:, col[first]:col[first] + count]
-
-    posterior = {}
-    for nm in param_names(sd):
-        base = nm.split("[")[0]
-        if base in ("z",):
-            continue
-        posterior.setdefault(base, flat[:, col[nm]])
-    posterior["z"] = block("z[1,1]", n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
-    posterior["p0"] = block("p0[1,1]", n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
-    posterior["p01"] = block("p01[1]", n1)
-    posterior["p02"] = block("p02[1]", n2)
-    posterior["Delta"] = block("Delta[1,1]", n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
-    posterior["GP"] = block("GP[1,1]", n1 * n2).reshape(n_save, n1, n2).transpose(0, 2, 1)
-    posterior["CPO"] = block("CPO[1]", N)
-    for nm in ("ec50_1", "ec50_2", "dss_1", "dss_2", "rVUS_f", "rVUS_p0", "VUS_Delta", "VUS_syn", "VUS_ant"):
-        posterior[nm] = flat[:, col[nm]]
-    posterior["lp__"] = (res["sampler_params"][0][:, :, 6].reshape(-1) if method == "sampling"
-                         else np.zeros(n_save))               # rstan::vb writes lp__ = 0
-
-    # R/bayesynergy.R:245-291
-    LPML = float(-np.sum(np.log(posterior["CPO"].sum(axis=0) / n_save)))
-    f = np.empty((n_save, n2 + 1, n1 + 1))
-    f[:, 0, 0] = 1.0
-    f[:, 1:, 0] = posterior["p02"]
-    f[:, 0, 1:] = posterior["p01"]
-    f[:, 1:, 1:] = posterior["p0"] + posterior["Delta"]
-    f_mean = np.median(f, axis=0) if robust else f.mean(axis=0)
-    p0 = f.copy()
-    p0[:, 1:, 1:] = posterior["p0"]
-    p0_mean = np.median(p0, axis=0)
-    Delta = np.zeros_like(f)
-    Delta[:, 1:, 1:] = posterior["Delta"]
-    Delta_mean = np.median(Delta, axis=0)
-    skip = {"z", "p0", "p01", "p02", "Delta", "CPO", "lp__"}
-    posterior_mean = {k: (float(v.mean()) if v.ndim == 1 else v.mean(axis=0)) for k, v in posterior.items()
-                      if k not in skip}
-    posterior_mean.update(f=f_mean, p0=p0_mean, Delta=Delta_mean)
-
     if method == "sampling":
-        messages, ndiv = _diagnose(res["sampler_params"][0], res["chain_stats"][0], res["qdraws"][0],
-                                   kw.get("max_treedepth", 10))
+        lp = res["sampler_params"][0][:, :, 6].reshape(-1)
+        surfaces_k, lpml = res["surfaces"][0], res["lpml"][0]
     else:
-        messages, ndiv = [], float("nan")
-    returnCode = 1 if messages else 0
-    # residual check (R/bayesynergy.R:305-314); f_mean is (n2+1) x (n1+1), as.vector is column-major
-    fvec = f_mean.T.reshape(-1)
-    resid = sd.y - fvec[sd.ii_obs - 1]
-    point_sd = np.sqrt(posterior_mean["s"] ** 2 * (fvec[sd.ii_obs - 1] + lambda_))
-    if (np.abs(resid) > 3 * point_sd).any():
-        msg = (f"Largest residuals from posterior median is {resid.max():.4g}, which is more than three times the "
-               "observation noise. This could indicate the presence of an outlier.")
-        warnings.warn(msg)
-        returnCode = 1
-        messages.append(msg)
-
-    obj = dict(posterior=posterior, posterior_mean=posterior_mean,
-               data=dict(y=np.asarray(y), x=np.asarray(x), drug_names=drug_names, experiment_ID=experiment_ID,
-                         units=units, indices=sd.ii_obs),
-               model=dict(type=type, lower_asymptotes=lower_asymptotes, method=method, bayes_factor=bayes_factor,
-                          heteroscedastic=heteroscedastic, robust=robust, pcprior=pcprior, lambda_=lambda_),
-               returnCode=returnCode, LPML=LPML, divergent=float("nan"))
+        lp = np.zeros(res["draws"][0].shape[0] * res["draws"][0].shape[1])      # rstan::vb writes lp__ = 0
+        surfaces_k, lpml = _host_surfaces(sd, res["draws"][0], robust)
+    posterior = _posterior_from_draws(sd, res["draws"][0], lp)
+    obj = _assemble_object(sd, meta, posterior, surfaces_k, lpml,
+                           res["sampler_params"][0] if method == "sampling" else None,
+                           res["chain_stats"][0] if method == "sampling" else None,
+                           res["qdraws"][0] if method == "sampling" else None, options, kw.get("max_treedepth", 10))
     if method == "sampling":
         obj.update(sampler_params=res["sampler_params"][0], chain_stats=res["chain_stats"][0], n_grad=res["n_grad"])
     else:
         obj.update(vb_info=dict(zip(_lib.VI_NAMES, res["info"][0])), vb_mean=res["mean"][0, :len(param_names(sd))],
                    n_grad=res["n_evals"])
-    if type == 3:
-        obj["model"].update(nu=nu, pcprior_hypers=tuple(pcprior_hypers))
-    if returnCode:
-        obj["messages"] = messages
-        obj["divergent"] = ndiv
     if bayes_factor:
         from .bridge import bayes_factor as _bf
         obj["bayesfactor"] = _bf(sd, res["udraws"][0], kw, device=device)
     return obj
+
+
+def _host_surfaces(sd, draws, robust):
+    """Surfaces / LPML of the ADVI output draws (1000 draws of one experiment; the sampler path reduces them on the
+    device): R/bayesynergy.R:244-283."""
+    post = _posterior_from_draws(sd, draws, np.zeros(draws.shape[0] * draws.shape[1]))
+    n_save, n1, n2 = post["p01"].shape[0], sd.n1, sd.n2
+    f = np.empty((n_save, n2 + 1, n1 + 1))
+    f[:, 0, 0] = 1.0
+    f[:, 1:, 0] = post["p02"]
+    f[:, 0, 1:] = post["p01"]
+    f[:, 1:, 1:] = post["p0"] + post["Delta"]
+    p0 = f.copy()
+    p0[:, 1:, 1:] = post["p0"]
+    Delta = np.zeros_like(f)
+    Delta[:, 1:, 1:] = post["Delta"]
+    surf = np.stack([(np.median(f, axis=0) if robust else f.mean(axis=0)).T.reshape(-1),
+                     np.median(p0, axis=0).T.reshape(-1), np.median(Delta, axis=0).T.reshape(-1)])
+    lpml = float(-np.sum(np.log(post["CPO"].sum(axis=0) / n_save)))
+    return surf, lpml
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -261,13 +304,26 @@ def _check_prepare_params(params):
         raise TypeError(f"unknown bayesynergy_params: {unknown}")
 
 
-def _fit_batch(sds, kw, device, max_treedepth):
-    """One batched launch over a list of prepared experiments; returns (res, returnCode[n])."""
+def _fit_batch(sds, kw, device, max_treedepth, want_samples=False, want_udraws=False):
+    """One batched launch over a list of prepared experiments; returns (res, returnCode[n]).
+
+    returnCode follows bayesynergy(): 1 where rstan would have warned (divergences, tree depth, R-hat, bulk / tail ESS)
+    or where the residual rule fires (R/bayesynergy.R:305-314, on the device-accumulated posterior mean surface of f;
+    the reference uses the median surface when robust = TRUE -- here only when the draws are kept anyway), 2 where the
+    chains could not be initialised."""
     b = _lib.Batch(sds, model="gp_grid", device=device)
     try:
-        res = b.sample(want_qdraws=False, want_sampler_params=False, **kw)
-        ess_syn, rhat_syn = b.ess("VUS_syn")
-        ess_ant, rhat_ant = b.ess("VUS_ant")
+        res = b.sample(want_qdraws=want_samples, want_sampler_params=want_samples, want_f_mean=True,
+                       want_draws=want_samples, want_surfaces=want_samples, want_udraws=want_udraws, **kw)
+        n_draws = res["n_save"] * res["chain_stats"].shape[1]
+        if n_draws <= 8192:         # rank-normalised bulk ESS / R-hat and tail ESS, as rstan >= 2.21 warns on
+            ess_syn, rhat_syn, tail_syn = b.bulk_ess("VUS_syn")
+            ess_ant, rhat_ant, tail_ant = b.bulk_ess("VUS_ant")
+            tail = np.fmin(tail_syn, tail_ant)
+        else:
+            ess_syn, rhat_syn = b.ess("VUS_syn")
+            ess_ant, rhat_ant = b.ess("VUS_ant")
+            tail = np.full(len(sds), np.inf)
     finally:
         b.close()
     cs = res["chain_stats"]
@@ -276,12 +332,37 @@ def _fit_batch(sds, kw, device, max_treedepth):
     warn = (cs[:, :, 1].sum(axis=1) > 0) | (cs[:, :, 2].sum(axis=1) > 0)
     rhat = np.fmax(rhat_syn, rhat_ant)
     ess = np.fmin(ess_syn, ess_ant)
-    warn |= (rhat > 1.05) | (ess < 100 * n_chains)
+    warn |= (rhat > 1.05) | (ess < 100 * n_chains) | (tail < 100 * n_chains)
+    s_mean = res["summary"][:, Q.index("s"), 0]
+    for k, sd in enumerate(sds):
+        ncf = (sd.n1 + 1) * (sd.n2 + 1)
+        f_cells = res["surfaces"][k, 0, :ncf] if want_samples else res["f_mean"][k, :ncf]
+        if _outlier_message(sd, f_cells, s_mean[k], sd.lambda_):
+            warn[k] = True
     rc[warn] = 1
     rc[cs[:, :, 6].sum(axis=1) > 0] = 2
     res["ess"] = ess
     res["rhat"] = rhat
     return res, rc
+
+
+def _screen_sample_object(sd, e, res, i, params, kw):
+    """The `fit` object synergyscreen(return_samples = TRUE) keeps per experiment (R/synergyscreen.R:264, 409-419):
+    the same fields bayesynergy() returns, assembled from experiment i of a batched launch."""
+    lp = res["sampler_params"][i][:, :, 6].reshape(-1)
+    posterior = _posterior_from_draws(sd, res["draws"][i], lp)
+    options = dict(type=params.get("type", 3), lower_asymptotes=params.get("lower_asymptotes", True), method="sampling",
+                   bayes_factor=bool(params.get("bayes_factor", False)), heteroscedastic=params.get("heteroscedastic", True),
+                   robust=params.get("robust", False), pcprior=params.get("pcprior", False),
+                   lambda_=params.get("lambda_", 0.005), nu=params.get("nu", 1.5),
+                   pcprior_hypers=params.get("pcprior_hypers", (1, 0.1, 1, 0.2)))
+    meta = dict(y=np.asarray(e["y"]), x=np.asarray(e["x"]), drug_names=e.get("drug_names", ["DrugA", "DrugB"]),
+                experiment_ID=e.get("experiment_ID", "Experiment"), units=e.get("units", ["conc.", "conc."]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")         # the screen reports through returnCode (suppressWarnings in the reference)
+        obj = _assemble_object(sd, meta, posterior, res["surfaces"][i], res["lpml"][i], res["sampler_params"][i],
+                               res["chain_stats"][i], res["qdraws"][i], options, kw.get("max_treedepth", 10))
+    return obj
 
 
 def _fit_batch_vb(sds, vbkw, seed, device):
@@ -323,8 +404,11 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
     if method not in ("sampling", "vb"):
         raise ValueError("Method must be one of {'sampling','vb'}")
     vbkw = dict(params.pop("vb", None) or {})
-    if return_samples:
-        raise NotImplementedError("return_samples=TRUE: call bayesynergy() on the experiments of interest")
+    want_bf = bool(params.get("bayes_factor", False))
+    if want_bf and method != "sampling":
+        raise ValueError("Computing the Bayes factor requires method = 'sampling')")
+    if return_samples and method != "sampling":
+        raise NotImplementedError("return_samples=TRUE with method='vb': call bayesynergy(method='vb') per experiment")
     control = params.pop("control", None)
     chains, iter_, warmup = params.pop("chains", 4), params.pop("iter", 2000), params.pop("warmup", None)
     thin, seed = params.pop("thin", 1), params.pop("seed", 1)
@@ -360,25 +444,56 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
             retry = [j for j in retry if bad(j)]
             tries += 1
     elif sds:
+        # return_samples keeps every write_array draw on the host (as the reference keeps every stanfit): the launches are
+        # then chunked so that a chunk's draws fit comfortably in host memory
+        chunk = max(1, int(2e9 // (8 * chains * max(1, iter_ // 2) * 1024))) if return_samples else len(sds)
+        samples, udraws_gp, kw_of = {}, {}, {}
+
+        def fit(js, kwj):
+            """fit the experiments js (indices into sds) and store their rows / samples"""
+            codes = {}
+            for c0 in range(0, len(js), chunk):
+                part = js[c0:c0 + chunk]
+                res_, rc_ = _fit_batch([sds[j] for j in part], kwj, device, kwj.get("max_treedepth", 10),
+                                       want_samples=return_samples, want_udraws=want_bf)
+                new_rows = _screen_rows([mine[ok_idx[j]] for j in part], 0, res_, rc_)
+                for i, (r, j) in enumerate(zip(new_rows, part)):
+                    r["listID"] = lo + ok_idx[j] + 1
+                    rows[ok_idx[j]] = r
+                    codes[j] = rc_[i]
+                    kw_of[j] = kwj
+                    if want_bf:
+                        udraws_gp[j] = res_["udraws"][i]
+                    if return_samples:
+                        samples[j] = _screen_sample_object(sds[j], mine[ok_idx[j]], res_, i, params, kwj)
+            return codes
+
         ctl = _control_defaults(type_, robust, control)
         kw = _sampler_kwargs(ctl, chains, iter_, warmup, thin, seed)
-        res, rc = _fit_batch(sds, kw, device, kw.get("max_treedepth", 10))
-        for r, k in zip(_screen_rows([mine[k] for k in ok_idx], 0, res, rc), ok_idx):
-            r["listID"] = lo + k + 1
-            rows[k] = r
+        codes = fit(list(range(len(sds))), kw)
         # retry the experiments with warnings at adapt_delta = 0.99 (R/synergyscreen.R:149-171), as ONE smaller launch
-        retry = [j for j in range(len(sds)) if rc[j] != 0]
+        retry = [j for j in range(len(sds)) if codes[j] != 0]
         tries = 0
         while retry and tries <= max_retries:   # the reference's loop body runs max_retries + 1 times (quirk 9)
             ctl2 = dict(ctl, adapt_delta=0.99)
             kw2 = _sampler_kwargs(ctl2, chains, iter_, warmup, thin, seed + 1000 * (tries + 1))
-            res2, rc2 = _fit_batch([sds[j] for j in retry], kw2, device, kw2.get("max_treedepth", 10))
-            new_rows = _screen_rows([mine[ok_idx[j]] for j in retry], 0, res2, rc2)
-            for r, j in zip(new_rows, retry):
-                r["listID"] = lo + ok_idx[j] + 1
-                rows[ok_idx[j]] = r
-            retry = [j for j, c in zip(retry, rc2) if c != 0]
+            codes2 = fit(retry, kw2)
+            retry = [j for j in retry if codes2[j] != 0]
             tries += 1
+        if want_bf:
+            # cfg4: "two models per combination" -- one nointeraction launch over every fitted experiment and one batched
+            # log_prob launch per model for all bridge points (bridge.bayes_factor_many)
+            from .bridge import bayes_factor_many
+            good = [j for j in range(len(sds)) if rows[ok_idx[j]]["returnCode"] != 2]
+            for kwj in {id(kw_of[j]): kw_of[j] for j in good}.values():
+                js = [j for j in good if kw_of[j] is kwj]
+                bfs = bayes_factor_many([sds[j] for j in js], [udraws_gp[j] for j in js], kwj, device=device, seed=seed)
+                for j, v in zip(js, bfs):
+                    rows[ok_idx[j]]["Bayes Factor"] = float(v)
+                    if return_samples and j in samples:
+                        samples[j]["bayesfactor"] = float(v)
+            for r in rows.values():
+                r.setdefault("Bayes Factor", float("nan"))
     summary = [rows[k] for k in sorted(rows)]
     # s > 1 => returnCode 2; drop code-2 rows; collect failed (R/synergyscreen.R:424-451)
     for r in summary:
@@ -387,6 +502,8 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
     kept = [r for r in summary if r["returnCode"] != 2]
     failed_ids = sorted(set(rows_failed) | {r["listID"] - lo - 1 for r in summary if r["returnCode"] == 2})
     out = dict(screenSummary=kept)
+    if return_samples and method == "sampling":
+        out["screenSamples"] = [samples[j] for j in sorted(samples) if rows[ok_idx[j]]["returnCode"] != 2]
     if failed_ids:
         out["failed"] = [mine[k] for k in failed_ids]
         out["failed_reason"] = {lo + k + 1: fail_reason.get(k, "returnCode 2") for k in failed_ids}

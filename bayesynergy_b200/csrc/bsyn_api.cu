@@ -610,9 +610,9 @@ static int ensure(double **p, size_t *have, size_t need)
 }
 
 struct DevSinks {
-    double *draws = nullptr, *udraws = nullptr, *cpo = nullptr, *inv_metric = nullptr, *init_u = nullptr;
+    double *draws = nullptr, *udraws = nullptr, *cpo = nullptr, *inv_metric = nullptr, *init_u = nullptr, *f_acc = nullptr;
     long long ld_draws = 0, ld_u = 0;
-    int ld_cpo = 0, ld_im = 0;
+    int ld_cpo = 0, ld_im = 0, ld_f = 0;
 };
 
 static int check_sampler_args(const bsyn_sampler_args *a)
@@ -660,6 +660,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     sp.qdraws = b->d_qdraws; sp.sp = b->d_sp; sp.chain_stats = b->d_chain_stats;
     sp.draws = ds.draws; sp.ld_draws = ds.ld_draws; sp.udraws = ds.udraws; sp.ld_u = ds.ld_u;
     sp.cpo_acc = ds.cpo; sp.ld_cpo = ds.ld_cpo; sp.inv_metric = ds.inv_metric; sp.ld_im = ds.ld_im; sp.init_u = ds.init_u;
+    sp.f_acc = ds.f_acc; sp.ld_f = ds.ld_f;
     // warps per CTA: the largest compiled variant (12, 6, 4, 1) whose shared memory fits on an SM.  A batch that
     // matches a compile-time specialisation (diag_e only) uses it: 12 or 16 warps per SM, with or without the tick barrier
     // (BSYN_NUTS_NW / BSYN_NUTS_TICK override the defaults for A/B measurements).
@@ -762,9 +763,14 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
     const size_t nch = (size_t)b->n * args->chains;
     DevSinks ds;
     int rc = BSYN_OK;
-    if (sinks->draws) {
-        if (sinks->ld_draws < b->maxOut) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_draws < bsyn_max_outputs");
-        ds.ld_draws = sinks->ld_draws;
+    int max_ncf = 0;
+    for (const ProbDesc &d : b->descs) max_ncf = std::max(max_ncf, d.ncf);
+    if ((sinks->f_mean || sinks->surfaces) && sinks->ld_f < max_ncf) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_f < (n1+1)(n2+1)");
+    if ((sinks->surfaces || sinks->lpml) && (long long)ns_samp * args->chains > BULK_MAX_DRAWS)
+        return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample: surfaces / lpml need <= 8192 pooled sampling draws per problem");
+    if (sinks->draws || sinks->surfaces || sinks->lpml) {
+        if (sinks->draws && sinks->ld_draws < b->maxOut) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_draws < bsyn_max_outputs");
+        ds.ld_draws = sinks->draws ? sinks->ld_draws : b->maxOut;
         if (cudaMalloc(&ds.draws, sizeof(double) * nrows * ds.ld_draws) != cudaSuccess) return fail(BSYN_ERR_ALLOC, "draws buffer does not fit on the device; use the summary sinks");
         cudaMemsetAsync(ds.draws, 0, sizeof(double) * nrows * ds.ld_draws, b->stream);
     }
@@ -785,6 +791,11 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
         if (cudaMalloc(&ds.inv_metric, sizeof(double) * nch * ds.ld_im) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); return fail(BSYN_ERR_ALLOC, "inv_metric buffer"); }
         cudaMemsetAsync(ds.inv_metric, 0, sizeof(double) * nch * ds.ld_im, b->stream);
     }
+    if (sinks->f_mean) {
+        ds.ld_f = max_ncf;
+        if (cudaMalloc(&ds.f_acc, sizeof(double) * nch * max_ncf) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); return fail(BSYN_ERR_ALLOC, "f_mean buffer"); }
+        cudaMemsetAsync(ds.f_acc, 0, sizeof(double) * nch * max_ncf, b->stream);
+    }
     if (sinks->init_u) {
         ds.ld_im = b->maxD;
         if (cudaMalloc(&ds.init_u, sizeof(double) * nch * b->maxD) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); return fail(BSYN_ERR_ALLOC, "init_u buffer"); }
@@ -803,6 +814,39 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
         if (e == cudaSuccess && sinks->inv_metric) e = cudaMemcpy(sinks->inv_metric, ds.inv_metric, sizeof(double) * nch * ds.ld_im, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && sinks->init_u) e = cudaMemcpy(sinks->init_u, ds.init_u, sizeof(double) * nch * b->maxD, cudaMemcpyDeviceToHost);
         if (sinks->elapsed_ms) *sinks->elapsed_ms = ms_total;
+        if (e == cudaSuccess && sinks->f_mean) {   // mean over chains and sampling draws of f per grid cell
+            std::vector<double> tmp(nch * (size_t)max_ncf);
+            e = cudaMemcpy(tmp.data(), ds.f_acc, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess)
+                for (int k = 0; k < b->n; ++k)
+                    for (int c = 0; c < b->descs[k].ncf; ++c) {
+                        double sacc = 0;
+                        for (int ch = 0; ch < args->chains; ++ch) sacc += tmp[((size_t)k * args->chains + ch) * max_ncf + c];
+                        sinks->f_mean[(size_t)k * sinks->ld_f + c] = sacc / ((double)args->chains * ns_samp);
+                    }
+        }
+        if (e == cudaSuccess && (sinks->surfaces || sinks->lpml)) {
+            // posterior surfaces (mean / median per grid cell) and LPML reduced on the device from the resident draws
+            DevBuf<double> d_surf, d_lpml;
+            const size_t ldf = sinks->surfaces ? (size_t)sinks->ld_f : (size_t)max_ncf;
+            if (d_surf.alloc((size_t)b->n * 3 * ldf) != cudaSuccess || d_lpml.alloc(b->n) != cudaSuccess) e = cudaErrorMemoryAllocation;
+            if (e == cudaSuccess) {
+                int S2 = 1;
+                while (S2 < ns_samp * args->chains) S2 <<= 1;
+                const size_t sb = sizeof(double) * ((size_t)S2 + 16);
+                e = cudaFuncSetAttribute(surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+                if (e == cudaSuccess) {
+                    surface_kernel<<<std::max(1, std::min(b->n, b->num_sms * 2)), BULK_THREADS, sb, b->stream>>>(
+                        ds.draws, ds.ld_draws, b->d_descs, b->n, args->chains, (int)n_save, ns_warm, ns_samp, b->F.model == 0, b->F.robust,
+                        d_surf, (int)ldf, d_lpml);
+                    ++g_launches;
+                    e = cudaGetLastError();
+                }
+                if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+                if (e == cudaSuccess && sinks->surfaces) e = cudaMemcpy(sinks->surfaces, d_surf, sizeof(double) * (size_t)b->n * 3 * ldf, cudaMemcpyDeviceToHost);
+                if (e == cudaSuccess && sinks->lpml) e = cudaMemcpy(sinks->lpml, d_lpml, sizeof(double) * b->n, cudaMemcpyDeviceToHost);
+            }
+        }
         if (e == cudaSuccess && sinks->cpo_mean) {
             // mean over chains and sampling draws of CPO_n
             std::vector<double> tmp(nch * std::max(1, ds.ld_cpo));
@@ -820,7 +864,7 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
         }
         if (e != cudaSuccess) rc = fail(BSYN_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
     }
-    cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); cudaFree(ds.init_u);
+    cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); cudaFree(ds.init_u); cudaFree(ds.f_acc);
     return rc;
 }
 

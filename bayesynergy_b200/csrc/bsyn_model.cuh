@@ -402,10 +402,12 @@ struct GQ {
 };
 // The sinks live in a small shared-memory block written by the caller (gq_publish) instead of in the struct: as
 // struct members they would occupy ~25 registers through every evaluation, 99 % of which have gq.on == false.
-enum GqSlot { GQS_ROW = 0, GQS_QOUT, GQS_CPO, GQS_Y, GQS_II, GQS_UZ = 5 /* 4 doubles */, GQS_D = 9, GQ_DOUBLES = 10 };
+enum GqSlot { GQS_ROW = 0, GQS_QOUT, GQS_CPO, GQS_Y, GQS_II, GQS_UZ = 5 /* 4 doubles */, GQS_D = 9, GQS_FACC = 10, GQ_DOUBLES = 12 };
 __device__ __forceinline__ void gq_publish(const int so, const int D, const double *yglob, const int *iiglob,
-                                           const double (&uz)[4], double *row, double *qout, double *cpo_acc)
+                                           const double (&uz)[4], double *row, double *qout, double *cpo_acc,
+                                           double *f_acc = nullptr)
 {
+    smem[so + GQS_FACC] = __longlong_as_double((long long)f_acc);
     // every lane stores the same values to the same addresses
     smem[so + GQS_ROW] = __longlong_as_double((long long)row);
     smem[so + GQS_QOUT] = __longlong_as_double((long long)qout);
@@ -612,6 +614,11 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         const int *const iiglob = gq_ptr<const int>(gq, GQS_II);
         const int o_delta = gq_D(gq) + G + nm, o_ec = gp ? o_delta + 2 * G : o_delta, o_cpo = o_ec + 2;
         const int o_dss = o_cpo + P.N, o_vus = o_dss + 2;
+        // per-chain accumulator of the response surface f on its (n2+1) x (n1+1) grid -> posterior mean of f per cell
+        if (double *const f_acc = gq_ptr<double>(gq, GQS_FACC)) {
+            const int ncf = (n1 + 1) * (n2 + 1);
+            for (int e = lane; e < ncf; e += 32) f_acc[e] += fg[e];
+        }
         const double vr = warp_sum8(vus);                       // lane L holds the total of vus[L & 7]
         double v_f = __shfl_sync(FULL, vr, 0), v_p0 = __shfl_sync(FULL, vr, 1), v_d = __shfl_sync(FULL, vr, 2);
         double v_syn = __shfl_sync(FULL, vr, 3), v_ant = __shfl_sync(FULL, vr, 4);

@@ -26,7 +26,7 @@ struct SmemLayout {
 };
 // per-warp chain-state block: the warp-uniform chain state (struct ChainSt, <= PARK_GQ doubles) lives here for the
 // whole life of a chain, followed by the generated-quantities sink block (GQ_DOUBLES) the evaluation reads when gq.on
-constexpr int PARK_GQ = 52, PARK_DOUBLES = 62;
+constexpr int PARK_GQ = 52, PARK_DOUBLES = 64;
 
 struct SamplerParams {
     int n_problems, chains;
@@ -44,6 +44,7 @@ struct SamplerParams {
     double *inv_metric; int ld_im;
     double *init_u;                  // [n_problems][chains][ld_im]: the initial point of every chain (unconstrained)
     double *cpo_acc; int ld_cpo;     // [n_problems][chains][ld_cpo]
+    double *f_acc; int ld_f;         // [n_problems][chains][ld_f]: sum over the saved sampling draws of f per grid cell
     // dense_e metric (metric == 1): per resident warp  M^-1 (float, column-major DI x DI),  its Cholesky factor
     // (double, column-major lower) and the Welford cross-product accumulator (double)
     int metric;
@@ -545,7 +546,8 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 rng_u2(rk, RT_GQ, 0xFFu, it, 0, uz[0], uz[1]);
                 rng_u2(rk, RT_GQ, 0xFFu, it, 1, uz[2], uz[3]);
                 gq_publish(gq.so, pd.D, yglob, iiglob, uz, sp.draws ? sp.draws + rowi * sp.ld_draws : nullptr,
-                           sp.qdraws ? sp.qdraws + rowi * 12 : nullptr, (it >= nw) ? cpo_acc : nullptr);
+                           sp.qdraws ? sp.qdraws + rowi * 12 : nullptr, (it >= nw) ? cpo_acc : nullptr,
+                           (sp.f_acc && it >= nw) ? sp.f_acc + cg * sp.ld_f : nullptr);
             }
             // The evaluation needs every register it can get; S, pprev and p are dead weight across it: they are parked
             // in shared memory (or, when it has no room, in the arena: L2-resident, coalesced).  M^-1 only changes at a
@@ -916,7 +918,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                     o[5] = info.energy; o[6] = -V;
                 }
             }
-            if (save && (sp.draws || sp.qdraws || (cpo_acc && !warm))) {
+            if (save && (sp.draws || sp.qdraws || ((cpo_acc || sp.f_acc) && !warm))) {
                 // one evaluation tick at the saved draw with the generated-quantities sink switched on
 #pragma unroll
                 for (int t = 0; t < CPL; ++t) p.z[t] = 0.0;

@@ -291,3 +291,94 @@ inline size_t bulk_ess_smem_bytes(int S)
 }
 
 }  // namespace bsyn
+
+namespace bsyn {
+
+// ---------------------------------------------------------------------------------------------------
+// Posterior surfaces and LPML from the full write_array draws (what bayesynergy() computes after rstan::extract,
+// R/bayesynergy.R:244-291): per cell of the (n2+1) x (n1+1) dose grid
+//   f     = mean over the draws (median when `robust`) of the response surface  [1 at (0,0), p02 / p01 on the edges,
+//           p0 + Delta inside]
+//   p0    = median of the non-interaction surface, Delta = median of the interaction surface (0 on the edges)
+// and LPML = -sum_n log(mean over draws of CPO_n).  One CTA per problem; every median is a shared-memory bitonic sort of
+// the chains x ns values of one cell (R's median: the mean of the two middle order statistics for an even count).
+// draws[(k*chains + c)*ld_save + i][ld_draws]; out[k][3][ld_f] column-major cells fc = b + a*(n2+1); lpml[k].
+__device__ __forceinline__ void block_bitonic_sort(double *key, const int S2)
+{
+    for (int kk = 2; kk <= S2; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int e = threadIdx.x; e < S2; e += BULK_THREADS) {
+                const int p = e ^ j;
+                if (p > e) {
+                    const bool up = (e & kk) == 0;
+                    const double a = key[e], b = key[p];
+                    if (up ? (a > b) : (a < b)) { key[e] = b; key[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(BULK_THREADS) surface_kernel(const double *__restrict__ draws, const long long ld_draws,
+                                                                const ProbDesc *__restrict__ descs, const int n_problems,
+                                                                const int chains, const int ld_save, const int n_skip,
+                                                                const int ns, const int gp, const int robust,
+                                                                double *__restrict__ out, const int ld_f,
+                                                                double *__restrict__ lpml)
+{
+    extern __shared__ double bsm[];
+    const int S = chains * ns;
+    int S2 = 1;
+    while (S2 < S) S2 <<= 1;
+    double *key = bsm, *red = bsm + S2;
+    for (int k = blockIdx.x; k < n_problems; k += gridDim.x) {
+        const ProbDesc pd = descs[k];
+        const int n1 = pd.n1, n2 = pd.n2, G = pd.G, D = pd.D, nm = n1 + n2;
+        const int o_p0 = D, o_pm = D + G, o_delta = D + G + nm, o_cpo = (gp ? o_delta + 2 * G : o_delta) + 2;
+        const double *base = draws + (size_t)k * chains * ld_save * ld_draws;
+        auto rowp = [&](int e) { const int c = e / ns, i = e - c * ns; return base + ((size_t)c * ld_save + n_skip + i) * ld_draws; };
+        for (int fc = 0; fc < pd.ncf; ++fc) {
+            const int a = fc / (n2 + 1), bb = fc - a * (n2 + 1);      // a: drug-1 level (column), bb: drug-2 level (row)
+            const bool inner = a > 0 && bb > 0;
+            const int cell = inner ? (bb - 1) + (a - 1) * n2 : 0;
+            for (int sfc = 0; sfc < 3; ++sfc) {
+                double *dst = out + ((size_t)k * 3 + sfc) * ld_f + fc;
+                if (sfc == 2 && (!inner || !gp)) { if (threadIdx.x == 0) *dst = 0.0; continue; }
+                if (fc == 0 && sfc < 2) { if (threadIdx.x == 0) *dst = 1.0; continue; }
+                __syncthreads();
+                double sum = 0.0;
+                for (int e = threadIdx.x; e < S2; e += BULK_THREADS) {
+                    double v = INFINITY;
+                    if (e < S) {
+                        const double *r = rowp(e);
+                        if (!inner) v = (a > 0) ? r[o_pm + a - 1] : r[o_pm + n1 + bb - 1];
+                        else if (sfc == 0) v = r[o_p0 + cell] + (gp ? r[o_delta + cell] : 0.0);
+                        else if (sfc == 1) v = r[o_p0 + cell];
+                        else v = r[o_delta + cell];
+                        sum += v;
+                    }
+                    key[e] = v;
+                }
+                if (sfc == 0 && !robust) {
+                    const double tot = block_sum(sum, red);
+                    if (threadIdx.x == 0) *dst = tot / S;
+                    continue;
+                }
+                __syncthreads();
+                block_bitonic_sort(key, S2);
+                if (threadIdx.x == 0) *dst = (S & 1) ? key[S / 2] : 0.5 * (key[S / 2 - 1] + key[S / 2]);
+            }
+        }
+        // LPML
+        double acc = 0.0;
+        for (int n = 0; n < pd.N; ++n) {
+            double s = 0.0;
+            for (int e = threadIdx.x; e < S; e += BULK_THREADS) s += rowp(e)[o_cpo + n];
+            const double tot = block_sum(s, red);
+            acc += log(tot / S);
+        }
+        if (threadIdx.x == 0) lpml[k] = -acc;
+    }
+}
+
+}  // namespace bsyn

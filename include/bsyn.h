@@ -184,6 +184,17 @@ typedef struct bsyn_sample_sinks {
     /* the initial point of every chain on the unconstrained scale [n_problems][chains][bsyn_max_params()] (what rstan
      * reports, constrained, as attr "inits"; constrain it with bsyn_write_array) */
     double *init_u;
+    /* posterior mean of the response surface f per cell of the column-major (n2+1) x (n1+1) dose grid, accumulated on
+     * the device per chain (no draws kept): [n_problems][ld_f].  What the outlier rule of bayesynergy() needs
+     * (R/bayesynergy.R:305-314) and, for non-robust fits, posterior_mean$f (R/bayesynergy.R:251-262). */
+    double *f_mean;
+    int64_t ld_f;            /* >= (n1+1)(n2+1) of every problem; stride of f_mean and surfaces */
+    /* posterior surfaces reduced on the device from the write_array draws (the draws stay in HBM unless `draws` is
+     * also requested): [n_problems][3][ld_f] = f (mean; median when robust), p0 (median), Delta (median), exactly
+     * R/bayesynergy.R:251-283 (R's median); and LPML = -sum_n log(mean CPO_n) (R/bayesynergy.R:246): [n_problems].
+     * Up to 8192 pooled sampling draws per problem. */
+    double *surfaces;
+    double *lpml;
     /* device time of the sampling launch in ms (attr "elapsed_time" is this, split by the leapfrog counts of chain_stats) */
     float *elapsed_ms;
 } bsyn_sample_sinks;

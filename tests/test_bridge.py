@@ -97,3 +97,103 @@ def test_bulk_ess_rank_normalised():
     eb, _ = bulk_ess_rhat(y)
     ec, _ = split_ess_rhat(y)
     assert abs(eb - ec) < 0.15 * ec and 500 < ec < 1400      # theory: 8000 (1 - phi) / (1 + phi) = 889
+
+
+@pytest.mark.gpu
+def test_device_surfaces_and_lpml_match_host(built, datasets):
+    """posterior_mean$f / p0 / Delta and LPML (R/bayesynergy.R:244-283) are reduced on the device from the resident
+    draws (bsyn_sample's `surfaces` / `lpml` sinks): compare with numpy mean / median on the returned draws, for the
+    mean (non-robust) and the median (robust) response surface."""
+    from bayesynergy_b200.api import bayesynergy
+    y, x = datasets["mathews:ispinesib + ibrutinib"]
+    for robust in (False, True):
+        fit = bayesynergy(y, x, iter=600, seed=3, robust=robust)
+        po, pm = fit["posterior"], fit["posterior_mean"]
+        n_save = po["lp__"].shape[0]
+        f = np.empty((n_save, 6, 6))
+        f[:, 0, 0] = 1.0
+        f[:, 1:, 0] = po["p02"]
+        f[:, 0, 1:] = po["p01"]
+        f[:, 1:, 1:] = po["p0"] + po["Delta"]
+        p0 = f.copy()
+        p0[:, 1:, 1:] = po["p0"]
+        Delta = np.zeros_like(f)
+        Delta[:, 1:, 1:] = po["Delta"]
+        f_ref = np.median(f, axis=0) if robust else f.mean(axis=0)
+        assert np.allclose(pm["f"], f_ref, rtol=1e-12, atol=1e-14), robust
+        assert np.allclose(pm["p0"], np.median(p0, axis=0), rtol=1e-12, atol=1e-14)
+        assert np.allclose(pm["Delta"], np.median(Delta, axis=0), rtol=1e-12, atol=1e-14)
+        lpml = -np.sum(np.log(po["CPO"].sum(axis=0) / n_save))
+        assert abs(fit["LPML"] - lpml) < 1e-9 * abs(lpml)
+
+
+@pytest.mark.gpu
+def test_screen_bayes_factor_and_samples(built):
+    """cfg4: synergyscreen(bayes_factor = TRUE) -- one gp_grid launch, one nointeraction launch, one batched log_prob
+    launch per model for all bridge points -- and return_samples = TRUE.  The Bayes factors are checked against the
+    bridge estimator fed by the ORACLE's log_prob on the same draws of 8 combinations."""
+    import warnings
+    from bayesynergy_b200 import _lib
+    from bayesynergy_b200.api import synergyscreen, SCREEN_COLUMNS
+    from bayesynergy_b200.bridge import bridge_logml_many
+    from bayesynergy_b200.dataprep import prepare, synthetic_experiment
+    from oracle.c_oracle import Problem
+    n = 8
+    exps = []
+    for k in range(n):
+        yy, xx = synthetic_experiment(300 + k)
+        exps.append(dict(y=yy, x=xx, drug_names=[f"A{k}", f"B{k}"], experiment_ID="syn"))
+    launches0 = _lib.load().bsyn_launch_count()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = synergyscreen(exps, return_samples=True, max_retries=0,
+                            bayesynergy_params=dict(bayes_factor=True, iter=600, chains=4, seed=2))
+    launches = _lib.load().bsyn_launch_count() - launches0
+    rows = out["screenSummary"]
+    assert len(rows) + len(out.get("failed", [])) == n and len(rows) >= n - 1
+    assert list(rows[0].keys()) == SCREEN_COLUMNS + ["Bayes Factor"]
+    bfs = np.array([r["Bayes Factor"] for r in rows])
+    assert np.isfinite(bfs).all() and (bfs > 0).all()
+    # batched: the launch count does not grow with the number of experiments (2 sampler launches + summaries / ESS +
+    # 2 log_prob launches), far below one launch per experiment and model
+    assert launches <= 16, launches
+    samples = out["screenSamples"]
+    assert len(samples) == len(rows)
+    s0 = samples[0]
+    assert s0["posterior"]["Delta"].shape == (1200, 10, 10) and s0["posterior_mean"]["f"].shape == (11, 11)
+    assert abs(s0["posterior_mean"]["VUS_syn"] - rows[0]["Synergy (mean)"]) < 1e-9
+    assert np.isfinite(s0["LPML"]) and s0["bayesfactor"] == rows[0]["Bayes Factor"]
+    # the same estimator with the oracle's log_prob on freshly sampled draws of every experiment
+    sds = [prepare(e["y"], e["x"]) for e in exps]
+
+    class _OracleBatch:
+        def __init__(self, model):
+            self.P = [Problem(sd, model) for sd in sds]
+            self.max_params = max(p.dim for p in self.P)
+
+        def num_params(self, k=0):
+            return self.P[k].dim
+
+        def logp_grad(self, u, prob_idx=None, jacobian=True, want_grad=True):
+            u = np.asarray(u)
+            lp, st = np.empty(len(u)), np.empty(len(u), dtype=np.int32)
+            for k in np.unique(prob_idx):
+                m = prob_idx == k
+                s_, l_, _ = self.P[k].logp_grad_batch(np.ascontiguousarray(u[m][:, :self.P[k].dim]), jacobian=jacobian)
+                lp[m], st[m] = l_, s_
+            return lp, None, st
+
+    lml = {}
+    for model in ("gp_grid", "nointeraction"):
+        b = _lib.Batch(sds, model=model)
+        res = b.sample(chains=4, iter=600, warmup=300, seed=2, want_udraws=True, want_qdraws=False, want_sampler_params=False)
+        ud = [res["udraws"][k] for k in range(n)]
+        dev, _ = bridge_logml_many(b, ud, seed=4)
+        orc, _ = bridge_logml_many(_OracleBatch(model), ud, seed=4)
+        b.close()
+        assert np.allclose(dev, orc, rtol=1e-7, atol=1e-6), (model, dev, orc)
+        lml[model] = dev
+    # the screen's Bayes factors agree in log scale with this independent run (different draws: Monte Carlo error)
+    ids = [r["listID"] - 1 for r in rows]
+    ref = (lml["gp_grid"] - lml["nointeraction"])[ids]
+    assert np.abs(np.log(bfs) - ref).max() < 1.5, (np.log(bfs), ref)
