@@ -156,6 +156,19 @@ template <int CPL> static bool fits(int n1, int n2)
 }
 
 static const VariantOps *variant(int cpl);
+const VariantOps *bsyn_variant_default_1();
+const VariantOps *bsyn_variant_default_2();
+const VariantOps *bsyn_variant_default_4();
+const VariantOps *bsyn_variant_default_8();
+const VariantOps *bsyn_variant_default(int cpl)
+{
+    switch (cpl) {
+        case 1: return bsyn_variant_default_1();
+        case 2: return bsyn_variant_default_2();
+        case 4: return bsyn_variant_default_4();
+        default: return bsyn_variant_default_8();
+    }
+}
 
 // shared memory layouts.  per_warp_problem: every warp has its own problem block (logp / write_array
 // kernels); otherwise one block per CTA (sampler).
@@ -235,9 +248,10 @@ extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const 
         for (int k = 0; k < n; ++k) all10 = all10 && problems[k].n1 == 10 && problems[k].n2 == 10;
         const bool def_lik = F.het == 1 && F.robust == 0 && F.est_la == 1;
         const char *nf = getenv("BSYN_NO_FAST");
-        if (all10 && def_lik && !(nf && atoi(nf))) {
-            if (F.model == 0 && F.kernel == 2 && F.nu_matern == 2 && F.pcprior == 0 && F.est_alpha == 0) b->fast = bsyn_variant_gp10();
-            if (F.model == 1) b->fast = bsyn_variant_h0_10();
+        const bool def_gp = F.model == 0 && F.kernel == 2 && F.nu_matern == 2 && F.pcprior == 0 && F.est_alpha == 0;
+        if (def_lik && !(nf && atoi(nf))) {
+            if (def_gp) b->fast = all10 ? bsyn_variant_gp10() : bsyn_variant_default(cpl);
+            if (F.model == 1 && all10) b->fast = bsyn_variant_h0_10();
         }
     }
     std::vector<double> dpool;

@@ -169,9 +169,11 @@ template <int CPL, class SP = SpecRT> struct VariantImpl {
         if constexpr (SP::fixed) {
             if (metric == 1) return cudaErrorInvalidValue;
             if (nw == 12 && tick) { BSYN_NUTS_CASE(12, 168, false, true); }
-            if (nw == 12 && !tick) { BSYN_NUTS_CASE(12, 168, false, false); }
-            if (nw == 14 && tick) { BSYN_NUTS_CASE(14, 144, false, true); }
-            if (nw == 16 && tick) { BSYN_NUTS_CASE(16, 128, false, true); }
+            if constexpr (SP::NF > 0) {   // the A/B variants are only built for the fixed-grid specialisation
+                if (nw == 12 && !tick) { BSYN_NUTS_CASE(12, 168, false, false); }
+                if (nw == 14 && tick) { BSYN_NUTS_CASE(14, 144, false, true); }
+                if (nw == 16 && tick) { BSYN_NUTS_CASE(16, 128, false, true); }
+            }
             return cudaErrorInvalidValue;
         } else {
             if (!tick) return cudaErrorInvalidValue;

@@ -30,5 +30,8 @@ const bsyn::VariantOps *bsyn_variant_4();
 const bsyn::VariantOps *bsyn_variant_8();
 // compile-time specialisations (bsyn_common.cuh: SpecCT): the package-default options on a fixed 10 x 10 dose grid
 // (cfg5, the bench workload) for the gp_grid model and for its H0, the nointeraction model
+// the package-default options (gp_grid, Matern 3/2, heteroscedastic Normal likelihood, lower asymptotes, default priors)
+// with runtime grid sizes, one per cells-per-lane class (bsyn_d.cu)
+const bsyn::VariantOps *bsyn_variant_default(int cpl);
 const bsyn::VariantOps *bsyn_variant_gp10();
 const bsyn::VariantOps *bsyn_variant_h0_10();

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             for (int t = 0; t < CPL; ++t) y.z[t] = 0.0;
             y.s = 0.0;
             const int nz = (O.model() == 0) ? P.G : 0;
-#pragma unroll 4
+#pragma unroll 8
             for (int gg = 0; gg < nz; ++gg) {
                 const double xg = pv[gg];
                 const float *col = Mf + (size_t)gg * DI + lane;

@@ -10,6 +10,7 @@ class _AnalyticBatch:
     """log p~(u) = c - 1/2 (u-m)' P (u-m): log marginal likelihood = c + D/2 log(2 pi) - 1/2 log det P."""
 
     def __init__(self, D, c, seed=0):
+        self.max_params = D
         rng = np.random.default_rng(seed)
         A = rng.normal(size=(D, D))
         self.P = A @ A.T + D * np.eye(D)
@@ -54,6 +55,7 @@ def test_bridge_gpu_matches_oracle(built, datasets):
 
         class _OracleBatch:
             P = Problem(sd, model)
+            max_params = P.dim
 
             def num_params(self, k=0):
                 return self.P.dim
