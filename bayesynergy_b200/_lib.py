@@ -400,8 +400,8 @@ class Batch:
         (bsyn_sample_to_ess): warm-up + `block` draws per chain, then extension launches of `block` draws over the
         experiments still below the target.  kw: sampler arguments (chains, warmup, seed, adapt_delta ...)."""
         kw = dict(kw)
-        kw["iter"] = kw.get("warmup", 1000) + block
         kw.setdefault("warmup", 1000)
+        kw["iter"] = kw["warmup"] + block
         a = self.sampler_args(**kw)
         n, ch, ld = self.n, a.chains, block * max_rounds
         s = BsynSinks()

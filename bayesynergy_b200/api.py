@@ -513,6 +513,51 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
     return out
 
 
+def screen_to_ess(sds, target=400.0, batch=None, device=0, chains=4, warmup=1000, block=150, max_rounds=6, seed=1,
+                  adapt_delta=0.9, retry_adapt_delta=0.99, retry_block=300, retry_rounds=6, want_summary=True):
+    """north_star's target run: sample every prepared experiment until min(bulk-ESS(VUS_syn), bulk-ESS(VUS_ant)) >=
+    `target` (rank-normalised, on the device).
+
+    Phase 1 (bsyn_sample_to_ess): warm-up + `block` draws per chain for everything, then extension launches over the
+    experiments still below the target -- chains resume from their adapted state -- up to `max_rounds` launches.
+    Phase 2, the reference's remedy for what is left (R/synergyscreen.R:149-171: refit with adapt_delta = 0.99): the few
+    experiments still below the target (divergent / funnel-shaped posteriors) are refitted from scratch in one small
+    batch with `retry_adapt_delta` and extended the same way.
+    `batch`: an existing _lib.Batch of `sds` (kept open); else one is created and closed here.
+    Returns dict(ess, draws_per_chain, summary, chain_stats, n_grad, kernel_ms, rounds, n_retry, reached)."""
+    own = batch is None
+    b = _lib.Batch(sds, device=device) if own else batch
+    try:
+        r = b.sample_to_ess(target=target, block=block, max_rounds=max_rounds, chains=chains, warmup=warmup, seed=seed,
+                            adapt_delta=adapt_delta, want_summary=want_summary)
+    finally:
+        if own:
+            b.close()
+    ess, nd = r["ess"].copy(), r["draws_per_chain"].copy()
+    out = dict(ess=ess, draws_per_chain=nd, n_grad=r["n_grad"], kernel_ms=r["kernel_ms"], rounds=r["rounds"], n_retry=0,
+               summary=r.get("summary"), chain_stats=r.get("chain_stats"))
+    left = np.where(~(ess >= target))[0]
+    if len(left) and retry_rounds > 0:
+        b2 = _lib.Batch([sds[k] for k in left], device=device)
+        try:
+            r2 = b2.sample_to_ess(target=target, block=retry_block, max_rounds=retry_rounds, chains=chains, warmup=warmup,
+                                  seed=seed + 7777, adapt_delta=retry_adapt_delta, want_summary=want_summary)
+        finally:
+            b2.close()
+        better = np.nan_to_num(r2["ess"], nan=-1.0) > np.nan_to_num(ess[left], nan=-1.0)
+        for i, k in enumerate(left):
+            if better[i]:
+                ess[k], nd[k] = r2["ess"][i], r2["draws_per_chain"][i]
+                if want_summary:
+                    out["summary"][k], out["chain_stats"][k] = r2["summary"][i], r2["chain_stats"][i]
+        out["n_grad"] += r2["n_grad"]
+        out["kernel_ms"] += r2["kernel_ms"]
+        out["rounds"] += r2["rounds"]
+        out["n_retry"] = int(len(left))
+    out["reached"] = int((ess >= target).sum())
+    return out
+
+
 def gather_screen(local, world_size):
     """The path's only collective: gather every rank's screenSummary rows (torch.distributed, any backend)."""
     if world_size == 1:

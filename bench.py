@@ -196,6 +196,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     from bayesynergy_b200 import _lib
+    from bayesynergy_b200.api import screen_to_ess
     L = _lib.load()
     it, wu = iters(args)
     t_setup = time.time()
@@ -217,8 +218,8 @@ def run_ours(args):
     def one_step(seed, n_it, n_wu):
         """One pass of the hot path over the resident batch; returns (grad evals, device ms, extra info)."""
         if target:
-            r = b.sample_to_ess(target=ESS_TARGET, chains=args.chains, warmup=n_wu, block=n_it - n_wu, seed=seed,
-                                max_rounds=args.max_rounds)
+            r = screen_to_ess(sds, target=ESS_TARGET, batch=b, device=dev, chains=args.chains, warmup=n_wu, block=n_it - n_wu,
+                              seed=seed, max_rounds=args.max_rounds, want_summary=False)
             return r["n_grad"], r["kernel_ms"], r
         ng, ms = b.sample_device(chains=args.chains, iter=n_it, warmup=n_wu, seed=seed)
         return ng, ms, None
@@ -255,8 +256,8 @@ def run_ours(args):
         t = time.time()
         bb = _lib.Batch(sds, device=dev)
         if target:
-            res = bb.sample_to_ess(target=ESS_TARGET, chains=args.chains, warmup=wu, block=it - wu, seed=2000 + s,
-                                   max_rounds=args.max_rounds, want_summary=True)
+            res = screen_to_ess(sds, target=ESS_TARGET, batch=bb, device=dev, chains=args.chains, warmup=wu, block=it - wu,
+                                seed=2000 + s, max_rounds=args.max_rounds, want_summary=True)
         else:
             res = bb.sample(chains=args.chains, iter=it, warmup=wu, seed=2000 + s, want_qdraws=False, want_sampler_params=False)
         bb.close()
@@ -300,6 +301,8 @@ def run_ours(args):
             "ess_ge_400_frac": float(sm[8] / n_combo_total),
             "time_to_ess400_all_s": float(step_time) if int(sm[8]) == n_combo_total else None,
             "sampler_launch_rounds_last_step": int(mx[9]),
+            "target_mode": ({"phase1_max_rounds": args.max_rounds, "combos_refitted_at_adapt_delta_0.99_last_step": int(info["n_retry"]),
+                             "combos_below_target_last_step_rank0": int(args.combos - info["reached"])} if target else None),
             "grad_evals_per_step": sm[1] / args.steps,
             "wall_s_timed_region": float(mx[2]),
             "setup_s_rank0": {"synthetic data + prepare (host, before any timed region)": t_setup},
@@ -347,7 +350,8 @@ def main():
     ap.add_argument("--iter", type=int, default=1150)
     ap.add_argument("--warmup-iter", type=int, default=1000,
                     help="warm-up iterations per chain (rstan: 1000); --iter 2000 --warmup-iter 1000 is rstan's default budget")
-    ap.add_argument("--max-rounds", type=int, default=8, help="--workload target: cap on the extension launches")
+    ap.add_argument("--max-rounds", type=int, default=6, help="--workload target: cap on the launches of phase 1 (warm-up + "
+                    "extensions); what is still below the target is refitted at adapt_delta 0.99 (api.screen_to_ess)")
     ap.add_argument("--e2e-reps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
