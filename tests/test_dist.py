@@ -86,7 +86,7 @@ def _toy_experiments(n):
     return [dict(y=y, x=x, drug_names=[f"A{k}", f"B{k}"], experiment_ID=f"e{k}") for k in range(n)]
 
 
-def test_synergyscreen_vb_retry_rule(monkeypatch):
+def test_synergyscreen_vb_retry_rule(monkeypatch, built):
     """method="vb": whatever errored (returnCode 2) or ended with s > 1 is refitted, up to max_retries more times
     (R/synergyscreen.R:159-167); what still fails is dropped from the summary and returned in `failed`."""
     from bayesynergy_b200 import api
@@ -113,12 +113,12 @@ def test_synergyscreen_vb_retry_rule(monkeypatch):
     assert [e["experiment_ID"] for e in out["failed"]] == ["e3"]
 
 
-def test_synergyscreen_sampling_retry_raises_adapt_delta(monkeypatch):
+def test_synergyscreen_sampling_retry_raises_adapt_delta(monkeypatch, built):
     """method="sampling": experiments with warnings are rerun with adapt_delta = 0.99 (R/synergyscreen.R:149-157)."""
     from bayesynergy_b200 import api
     seen = []
 
-    def fake_fit(sds, kw, device, max_treedepth):
+    def fake_fit(sds, kw, device, max_treedepth, want_samples=False, want_udraws=False):
         seen.append((len(sds), kw["adapt_delta"]))
         n = len(sds)
         rc = np.array([0, 1, 0]) if len(seen) == 1 else np.zeros(n, dtype=int)

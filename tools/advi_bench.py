@@ -28,4 +28,4 @@ out = {"combos": n, "iter_cap": it, "kernel_ms": res["kernel_ms"], "wall_s": wal
        "converged_bits": {str(int(c)): int((info[:, 4] == c).sum()) for c in np.unique(info[:, 4])}}
 print(json.dumps(out))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "advi_bench.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r02_advi_bench.json"), "w"), indent=1)

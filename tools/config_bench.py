@@ -25,13 +25,17 @@ def run(name, sds, model="gp_grid", iters=int(os.environ.get("CB_ITER", "2000"))
     b = _lib.Batch(sds, model=model)
     b.sample_device(chains=4, iter=200, warmup=100, seed=9, **kw)     # warm-up launch
     ng, ms = b.sample_device(chains=4, iter=iters, warmup=iters // 2, seed=1, **kw)
-    ess_syn, _ = b.ess("VUS_syn") if model == "gp_grid" else b.ess("rVUS_f")
-    ess_ant, rhat = b.ess("VUS_ant") if model == "gp_grid" else b.ess("rVUS_p0")
+    q1, q2 = ("VUS_syn", "VUS_ant") if model == "gp_grid" else ("rVUS_f", "rVUS_p0")
+    ess_syn, rhat1, _ = b.bulk_ess(q1)          # rank-normalised bulk ESS / R-hat
+    ess_ant, rhat2, _ = b.bulk_ess(q2)
     ess = np.fmin(ess_syn, ess_ant)
+    rhat = np.fmax(rhat1, rhat2)
     out = dict(config=name, model=model, combos=len(sds), D=b.max_params, n_grad=ng, kernel_s=ms * 1e-3,
                grad_evals_per_s=ng / ms * 1e3, leapfrogs_per_iter=ng / (len(sds) * 4 * iters),
                ess_min_mean=float(np.nanmean(ess)), total_ess_per_s=float(np.nansum(ess) / (ms * 1e-3)),
-               rhat_max=float(np.nanmax(rhat)), sampler=kw)
+               ess_ge_400_frac=float(np.mean(ess >= 400)), rhat_max=float(np.nanmax(rhat)),
+               rhat_gt_1_05=int((rhat > 1.05).sum()), sampler=kw, iter=iters, chains=4,
+               ess_estimator="rank-normalised bulk ESS, min over " + q1 + " / " + q2)
     b.close()
     print(json.dumps(out), flush=True)
     return out
@@ -60,7 +64,7 @@ def main():
     syn = [prepare(*synthetic_experiment(k)) for k in range(nb)]
     res.append(go("cfg4 nointeraction (H0 of the Bayes factor) on cfg5 data", syn, model="nointeraction"))
     res.append(go("cfg5 synthetic 10x10x3 (bench line)", syn))
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "config_bench.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r02_config_bench.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
