@@ -535,7 +535,8 @@ def screen_to_ess(sds, target=400.0, batch=None, device=0, chains=4, warmup=1000
             b.close()
     ess, nd = r["ess"].copy(), r["draws_per_chain"].copy()
     out = dict(ess=ess, draws_per_chain=nd, n_grad=r["n_grad"], kernel_ms=r["kernel_ms"], rounds=r["rounds"], n_retry=0,
-               summary=r.get("summary"), chain_stats=r.get("chain_stats"))
+               summary=r.get("summary"), chain_stats=r.get("chain_stats"), phase1_ms=r["kernel_ms"], phase2_ms=0.0,
+               reached_phase1=int((ess >= target).sum()))
     left = np.where(~(ess >= target))[0]
     if len(left) and retry_rounds > 0:
         b2 = _lib.Batch([sds[k] for k in left], device=device)
@@ -552,6 +553,7 @@ def screen_to_ess(sds, target=400.0, batch=None, device=0, chains=4, warmup=1000
                     out["summary"][k], out["chain_stats"][k] = r2["summary"][i], r2["chain_stats"][i]
         out["n_grad"] += r2["n_grad"]
         out["kernel_ms"] += r2["kernel_ms"]
+        out["phase2_ms"] = r2["kernel_ms"]
         out["rounds"] += r2["rounds"]
         out["n_retry"] = int(len(left))
     out["reached"] = int((ess >= target).sum())

@@ -301,8 +301,14 @@ def run_ours(args):
             "ess_ge_400_frac": float(sm[8] / n_combo_total),
             "time_to_ess400_all_s": float(step_time) if int(sm[8]) == n_combo_total else None,
             "sampler_launch_rounds_last_step": int(mx[9]),
-            "target_mode": ({"phase1_max_rounds": args.max_rounds, "combos_refitted_at_adapt_delta_0.99_last_step": int(info["n_retry"]),
-                             "combos_below_target_last_step_rank0": int(args.combos - info["reached"])} if target else None),
+            "target_mode": ({"phase1_max_rounds": args.max_rounds, "phase1_s_last_step_rank0": info["phase1_ms"] * 1e-3,
+                             "phase1_reached_frac_rank0": info["reached_phase1"] / args.combos,
+                             "phase2_s_last_step_rank0": info["phase2_ms"] * 1e-3,
+                             "combos_refitted_at_adapt_delta_0.99_last_step_rank0": int(info["n_retry"]),
+                             "combos_below_target_after_both_phases_rank0": int(args.combos - info["reached"]),
+                             "note": "what stays below the target after the adapt_delta 0.99 refit has R-hat > 1.05 (divergent / "
+                                     "multimodal posteriors: profiles/r02_target_diag.json); the reference reports such fits with "
+                                     "returnCode 1"} if target else None),
             "grad_evals_per_step": sm[1] / args.steps,
             "wall_s_timed_region": float(mx[2]),
             "setup_s_rank0": {"synthetic data + prepare (host, before any timed region)": t_setup},
