@@ -596,9 +596,13 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     }
     // boundary cells of f: f[0,a] = p01[a-1], f[b,0] = p02[b-1], f[0,0] = 1 (gp_grid.stan:170-172)
     double pmbar = 0.0;
+    if (!O.robust()) {   // Normal likelihoods: the branch-free form on every lane (lanes beyond the edge cells masked off)
+        const int fc = lane < n1 ? (lane + 1) * (n2 + 1) : (lane < nm ? lane - n1 + 1 : 0);
+        pmbar = lik_cell_normal(O, P, fc, lane < nm ? pmv : 1.0, is2, lane <= nm, lpl, slogbar, vprod, ok);
+    }
     if (lane <= nm) {
         const int fc = lane < n1 ? (lane + 1) * (n2 + 1) : (lane < nm ? lane - n1 + 1 : 0);
-        pmbar = lik_cell(O, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, vprod, ok);
+        if (O.robust()) pmbar = lik_cell(O, P, fc, lane < nm ? pmv : 1.0, s, is2, lpl, slogbar, vprod, ok);
         if (gq.on) {
             fg[fc] = lane < nm ? pmv : 1.0;
             double *const row = gq_ptr<double>(gq, GQS_ROW);
