@@ -254,3 +254,50 @@ def test_unconstrain_roundtrip(built, datasets):
         u2 = b.unconstrain(out[0, :D])
         assert np.abs(u2 - u).max() < 1e-12
         b.close()
+
+
+def test_specialised_and_fallback_kernels_agree(built, datasets, monkeypatch):
+    """The compile-time specialised kernels (SpecCT: package-default options; fixed 10 x 10 grid or run-time grid) and the
+    run-time-flags fallback (BSYN_NO_FAST=1) against the oracle and against each other, for every data set whose default
+    fit qualifies for a specialised variant, both models; plus a short sampler run through both (same seeds: the
+    variants differ only in summation order, so the first draws agree closely and the posterior means within MC error)."""
+    for dname in ("synthetic:7", "mathews:ispinesib + ibrutinib", "oneil_failed:0"):
+        y, x = datasets[dname]
+        sd = prepare(y, x)
+        rng = np.random.default_rng(5)
+        for model in ("gp_grid", "nointeraction"):
+            P = Problem(sd, model)
+            U = rng.uniform(-0.7, 0.7, size=(32, P.dim))
+            st_o, lp_o, g_o = P.logp_grad_batch(U)
+            res = {}
+            for nofast in ("0", "1"):
+                monkeypatch.setenv("BSYN_NO_FAST", nofast)
+                b = _lib.Batch([sd], model=model)
+                lp, g, st = b.logp_grad(U)
+                lpv, _, _ = b.logp_grad(U, want_grad=False)           # value-only path
+                res[nofast] = (lp, g[:, :P.dim])
+                assert (st == 0).all()
+                for k in range(U.shape[0]):
+                    tol = tol_for(kernel_cond_safe(sd, U[k], model))
+                    assert abs(lp[k] - lp_o[k]) <= tol * max(1.0, abs(lp_o[k])), (dname, model, nofast, k)
+                    assert relerr(g[k, :P.dim], g_o[k]) <= tol, (dname, model, nofast, k)
+                    assert abs(lpv[k] - lp[k]) <= 1e-12 * max(1.0, abs(lp[k]))
+                b.close()
+            assert relerr(res["0"][0], res["1"][0]) < 1e-11
+    # sampler through both kernel families
+    y, x = datasets["synthetic:7"]
+    sd = prepare(y, x)
+    means = {}
+    for nofast in ("0", "1"):
+        monkeypatch.setenv("BSYN_NO_FAST", nofast)
+        b = _lib.Batch([sd, sd])
+        r = b.sample(chains=4, iter=500, warmup=250, seed=12)
+        b.close()
+        assert (r["chain_stats"][:, :, 6] == 0).all()
+        means[nofast] = r["summary"][:, _lib.Q_NAMES.index("rVUS_f"), :]
+    assert np.abs(means["0"][:, 0] - means["1"][:, 0]).max() < 4 * means["0"][:, 1].max() / np.sqrt(200)
+
+
+def kernel_cond_safe(sd, u, model):
+    from conftest import kernel_cond
+    return kernel_cond(sd, u, model)
