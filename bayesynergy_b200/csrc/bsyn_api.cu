@@ -160,6 +160,7 @@ const VariantOps *bsyn_variant_default_1();
 const VariantOps *bsyn_variant_default_2();
 const VariantOps *bsyn_variant_default_4();
 const VariantOps *bsyn_variant_default_8();
+const VariantOps *bsyn_variant_robust_pc_4();
 const VariantOps *bsyn_variant_default(int cpl)
 {
     switch (cpl) {
@@ -249,6 +250,9 @@ extern "C" int bsyn_batch_create(const bsyn_problem *problems, int32_t n, const 
         const bool def_lik = F.het == 1 && F.robust == 0 && F.est_la == 1;
         const char *nf = getenv("BSYN_NO_FAST");
         const bool def_gp = F.model == 0 && F.kernel == 2 && F.nu_matern == 2 && F.pcprior == 0 && F.est_alpha == 0;
+        if (F.model == 0 && F.kernel == 2 && F.nu_matern == 2 && F.pcprior == 1 && F.est_alpha == 0 && F.het == 1 && F.robust == 1 &&
+            F.est_la == 1 && cpl == 4 && !(nf && atoi(nf)))
+            b->fast = bsyn_variant_robust_pc_4();
         if (def_lik && !(nf && atoi(nf))) {
             if (def_gp) b->fast = all10 ? bsyn_variant_gp10() : bsyn_variant_default(cpl);
             if (F.model == 1 && all10) b->fast = bsyn_variant_h0_10();
@@ -680,7 +684,7 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     // (BSYN_NUTS_NW / BSYN_NUTS_TICK override the defaults for A/B measurements).
     size_t bytes = 0;
     int nw = 0, per_sm = 0;
-    const VariantOps *ops = ops_for(b, a->metric == 0);
+    const VariantOps *ops = ops_for(b, a->metric == 0 || (b->fast && b->F.robust));   // dense_e: only the robust specialisation has it
     const int want = getenv("BSYN_NUTS_NW") ? atoi(getenv("BSYN_NUTS_NW")) : 0;
     const bool fast = ops != variant(b->cpl);
     int tick = 1;

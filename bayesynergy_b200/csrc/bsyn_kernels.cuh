@@ -167,7 +167,12 @@ template <int CPL, class SP = SpecRT> struct VariantImpl {
     return op == 0 ? nuts_launch<NW_, MINB_, DENSE_, TICK_>(grid, bytes, st, *F, descs, dpool, ipool, tri, *sp)            \
                    : nuts_occ<NW_, MINB_, DENSE_, TICK_>(bytes, per_sm)
         if constexpr (SP::fixed) {
-            if (metric == 1) return cudaErrorInvalidValue;
+            if (metric == 1) {   // dense_e is what bayesynergy() selects for robust = TRUE: built for the robust specialisations
+                if constexpr (SP::robust != 0) {
+                    if (nw == 12 && tick) { BSYN_NUTS_CASE(12, 168, true, true); }
+                }
+                return cudaErrorInvalidValue;
+            }
             if (nw == 12 && tick) { BSYN_NUTS_CASE(12, 168, false, true); }
             if constexpr (SP::NF > 0) {   // the A/B variants are only built for the fixed-grid specialisation
                 if (nw == 12 && !tick) { BSYN_NUTS_CASE(12, 168, false, false); }

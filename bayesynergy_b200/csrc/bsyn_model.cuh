@@ -28,6 +28,10 @@ namespace bsyn {
 // v^n, n <= 4; a factor below this bound (only possible with a user lambda << the default 0.005) takes its own logarithm
 // instead, so the product stays a normal double (1e-8^36 = 1e-288).
 #define BSYN_VPROD_MIN 1e-8
+// fixed even grids: 2 x 2 register-blocked products (block_product) instead of the 4-row strips
+#ifndef BSYN_USE_BLOCK_PRODUCT
+#define BSYN_USE_BLOCK_PRODUCT 1
+#endif
 
 template <int CPL> struct WVec {
     double z[CPL];
@@ -143,6 +147,52 @@ template <int NM> __device__ __forceinline__ void st4t(double *p, int r0, double
     if ((NM & 3) == 0 || r0 + 2 < NM) { p[2 * NM] = a2; p[3 * NM] = a3; }
 }
 
+// Fixed-grid variant of the product (CF columns, KF terms, both even): a lane owns a 2 x 2 block of the output,
+//   Out[r0..r0+1, c0..c0+1] = sum_m A[r0..r0+1 + m*NM] * B[(c0..c0+1)*SBC + m*SBM],
+// so per term it issues ONE LDS.128 for its two rows of A and one for its two columns of B (SBC == 1), or per PAIR of
+// terms two LDS.128 along m (SBM == 1): 8 shared-memory wavefronts per term instead of the strip mapping's 10, and the
+// transposed copy of a result is two 16-byte stores instead of four conflicting 8-byte ones.  (NM/2) x (CF/2) <= 32 lanes.
+template <int NM, int SBC, int SBM, int CF, int KF, class Epi>
+__device__ __forceinline__ void block_product(const double *A, const double *B, Epi &&epi)
+{
+    static_assert((NM & 1) == 0 && (CF & 1) == 0 && (KF & 1) == 0 && (NM / 2) * (CF / 2) <= 32, "block_product: even sizes, <= 32 blocks");
+    static_assert(SBC == 1 || SBM == 1, "block_product: B must be contiguous along c or along m");
+    constexpr int RB = NM / 2, NB = RB * (CF / 2);
+    const int lane = threadIdx.x & 31;
+    const int s = lane < NB ? lane : 0;      // idle lanes recompute block 0 and do not store
+    const int cp = s / RB, r0 = 2 * (s - cp * RB), c0 = 2 * cp;
+    const double2 *Ap = reinterpret_cast<const double2 *>(A + r0);
+    double a00 = 0.0, a10 = 0.0, a01 = 0.0, a11 = 0.0;   // a<row><col>
+    if constexpr (SBC == 1) {
+        const double2 *Bp = reinterpret_cast<const double2 *>(B + c0);
+#pragma unroll
+        for (int m = 0; m < KF; ++m) {
+            const double2 x = Ap[m * (NM / 2)], b = Bp[m * (SBM / 2)];
+            a00 = fma(x.x, b.x, a00); a10 = fma(x.y, b.x, a10); a01 = fma(x.x, b.y, a01); a11 = fma(x.y, b.y, a11);
+        }
+    } else {
+        const double2 *B0 = reinterpret_cast<const double2 *>(B + c0 * SBC), *B1 = reinterpret_cast<const double2 *>(B + (c0 + 1) * SBC);
+#pragma unroll
+        for (int m = 0; m < KF; m += 2) {
+            const double2 x = Ap[m * (NM / 2)], y = Ap[(m + 1) * (NM / 2)], b0 = B0[m / 2], b1 = B1[m / 2];
+            a00 = fma(x.x, b0.x, a00); a10 = fma(x.y, b0.x, a10); a01 = fma(x.x, b1.x, a01); a11 = fma(x.y, b1.x, a11);
+            a00 = fma(y.x, b0.y, a00); a10 = fma(y.y, b0.y, a10); a01 = fma(y.x, b1.y, a01); a11 = fma(y.y, b1.y, a11);
+        }
+    }
+    if (lane < NB) epi(r0, c0, a00, a10, a01, a11);
+}
+// stores of a 2 x 2 block: column-major Out[r + c*NM], and its transpose Out[c + r*NM]
+template <int NM> __device__ __forceinline__ void stb(double *Out, int r0, int c0, double a00, double a10, double a01, double a11)
+{
+    st2(Out + r0 + c0 * NM, a00, a10);
+    st2(Out + r0 + (c0 + 1) * NM, a01, a11);
+}
+template <int NM> __device__ __forceinline__ void stbt(double *Out, int r0, int c0, double a00, double a10, double a01, double a11)
+{
+    st2(Out + c0 + r0 * NM, a00, a01);
+    st2(Out + c0 + (r0 + 1) * NM, a10, a11);
+}
+
 template <int CPL, class SP = SpecRT> __device__ __forceinline__ int zoff(const int cell)   // cell -> offset in a grid-shaped buffer
 {
     return (cell & 255) + ((cell >> 8) & 255) * Cfg<CPL, SP>::NM;
@@ -233,14 +283,25 @@ __device__ __forceinline__ bool gp_forward(const OptV<SP> &F, const ProbS &P, co
     for (int t = 0; t < CPL; ++t)
         if (cell[t] >> 16) Zs[zoff<CPL, SP>(cell[t])] = z[t];
     __syncwarp();
-    strip_product<NM, NM, 1, NF, NF>(L2c, Zs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-        st4<NM>(Ts + r0 + c * NM, r0, a0, a1, a2, a3);
-        st4t<NM>(Tt + c + r0 * NM, r0, a0, a1, a2, a3);
-    });
-    __syncwarp();
-    strip_product<NM, NM, 1, NF, NF>(Ts, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-        st4<NM>(Gs + r0 + c * NM, r0, a0, a1, a2, a3);
-    });
+    if constexpr (BSYN_USE_BLOCK_PRODUCT && NF > 0 && (NF & 1) == 0) {
+        block_product<NM, NM, 1, NF, NF>(L2c, Zs, [&](int r0, int c0, double a00, double a10, double a01, double a11) {
+            stb<NM>(Ts, r0, c0, a00, a10, a01, a11);
+            stbt<NM>(Tt, r0, c0, a00, a10, a01, a11);
+        });
+        __syncwarp();
+        block_product<NM, NM, 1, NF, NF>(Ts, L1r, [&](int r0, int c0, double a00, double a10, double a01, double a11) {
+            stb<NM>(Gs, r0, c0, a00, a10, a01, a11);
+        });
+    } else {
+        strip_product<NM, NM, 1, NF, NF>(L2c, Zs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st4<NM>(Ts + r0 + c * NM, r0, a0, a1, a2, a3);
+            st4t<NM>(Tt + c + r0 * NM, r0, a0, a1, a2, a3);
+        });
+        __syncwarp();
+        strip_product<NM, NM, 1, NF, NF>(Ts, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+            st4<NM>(Gs + r0 + c * NM, r0, a0, a1, a2, a3);
+        });
+    }
     __syncwarp();
 #pragma unroll
     for (int t = 0; t < CPL; ++t) Gv[t] = (cell[t] >> 16) ? Gs[zoff<CPL, SP>(cell[t])] : 0.0;
@@ -713,40 +774,72 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
     double ellbar = 0.0, sigfbar = 0.0, alphabar = 0.0;
     if (gp) {
         __syncwarp();   // p0bar (in Ws) has been consumed
-        // W = Gbar * L1 -> Ws            W[i,l] = sum_j Gbar[i,j] L1[j,l]
-        strip_product<NM, 1, NM, NF, NF>(Gs, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st4<NM>(Ws + r0 + c * NM, r0, a0, a1, a2, a3);
-        });
-        // L1bar = tril(Gbar^T T) -> Lb1 row-major: strip rows l of column j hold L1bar[j,l], kept for l <= j
-        strip_product<NM, NM, 1, NF, NF>(Tt, Gs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st4<NM>(Lb1 + r0 + c * NM, r0, (r0 <= c) ? a0 : 0.0, (r0 + 1 <= c) ? a1 : 0.0, (r0 + 2 <= c) ? a2 : 0.0,
-                    (r0 + 3 <= c) ? a3 : 0.0);
-        });
-        __syncwarp();
-        // L2bar = tril(W Z^T) -> Lb2 col-major [i + k*NM], kept for i >= k
-        strip_product<NM, 1, NM, NF, NF>(Ws, Zs, n2, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st4<NM>(Lb2 + r0 + c * NM, r0, (r0 >= c) ? a0 : 0.0, (r0 + 1 >= c) ? a1 : 0.0, (r0 + 2 >= c) ? a2 : 0.0,
-                    (r0 + 3 >= c) ? a3 : 0.0);
-        });
-        if (DBG) {
+        if constexpr (BSYN_USE_BLOCK_PRODUCT && NF > 0 && (NF & 1) == 0) {
+            // the same six products on 2 x 2 blocks (fixed even grid); masks keep the triangles the adjoints need
+            block_product<NM, 1, NM, NF, NF>(Gs, L1r, [&](int r0, int c0, double a00, double a10, double a01, double a11) {
+                stb<NM>(Ws, r0, c0, a00, a10, a01, a11);                                    // W = Gbar L1
+            });
+            block_product<NM, NM, 1, NF, NF>(Tt, Gs, [&](int r0, int c0, double a00, double a10, double a01, double a11) {
+                stb<NM>(Lb1, r0, c0, (r0 <= c0) ? a00 : 0.0, (r0 + 1 <= c0) ? a10 : 0.0, (r0 <= c0 + 1) ? a01 : 0.0,
+                        (r0 + 1 <= c0 + 1) ? a11 : 0.0);                                    // L1bar[j = c][l = r], l <= j
+            });
+            __syncwarp();
+            block_product<NM, 1, NM, NF, NF>(Ws, Zs, [&](int r0, int c0, double a00, double a10, double a01, double a11) {
+                stb<NM>(Lb2, r0, c0, (r0 >= c0) ? a00 : 0.0, (r0 + 1 >= c0) ? a10 : 0.0, (r0 >= c0 + 1) ? a01 : 0.0,
+                        (r0 + 1 >= c0 + 1) ? a11 : 0.0);                                    // L2bar[i = r][k = c], i >= k
+            });
+            if (DBG) {
 #pragma unroll
-            for (int t = 0; t < CPL; ++t)
-                if (cell[t] >> 16) dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gs[zoff<CPL, SP>(cell[t])];
+                for (int t = 0; t < CPL; ++t)
+                    if (cell[t] >> 16) dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gs[zoff<CPL, SP>(cell[t])];
+            }
+            __syncwarp();
+            block_product<NM, NM, 1, NF, NF>(L2r, Ws, [&](int r0, int c0, double a00, double a10, double a01, double a11) {
+                stb<NM>(Gs, r0, c0, a00, a10, a01, a11);                                    // Zbar = L2^T W
+            });
+            block_product<NM, 1, NM, NF, NF>(L1r, Lb1, [&](int r0, int c0, double a00, double a10, double a01, double a11) {
+                stb<NM>(Zs, r0, c0, a00, a10, a01, a11);                                    // S1 = L1^T L1bar
+            });
+            block_product<NM, NM, 1, NF, NF>(L2r, Lb2, [&](int r0, int c0, double a00, double a10, double a01, double a11) {
+                stb<NM>(Ts, r0, c0, a00, a10, a01, a11);                                    // S2 = L2^T L2bar
+            });
+            __syncwarp();
+        } else {
+        // W = Gbar * L1 -> Ws            W[i,l] = sum_j Gbar[i,j] L1[j,l]
+            strip_product<NM, 1, NM, NF, NF>(Gs, L1r, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+                st4<NM>(Ws + r0 + c * NM, r0, a0, a1, a2, a3);
+            });
+            // L1bar = tril(Gbar^T T) -> Lb1 row-major: strip rows l of column j hold L1bar[j,l], kept for l <= j
+            strip_product<NM, NM, 1, NF, NF>(Tt, Gs, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+                st4<NM>(Lb1 + r0 + c * NM, r0, (r0 <= c) ? a0 : 0.0, (r0 + 1 <= c) ? a1 : 0.0, (r0 + 2 <= c) ? a2 : 0.0,
+                        (r0 + 3 <= c) ? a3 : 0.0);
+            });
+            __syncwarp();
+            // L2bar = tril(W Z^T) -> Lb2 col-major [i + k*NM], kept for i >= k
+            strip_product<NM, 1, NM, NF, NF>(Ws, Zs, n2, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+                st4<NM>(Lb2 + r0 + c * NM, r0, (r0 >= c) ? a0 : 0.0, (r0 + 1 >= c) ? a1 : 0.0, (r0 + 2 >= c) ? a2 : 0.0,
+                        (r0 + 3 >= c) ? a3 : 0.0);
+            });
+            if (DBG) {
+#pragma unroll
+                for (int t = 0; t < CPL; ++t)
+                    if (cell[t] >> 16) dbg[2 * C::NN + 2 * C::GM + lane + 32 * t] = Gs[zoff<CPL, SP>(cell[t])];
+            }
+            __syncwarp();
+            // Zbar = L2^T W -> Gs            Zbar[k,l] = sum_i L2[i,k] W[i,l]
+            strip_product<NM, NM, 1, NF, NF>(L2r, Ws, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+                st4<NM>(Gs + r0 + c * NM, r0, a0, a1, a2, a3);
+            });
+            // Cholesky adjoint (Murray 2016): Xfull = L^-T (Phi + Phi^T) L^-1, Phi = tril(L^T Lbar), diag halved.
+            // Stage A: P = L^T Lbar (only its lower triangle is used) -> S1 (over Zs), S2 (over Ts)
+            strip_product<NM, 1, NM, NF, NF>(L1r, Lb1, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+                st4<NM>(Zs + r0 + c * NM, r0, a0, a1, a2, a3);
+            });
+            strip_product<NM, NM, 1, NF, NF>(L2r, Lb2, n2, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
+                st4<NM>(Ts + r0 + c * NM, r0, a0, a1, a2, a3);
+            });
+            __syncwarp();
         }
-        __syncwarp();
-        // Zbar = L2^T W -> Gs            Zbar[k,l] = sum_i L2[i,k] W[i,l]
-        strip_product<NM, NM, 1, NF, NF>(L2r, Ws, n1, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st4<NM>(Gs + r0 + c * NM, r0, a0, a1, a2, a3);
-        });
-        // Cholesky adjoint (Murray 2016): Xfull = L^-T (Phi + Phi^T) L^-1, Phi = tril(L^T Lbar), diag halved.
-        // Stage A: P = L^T Lbar (only its lower triangle is used) -> S1 (over Zs), S2 (over Ts)
-        strip_product<NM, 1, NM, NF, NF>(L1r, Lb1, n1, n1, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st4<NM>(Zs + r0 + c * NM, r0, a0, a1, a2, a3);
-        });
-        strip_product<NM, NM, 1, NF, NF>(L2r, Lb2, n2, n2, [&](int r0, int c, double a0, double a1, double a2, double a3) {
-            st4<NM>(Ts + r0 + c * NM, r0, a0, a1, a2, a3);
-        });
-        __syncwarp();
         // Zbar is complete: gradient wrt z (+ its N(0,1) prior)
 #pragma unroll
         for (int t = 0; t < CPL; ++t) {
