@@ -278,7 +278,7 @@ def run_ours(args):
     if rank == 0:
         dev_s = mx[0] * 1e-3
         value = sm[1] / dev_s
-        e2e_value = sm[4] / mx[5]
+        e2e_value = sm[4] / mx[5] if mx[5] > 0 else None
         n_combo_total = args.combos * world
         step_time = dev_s / args.steps
         peaks = {}
@@ -313,7 +313,8 @@ def run_ours(args):
             "wall_s_timed_region": float(mx[2]),
             "setup_s_rank0": {"synthetic data + prepare (host, before any timed region)": t_setup},
             "e2e": {"value": e2e_value, "unit": "grad evals/s", "h2d_bytes_per_step": h2d_bytes(sds),
-                    "d2h_bytes_per_step": d2h, "seconds_per_step": float(mx[5] / len(e2e_t)), "reps": len(e2e_t)},
+                    "d2h_bytes_per_step": d2h, "seconds_per_step": float(mx[5] / len(e2e_t)) if e2e_t else None,
+                    "reps": len(e2e_t)},
             "gpu_launches": int(mx[7]),
             "clocks": clocks.summary(),
             # the bound of this path is FP64 issue throughput (neither HBM nor tensor cores)

@@ -301,3 +301,33 @@ def test_specialised_and_fallback_kernels_agree(built, datasets, monkeypatch):
 def kernel_cond_safe(sd, u, model):
     from conftest import kernel_cond
     return kernel_cond(sd, u, model)
+
+
+def test_tiny_lambda_does_not_underflow_the_variance_product(built, datasets, cond_fn):
+    """lambda is a user option (R/bayesynergy.R:57, default 0.005).  The kernels fold the heteroscedastic -n/2 log(f +
+    lambda) terms of a lane into one logarithm of a product; with lambda = 1e-10 and f -> 0 at high doses that product
+    would underflow, so factors below 1e-8 take their own logarithm.  lp and gradient against the oracle at such points."""
+    y, x = datasets["synthetic:7"]
+    sd = prepare(y, x, lambda_=1e-10)
+    rng = np.random.default_rng(3)
+    for model in ("gp_grid", "nointeraction"):
+        P = Problem(sd, model)
+        b = _lib.Batch([sd], model=model)
+        U = rng.uniform(-0.5, 0.5, size=(32, P.dim))
+        k0 = 2 * sd.est_la
+        U[:, 0:2] = rng.uniform(-14.0, -9.0, size=(32, 2))            # lower asymptotes ~ 1e-5: f can reach ~ 1e-10
+        U[:, k0 + 0:k0 + 2] = rng.uniform(-2.5, -1.5, size=(32, 2))   # log10 EC50 far below the top doses
+        U[:, k0 + 4:k0 + 6] = rng.uniform(1.0, 1.6, size=(32, 2))     # steep slopes (log scale)
+        lp, g, st = b.logp_grad(U)
+        st_o, lp_o, g_o = P.logp_grad_batch(U)
+        assert np.array_equal(st, st_o)
+        checked = 0
+        for k in range(U.shape[0]):
+            if st[k] != 0 or not np.isfinite(g_o[k]).all():
+                continue
+            tol = max(1e-9, tol_for(cond_fn(sd, U[k], model)))       # 1/(f + lambda) ~ 1e10 amplifies rounding in f
+            assert abs(lp[k] - lp_o[k]) <= tol * max(1.0, abs(lp_o[k])), (model, k, lp[k], lp_o[k])
+            assert relerr(g[k, :P.dim], g_o[k]) <= 1e-6, (model, k)
+            checked += 1
+        assert checked >= 8
+        b.close()
