@@ -208,7 +208,9 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
             if st != 0:
                 raise RuntimeError("variational inference failed: " + _VB_ERRORS.get(st, f"status {st}"))
         else:
-            res = b.sample(want_draws=True, want_udraws=bool(bayes_factor), want_surfaces=True, **kw)
+            res = b.sample(want_draws=True, want_udraws=bool(bayes_factor), want_surfaces=True, want_inv_metric=True,
+                           want_inits=True, **kw)
+            blocks = b.param_blocks(0)
     finally:
         b.close()
     if method == "sampling":
@@ -223,7 +225,13 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
                            res["chain_stats"][0] if method == "sampling" else None,
                            res["qdraws"][0] if method == "sampling" else None, options, kw.get("max_treedepth", 10))
     if method == "sampling":
+        from .stanfit import StanFit
         obj.update(sampler_params=res["sampler_params"][0], chain_stats=res["chain_stats"][0], n_grad=res["n_grad"])
+        # object$stanfit (R/bayesynergy.R:317): extract / summary / get_sampler_params / get_divergent_iterations ...
+        D = len(param_names(sd))
+        obj["stanfit"] = StanFit(output_names(sd), blocks, res["draws"][0][:, :, :len(output_names(sd))],
+                                 res["sampler_params"][0], res["chain_stats"][0], res["inv_metric"][0][:, :D],
+                                 res["init_u"][0][:, :D], res["kernel_ms"], warmup=kw["warmup"], args=kw)
     else:
         obj.update(vb_info=dict(zip(_lib.VI_NAMES, res["info"][0])), vb_mean=res["mean"][0, :len(param_names(sd))],
                    n_grad=res["n_evals"])

@@ -683,23 +683,26 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
     // matches a compile-time specialisation (diag_e only) uses it: 12 or 16 warps per SM, with or without the tick barrier
     // (BSYN_NUTS_NW / BSYN_NUTS_TICK override the defaults for A/B measurements).
     size_t bytes = 0;
-    int nw = 0, per_sm = 0;
-    const VariantOps *ops = ops_for(b, a->metric == 0 || (b->fast && b->F.robust));   // dense_e: only the robust specialisation has it
+    int nw = 0, per_sm = 0, tick = 1;
+    const VariantOps *ops = nullptr;
     const int want = getenv("BSYN_NUTS_NW") ? atoi(getenv("BSYN_NUTS_NW")) : 0;
-    const bool fast = ops != variant(b->cpl);
-    int tick = 1;
-    if (fast) tick = getenv("BSYN_NUTS_TICK") ? atoi(getenv("BSYN_NUTS_TICK")) : BSYN_FAST_DEFAULT_TICK;
     sp.tick_period = std::max(1, getenv("BSYN_TICK_PERIOD") ? atoi(getenv("BSYN_TICK_PERIOD")) : BSYN_DEFAULT_TICK_PERIOD);
-    for (int cand : {16, 14, 12, 6, 4, 1}) {
-        if (want && cand != want) continue;
-        if (fast && cand != 12 && cand != 14 && cand != 16) continue;
-        if (fast && !want && cand != BSYN_FAST_DEFAULT_NW) continue;
-        if (!fast && (cand == 16 || cand == 14)) continue;
-        if (a->metric == 1 && cand != 12 && cand != 4) continue;
-        sp.sl = make_layout(b, ops, true, &bytes, cand, (b->cpl + 1) * 32);
-        if (bytes > 227 * 1024) continue;
-        if (ops->nuts_occupancy(cand, a->metric, tick, bytes, &per_sm) != cudaSuccess) { cudaGetLastError(); continue; }
-        if (per_sm >= 1) { nw = cand; break; }
+    // the specialised variant first (when the batch has one and it has a kernel for this metric), then the fallback
+    const VariantOps *cands_ops[2] = {(b->fast && (a->metric == 0 || b->F.robust)) ? b->fast : nullptr, variant(b->cpl)};
+    for (const VariantOps *o : cands_ops) {
+        if (!o || nw) continue;
+        const bool fast = o != variant(b->cpl);
+        const int tk = fast ? (getenv("BSYN_NUTS_TICK") ? atoi(getenv("BSYN_NUTS_TICK")) : BSYN_FAST_DEFAULT_TICK) : 1;
+        for (int cand : {16, 14, 12, 6, 4, 1}) {
+            if (want && cand != want) continue;
+            if ((cand == 16 || cand == 14) && !(fast && want)) continue;          // A/B variants of the fixed-grid kernels, on request
+            if (fast && cand != 16 && cand != 14 && cand != 12 && cand != 4) continue;
+            if (a->metric == 1 && cand != 12 && cand != 4) continue;
+            SmemLayout sl = make_layout(b, o, true, &bytes, cand, (b->cpl + 1) * 32);
+            if (bytes > 227 * 1024) continue;
+            if (o->nuts_occupancy(cand, a->metric, tk, bytes, &per_sm) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (per_sm >= 1) { nw = cand; ops = o; tick = tk; sp.sl = sl; break; }
+        }
     }
     if (!nw) return fail(BSYN_ERR_UNSUPPORTED, "sampler kernel does not fit on an SM");
     const int n_items = (plan.d_list ? plan.n_list : b->n) * a->chains;

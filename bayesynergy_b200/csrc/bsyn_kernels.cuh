@@ -167,12 +167,14 @@ template <int CPL, class SP = SpecRT> struct VariantImpl {
     return op == 0 ? nuts_launch<NW_, MINB_, DENSE_, TICK_>(grid, bytes, st, *F, descs, dpool, ipool, tri, *sp)            \
                    : nuts_occ<NW_, MINB_, DENSE_, TICK_>(bytes, per_sm)
         if constexpr (SP::fixed) {
-            if (metric == 1) {   // dense_e is what bayesynergy() selects for robust = TRUE: built for the robust specialisations
-                if constexpr (SP::robust != 0) {
-                    if (nw == 12 && tick) { BSYN_NUTS_CASE(12, 168, true, true); }
-                }
-                return cudaErrorInvalidValue;
+            if constexpr (SP::robust != 0) {
+                // robust models keep their sorted observations in shared memory: on the O'Neil grids 12 warps do not fit,
+                // so 3 CTAs of 4 warps are built as well; dense_e is what bayesynergy() selects for robust = TRUE
+                if (metric == 1 && nw == 12 && tick) { BSYN_NUTS_CASE(12, 168, true, true); }
+                if (metric == 1 && nw == 4 && tick) { BSYN_NUTS_CASE(4, 168, true, true); }
+                if (metric == 0 && nw == 4 && tick) { BSYN_NUTS_CASE(4, 168, false, true); }
             }
+            if (metric == 1) return cudaErrorInvalidValue;
             if (nw == 12 && tick) { BSYN_NUTS_CASE(12, 168, false, true); }
             if constexpr (SP::NF > 0) {   // the A/B variants are only built for the fixed-grid specialisation
                 if (nw == 12 && !tick) { BSYN_NUTS_CASE(12, 168, false, false); }

@@ -227,12 +227,15 @@ __device__ __forceinline__ void store_user_vec(const Flags &F, const ProbDesc &p
 // The sampler kernel.
 //
 // A CTA is NW warps, each warp runs one chain at a time (work items = (problem, chain), pulled from an atomic
-// counter).  The kernel is a TICK state machine: every pass of the main loop starts with a CTA barrier and
-// contains exactly ONE leapfrog (one lp+gradient evaluation) per warp, followed by that chain's bookkeeping
-// (tree logic, adaptation, fetching the next chain ...).  Two reasons:
-//   * one copy of the ~10k-instruction model code in the kernel instead of one per call site;
+// counter).  The kernel is a TICK state machine: every pass of the main loop contains exactly ONE leapfrog (one
+// lp+gradient evaluation) per warp, followed by that chain's bookkeeping (tree logic, adaptation, fetching the next
+// chain ...), and every tick_period-th pass (default 2) starts with a CTA barrier.  Two reasons:
+//   * one copy of the model code (5-10 k instructions) in the kernel instead of one per call site;
 //   * the warps of a CTA run the evaluation in step, so they share instruction-cache lines.  With free-running
-//     warps the sampler spent a third of its issue slots waiting for instructions (profiles/r01_nuts_v3*).
+//     warps the sampler spent a third of its issue slots waiting for instructions (profiles/r01_nuts_v3*); with the
+//     compile-time specialised model code (35 % smaller) free-running warps are still 11 % slower than the tick, two
+//     independently synchronised halves of the CTA 9 % slower, and barriers INSIDE the evaluation 5 % slower
+//     (profiles/r02_ab_nuts_v1 / v6 / v7): one barrier per two ticks is the measured optimum.
 // The phases map onto Stan's control flow: PH_INIT = services::util::initialize, PH_ISTEP =
 // base_hmc::init_stepsize, PH_TREE = base_nuts::transition / build_tree (iteratively, see the header comment),
 // end-of-transition = stepsize_adaptation + windowed var_adaptation, PH_GQ = write_array of the saved draw.
@@ -659,7 +662,19 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
             if (!(h == h)) h = INFINITY;
             const double w = H0 - h;
             if (h - H0 > 1000.0) divergent = 1;
-            lsw_sub = log_add_exp(lsw_sub, w);
+            // ONE exponential serves the running log-sum of the subtree's weights and the reservoir probability of this
+            // leaf: with a = w - lsw_sub(old) and e = exp(-|a|),  lsw_sub(new) = max + log(1 + e)  and
+            // pr = exp(w - lsw_sub(new)) = 1 / (1 + exp(-a)).
+            double pr = 1.0;
+            if (lsw_sub == -INFINITY) {
+                lsw_sub = w;                       // first weight of the subtree
+            } else if (w == -INFINITY) {
+                pr = 0.0;                          // H = inf: weight zero
+            } else {
+                const double a = w - lsw_sub, e = fast_exp(-fabs(a)), r1 = fast_rcp(1.0 + e);
+                pr = (a >= 0.0) ? r1 : e * r1;
+                lsw_sub = fmax(lsw_sub, w) + fast_log(1.0 + e);
+            }
             summetro += (w > 0.0) ? 1.0 : fast_exp(w);
             bool valid = !divergent;
             if (valid) {
@@ -667,9 +682,8 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 // after a Bernoulli(pr) decision taken as (u < pr), u/pr resp. (u-pr)/(1-pr) is again U(0,1).
                 bool take = (k == 0);
                 if (!take) {
-                    const double pr = fast_exp(w - lsw_sub);
                     take = u_leaf < pr;
-                    u_leaf = take ? u_leaf * fast_rcp(pr) : (u_leaf - pr) * fast_rcp(1.0 - pr);
+                    u_leaf = (take ? u_leaf : u_leaf - pr) * fast_rcp(take ? pr : 1.0 - pr);
                     u_leaf = fmin(fmax(u_leaf, 0.0), 1.0);
                 }
                 if (take) {

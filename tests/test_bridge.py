@@ -81,6 +81,21 @@ def test_bayesynergy_api_with_bayes_factor(built, datasets):
     assert np.isfinite(fit["LPML"]) and fit["returnCode"] in (0, 1)
     assert fit["posterior"]["Delta"].shape == (2000, 5, 5) and fit["posterior"]["CPO"].shape == (2000, 36)
     assert fit["bayesfactor"] > 1.0          # strong interaction in this experiment (the vignette reports synergy)
+    # the stanfit-shaped view: rstan::extract / summary / get_sampler_params / get_divergent_iterations
+    sf = fit["stanfit"]
+    ex = sf.extract()
+    assert ex["z"].shape == (2000, 5, 5) and ex["la_1"].shape == (2000, 1) and ex["alpha"].shape == (2000, 0)
+    assert np.array_equal(ex["VUS_syn"], fit["posterior"]["VUS_syn"]) and np.array_equal(ex["Delta"], fit["posterior"]["Delta"])
+    assert np.array_equal(ex["lp__"], fit["posterior"]["lp__"])
+    sm = sf.summary(pars=["VUS_syn", "s", "lp__"])
+    assert sm["rownames"] == ["s", "VUS_syn", "lp__"] and sm["colnames"][:3] == ["mean", "se_mean", "sd"]
+    assert abs(sm["summary"][1, 0] - pm["VUS_syn"]) < 1e-12 and (sm["summary"][:, -1] < 1.05).all()
+    assert (sm["summary"][:, -2] > 100).all()                          # n_eff
+    sp = sf.get_sampler_params()
+    assert len(sp) == 4 and sp[0]["n_leapfrog__"].shape == (500,) and (sp[0]["stepsize__"] > 0).all()
+    assert sf.get_divergent_iterations().shape == (2000,)
+    assert "# Step size = " in sf.get_adaptation_info()[0] and sf.get_elapsed_time().shape == (4, 2)
+    assert sf.get_inits().shape == (4, 40) and np.abs(sf.get_inits()).max() <= 2.0
 
 
 def test_bulk_ess_rank_normalised():
