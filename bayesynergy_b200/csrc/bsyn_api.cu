@@ -783,44 +783,46 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
     const size_t nrows = (size_t)b->n * args->chains * n_save;
     const size_t nch = (size_t)b->n * args->chains;
     DevSinks ds;
+    struct Holder {   // the device sinks of this call: freed on every return path
+        DevSinks &d;
+        ~Holder() { cudaFree(d.draws); cudaFree(d.udraws); cudaFree(d.cpo); cudaFree(d.inv_metric); cudaFree(d.init_u); cudaFree(d.f_acc); }
+    } holder{ds};
+    auto alloc0 = [&](double **p, size_t n, const char *what) -> int {   // zero-filled device buffer
+        if (cudaMalloc(p, sizeof(double) * std::max<size_t>(n, 1)) != cudaSuccess) {
+            *p = nullptr;
+            cudaGetLastError();
+            return fail(BSYN_ERR_ALLOC, std::string("bsyn_sample: the ") + what + " buffer does not fit on the device");
+        }
+        if (cudaMemsetAsync(*p, 0, sizeof(double) * std::max<size_t>(n, 1), b->stream) != cudaSuccess) return fail(BSYN_ERR_CUDA, "bsyn_sample: memset");
+        return BSYN_OK;
+    };
     int rc = BSYN_OK;
     int max_ncf = 0;
     for (const ProbDesc &d : b->descs) max_ncf = std::max(max_ncf, d.ncf);
     if ((sinks->f_mean || sinks->surfaces) && sinks->ld_f < max_ncf) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_f < (n1+1)(n2+1)");
     if ((sinks->surfaces || sinks->lpml) && (long long)ns_samp * args->chains > BULK_MAX_DRAWS)
         return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample: surfaces / lpml need <= 8192 pooled sampling draws per problem");
+    if (sinks->draws && sinks->ld_draws < b->maxOut) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_draws < bsyn_max_outputs");
+    if (sinks->udraws && sinks->ld_udraws < b->maxD) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_udraws < bsyn_max_params");
+    if (sinks->cpo_mean && sinks->ld_cpo < b->maxN) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_cpo < max N");
     if (sinks->draws || sinks->surfaces || sinks->lpml) {
-        if (sinks->draws && sinks->ld_draws < b->maxOut) return fail(BSYN_ERR_ARG, "bsyn_sample: ld_draws < bsyn_max_outputs");
         ds.ld_draws = sinks->draws ? sinks->ld_draws : b->maxOut;
-        if (cudaMalloc(&ds.draws, sizeof(double) * nrows * ds.ld_draws) != cudaSuccess) return fail(BSYN_ERR_ALLOC, "draws buffer does not fit on the device; use the summary sinks");
-        cudaMemsetAsync(ds.draws, 0, sizeof(double) * nrows * ds.ld_draws, b->stream);
+        if ((rc = alloc0(&ds.draws, nrows * ds.ld_draws, "draws (use the summary / surfaces sinks for large screens)"))) return rc;
     }
     if (sinks->udraws) {
-        if (sinks->ld_udraws < b->maxD) { cudaFree(ds.draws); return fail(BSYN_ERR_ARG, "bsyn_sample: ld_udraws < bsyn_max_params"); }
         ds.ld_u = sinks->ld_udraws;
-        if (cudaMalloc(&ds.udraws, sizeof(double) * nrows * ds.ld_u) != cudaSuccess) { cudaFree(ds.draws); return fail(BSYN_ERR_ALLOC, "udraws buffer does not fit on the device"); }
-        cudaMemsetAsync(ds.udraws, 0, sizeof(double) * nrows * ds.ld_u, b->stream);
+        if ((rc = alloc0(&ds.udraws, nrows * ds.ld_u, "udraws"))) return rc;
     }
     if (sinks->cpo_mean) {
-        if (sinks->ld_cpo < b->maxN) { cudaFree(ds.draws); cudaFree(ds.udraws); return fail(BSYN_ERR_ARG, "bsyn_sample: ld_cpo < max N"); }
         ds.ld_cpo = b->maxN;
-        if (cudaMalloc(&ds.cpo, sizeof(double) * nch * std::max(1, ds.ld_cpo)) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); return fail(BSYN_ERR_ALLOC, "cpo buffer"); }
-        cudaMemsetAsync(ds.cpo, 0, sizeof(double) * nch * std::max(1, ds.ld_cpo), b->stream);
+        if ((rc = alloc0(&ds.cpo, nch * std::max(1, ds.ld_cpo), "cpo"))) return rc;
     }
-    if (sinks->inv_metric) {
-        ds.ld_im = b->maxD;
-        if (cudaMalloc(&ds.inv_metric, sizeof(double) * nch * ds.ld_im) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); return fail(BSYN_ERR_ALLOC, "inv_metric buffer"); }
-        cudaMemsetAsync(ds.inv_metric, 0, sizeof(double) * nch * ds.ld_im, b->stream);
-    }
+    if (sinks->inv_metric || sinks->init_u) ds.ld_im = b->maxD;
+    if (sinks->inv_metric && (rc = alloc0(&ds.inv_metric, nch * ds.ld_im, "inv_metric"))) return rc;
+    if (sinks->init_u && (rc = alloc0(&ds.init_u, nch * ds.ld_im, "init_u"))) return rc;
     if (sinks->f_mean) {
         ds.ld_f = max_ncf;
-        if (cudaMalloc(&ds.f_acc, sizeof(double) * nch * max_ncf) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); return fail(BSYN_ERR_ALLOC, "f_mean buffer"); }
-        cudaMemsetAsync(ds.f_acc, 0, sizeof(double) * nch * max_ncf, b->stream);
-    }
-    if (sinks->init_u) {
-        ds.ld_im = b->maxD;
-        if (cudaMalloc(&ds.init_u, sizeof(double) * nch * b->maxD) != cudaSuccess) { cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); return fail(BSYN_ERR_ALLOC, "init_u buffer"); }
-        cudaMemsetAsync(ds.init_u, 0, sizeof(double) * nch * b->maxD, b->stream);
+        if ((rc = alloc0(&ds.f_acc, nch * max_ncf, "f_mean"))) return rc;
     }
     float ms_total = 0.f;
     rc = run_sampler(b, args, ds, total_grad_evals, &ms_total);
@@ -885,7 +887,6 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
         }
         if (e != cudaSuccess) rc = fail(BSYN_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
     }
-    cudaFree(ds.draws); cudaFree(ds.udraws); cudaFree(ds.cpo); cudaFree(ds.inv_metric); cudaFree(ds.init_u); cudaFree(ds.f_acc);
     return rc;
 }
 

@@ -266,3 +266,20 @@ def test_sample_to_ess_extends_only_what_is_below_target(built):
             zs.append(abs(a.mean() - c.mean()) / (np.hypot(mcse_mean(a), mcse_mean(c)) + 1e-9))
     zs = np.array(zs)
     assert zs.max() < 4.5 and (zs > 3.0).sum() <= 2, zs
+
+
+def test_screen_to_ess_two_phases(built):
+    """api.screen_to_ess: phase 1 (extension launches) then the reference's remedy for what is left (a refit at
+    adapt_delta 0.99).  A deliberately small phase-1 budget forces phase 2 to run."""
+    from bayesynergy_b200.api import screen_to_ess
+    from bayesynergy_b200.dataprep import synthetic_experiment
+    n = 32
+    sds = [prepare(*synthetic_experiment(2000 + k)) for k in range(n)]
+    r = screen_to_ess(sds, target=400.0, chains=4, warmup=300, block=100, max_rounds=2, seed=9, retry_block=200,
+                      retry_rounds=4)
+    assert r["ess"].shape == (n,) and r["summary"].shape == (n, 12, 2) and r["chain_stats"].shape == (n, 4, 8)
+    assert r["reached_phase1"] < n and r["n_retry"] == n - r["reached_phase1"]        # phase 2 ran on exactly the rest
+    assert r["reached"] >= r["reached_phase1"] and r["reached"] >= n - 2
+    assert r["phase2_ms"] > 0 and abs(r["kernel_ms"] - r["phase1_ms"] - r["phase2_ms"]) < 1e-6 * r["kernel_ms"]
+    assert (r["draws_per_chain"] >= 100).all() and np.isfinite(r["summary"][:, Q.index("rVUS_f"), 0]).all()
+    assert ((r["summary"][:, Q.index("rVUS_f"), 0] > 0) & (r["summary"][:, Q.index("rVUS_f"), 0] < 100)).all()
