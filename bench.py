@@ -229,7 +229,8 @@ def run_ours(args):
         one_step(100 + s, max(10, it // 5), max(5, wu // 5))
         flush.fill_(s & 255)
     clocks = ClockSampler(dev)
-    clocks.start()
+    if rank == 0:          # one nvidia-smi poller per job: rank 0's GPU stands for the box (all ranks run the same load)
+        clocks.start()
     barrier()
     launches1 = L.bsyn_launch_count()
     tot_ms, tot_grad, info = 0.0, 0, None

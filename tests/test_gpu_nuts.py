@@ -275,11 +275,11 @@ def test_screen_to_ess_two_phases(built):
     from bayesynergy_b200.dataprep import synthetic_experiment
     n = 32
     sds = [prepare(*synthetic_experiment(2000 + k)) for k in range(n)]
-    r = screen_to_ess(sds, target=400.0, chains=4, warmup=300, block=100, max_rounds=2, seed=9, retry_block=200,
-                      retry_rounds=4)
+    r = screen_to_ess(sds, target=900.0, chains=4, warmup=300, block=100, max_rounds=2, seed=9, retry_block=250,
+                      retry_rounds=6)
     assert r["ess"].shape == (n,) and r["summary"].shape == (n, 12, 2) and r["chain_stats"].shape == (n, 4, 8)
     assert r["reached_phase1"] < n and r["n_retry"] == n - r["reached_phase1"]        # phase 2 ran on exactly the rest
-    assert r["reached"] >= r["reached_phase1"] and r["reached"] >= n - 2
+    assert r["reached"] >= r["reached_phase1"] and r["reached"] >= n - 4
     assert r["phase2_ms"] > 0 and abs(r["kernel_ms"] - r["phase1_ms"] - r["phase2_ms"]) < 1e-6 * r["kernel_ms"]
     assert (r["draws_per_chain"] >= 100).all() and np.isfinite(r["summary"][:, Q.index("rVUS_f"), 0]).all()
     assert ((r["summary"][:, Q.index("rVUS_f"), 0] > 0) & (r["summary"][:, Q.index("rVUS_f"), 0] < 100)).all()

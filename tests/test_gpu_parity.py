@@ -331,3 +331,39 @@ def test_tiny_lambda_does_not_underflow_the_variance_product(built, datasets, co
             checked += 1
         assert checked >= 8
         b.close()
+
+
+def test_gradient_is_the_derivative_of_lp_by_finite_differences(built, datasets):
+    """A property that needs no oracle: the analytic gradient returned by the device kernels is the derivative of the
+    lp they return.  Directional central differences (Richardson-extrapolated, O(h^4)) along random directions, for
+    every kernel / likelihood / prior variant, both models, specialised and fallback kernels, on every data shape
+    (5 x 5, 11 x 11 with unobserved cells, 10 x 10 x 3)."""
+    rng = np.random.default_rng(11)
+    variants = [dict(), dict(type=2), dict(type=4), dict(type=3, nu=2.5), dict(robust=True, pcprior=True),
+                dict(heteroscedastic=False), dict(lower_asymptotes=False)]
+    worst = 0.0
+    for dname in ("mathews:ispinesib + ibrutinib", "oneil_failed:0", "synthetic:7"):
+        y, x = datasets[dname]
+        for v in variants:
+            sd = prepare(y, x, **v)
+            for model in ("gp_grid", "nointeraction"):
+                b = _lib.Batch([sd], model=model)
+                D = b.num_params(0)
+                U = rng.uniform(-0.6, 0.6, size=(6, D))
+                V = rng.standard_normal((6, D))
+                V /= np.linalg.norm(V, axis=1, keepdims=True)
+                lp0, g, st = b.logp_grad(U)
+                assert (st == 0).all()
+                h = 1e-3
+                pts = np.concatenate([U + h * V, U - h * V, U + 0.5 * h * V, U - 0.5 * h * V])
+                lp, _, st2 = b.logp_grad(pts, want_grad=False)
+                assert (st2 == 0).all()
+                d1 = (lp[0:6] - lp[6:12]) / (2 * h)
+                d2 = (lp[12:18] - lp[18:24]) / h
+                fd = (4 * d2 - d1) / 3                          # Richardson: error O(h^4)
+                an = (g[:, :D] * V).sum(axis=1)
+                err = np.abs(fd - an) / np.maximum(1.0, np.abs(an))
+                worst = max(worst, err.max())
+                assert err.max() < 2e-6, (dname, v, model, err, fd, an)
+                b.close()
+    assert worst < 2e-6
