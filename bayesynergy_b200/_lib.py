@@ -57,7 +57,9 @@ class BsynSinks(C.Structure):
                 ("summary", C.POINTER(C.c_double)), ("cpo_mean", C.POINTER(C.c_double)), ("ld_cpo", C.c_int64),
                 ("chain_stats", C.POINTER(C.c_double)), ("inv_metric", C.POINTER(C.c_double)),
                 ("init_u", C.POINTER(C.c_double)), ("f_mean", C.POINTER(C.c_double)), ("ld_f", C.c_int64),
-                ("surfaces", C.POINTER(C.c_double)), ("lpml", C.POINTER(C.c_double)), ("elapsed_ms", C.POINTER(C.c_float))]
+                ("surfaces", C.POINTER(C.c_double)), ("lpml", C.POINTER(C.c_double)),
+                ("bridge_logml", C.POINTER(C.c_double)), ("bridge_niter", C.POINTER(C.c_int32)),
+                ("elapsed_ms", C.POINTER(C.c_float))]
 
 
 class BsynAdviArgs(C.Structure):
@@ -304,7 +306,8 @@ class Batch:
         return out
 
     def sample(self, want_draws=False, want_udraws=False, want_qdraws=True, want_sampler_params=True,
-               want_cpo=False, want_inv_metric=False, want_inits=False, want_f_mean=False, want_surfaces=False, **kw):
+               want_cpo=False, want_inv_metric=False, want_inits=False, want_f_mean=False, want_surfaces=False, want_bridge=False,
+               **kw):
         """Run adaptive NUTS for every experiment x chain in one launch.  Returns a dict of numpy arrays."""
         a = self.sampler_args(**kw)
         ns = (a.iter - a.warmup + a.thin - 1) // a.thin + ((a.warmup + a.thin - 1) // a.thin if a.save_warmup else 0)
@@ -346,6 +349,10 @@ class Batch:
             res["surfaces"] = np.zeros((n, 3, s.ld_f))
             res["lpml"] = np.zeros(n)
             s.surfaces, s.lpml = _dp(res["surfaces"]), _dp(res["lpml"])
+        if want_bridge:            # bridge-sampling log marginal likelihood per experiment, on the device
+            res["bridge_logml"] = np.zeros(n)
+            res["bridge_niter"] = np.zeros(n, dtype=np.int32)
+            s.bridge_logml, s.bridge_niter = _dp(res["bridge_logml"]), _ip(res["bridge_niter"])
         ems = C.c_float()
         s.elapsed_ms = C.pointer(ems)
         ng = C.c_int64()

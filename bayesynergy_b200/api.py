@@ -208,8 +208,10 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
             if st != 0:
                 raise RuntimeError("variational inference failed: " + _VB_ERRORS.get(st, f"status {st}"))
         else:
-            res = b.sample(want_draws=True, want_udraws=bool(bayes_factor), want_surfaces=True, want_inv_metric=True,
-                           want_inits=True, **kw)
+            from .bridge import DEVICE_BRIDGE_MAX_D
+            dev_bridge = bool(bayes_factor) and sd.dim_gp_grid <= DEVICE_BRIDGE_MAX_D
+            res = b.sample(want_draws=True, want_udraws=bool(bayes_factor) and not dev_bridge, want_bridge=dev_bridge,
+                           want_surfaces=True, want_inv_metric=True, want_inits=True, **kw)
             blocks = b.param_blocks(0)
     finally:
         b.close()
@@ -236,8 +238,12 @@ def bayesynergy(y, x, type=3, drug_names=None, experiment_ID=None, units=None, l
         obj.update(vb_info=dict(zip(_lib.VI_NAMES, res["info"][0])), vb_mean=res["mean"][0, :len(param_names(sd))],
                    n_grad=res["n_evals"])
     if bayes_factor:
-        from .bridge import bayes_factor as _bf
-        obj["bayesfactor"] = _bf(sd, res["udraws"][0], kw, device=device)
+        from .bridge import bayes_factor as _bf, bayes_factor_from_logml
+        if dev_bridge:
+            obj["bayesfactor"] = float(bayes_factor_from_logml([sd], res["bridge_logml"], kw, device=device)[0])
+            obj["logml"] = float(res["bridge_logml"][0])
+        else:
+            obj["bayesfactor"] = _bf(sd, res["udraws"][0], kw, device=device)
     return obj
 
 
@@ -312,7 +318,7 @@ def _check_prepare_params(params):
         raise TypeError(f"unknown bayesynergy_params: {unknown}")
 
 
-def _fit_batch(sds, kw, device, max_treedepth, want_samples=False, want_udraws=False):
+def _fit_batch(sds, kw, device, max_treedepth, want_samples=False, want_udraws=False, want_bridge=False):
     """One batched launch over a list of prepared experiments; returns (res, returnCode[n]).
 
     returnCode follows bayesynergy(): 1 where rstan would have warned (divergences, tree depth, R-hat, bulk / tail ESS)
@@ -322,7 +328,8 @@ def _fit_batch(sds, kw, device, max_treedepth, want_samples=False, want_udraws=F
     b = _lib.Batch(sds, model="gp_grid", device=device)
     try:
         res = b.sample(want_qdraws=want_samples, want_sampler_params=want_samples, want_f_mean=True,
-                       want_draws=want_samples, want_surfaces=want_samples, want_udraws=want_udraws, **kw)
+                       want_draws=want_samples, want_surfaces=want_samples, want_udraws=want_udraws,
+                       want_bridge=want_bridge, **kw)
         n_draws = res["n_save"] * res["chain_stats"].shape[1]
         if n_draws <= 8192:         # rank-normalised bulk ESS / R-hat and tail ESS, as rstan >= 2.21 warns on
             ess_syn, rhat_syn, tail_syn = b.bulk_ess("VUS_syn")
@@ -455,7 +462,9 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
         # return_samples keeps every write_array draw on the host (as the reference keeps every stanfit): the launches are
         # then chunked so that a chunk's draws fit comfortably in host memory
         chunk = max(1, int(2e9 // (8 * chains * max(1, iter_ // 2) * 1024))) if return_samples else len(sds)
-        samples, udraws_gp, kw_of = {}, {}, {}
+        samples, udraws_gp, kw_of, lml_gp = {}, {}, {}, {}
+        from .bridge import DEVICE_BRIDGE_MAX_D
+        dev_bridge = want_bf and max(sd.dim_gp_grid for sd in sds) <= DEVICE_BRIDGE_MAX_D
 
         def fit(js, kwj):
             """fit the experiments js (indices into sds) and store their rows / samples"""
@@ -463,14 +472,17 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
             for c0 in range(0, len(js), chunk):
                 part = js[c0:c0 + chunk]
                 res_, rc_ = _fit_batch([sds[j] for j in part], kwj, device, kwj.get("max_treedepth", 10),
-                                       want_samples=return_samples, want_udraws=want_bf)
+                                       want_samples=return_samples, want_udraws=want_bf and not dev_bridge,
+                                       want_bridge=dev_bridge)
                 new_rows = _screen_rows([mine[ok_idx[j]] for j in part], 0, res_, rc_)
                 for i, (r, j) in enumerate(zip(new_rows, part)):
                     r["listID"] = lo + ok_idx[j] + 1
                     rows[ok_idx[j]] = r
                     codes[j] = rc_[i]
                     kw_of[j] = kwj
-                    if want_bf:
+                    if dev_bridge:
+                        lml_gp[j] = res_["bridge_logml"][i]
+                    elif want_bf:
                         udraws_gp[j] = res_["udraws"][i]
                     if return_samples:
                         samples[j] = _screen_sample_object(sds[j], mine[ok_idx[j]], res_, i, params, kwj)
@@ -491,11 +503,16 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
         if want_bf:
             # cfg4: "two models per combination" -- one nointeraction launch over every fitted experiment and one batched
             # log_prob launch per model for all bridge points (bridge.bayes_factor_many)
-            from .bridge import bayes_factor_many
+            # log_prob launch per model for all bridge points; with <= 160 parameters the whole estimator runs on the device
+            # and only the log marginal likelihoods come back (bsyn_sample's bridge_logml sink), else bridge.bayes_factor_many
+            from .bridge import bayes_factor_many, bayes_factor_from_logml
             good = [j for j in range(len(sds)) if rows[ok_idx[j]]["returnCode"] != 2]
             for kwj in {id(kw_of[j]): kw_of[j] for j in good}.values():
                 js = [j for j in good if kw_of[j] is kwj]
-                bfs = bayes_factor_many([sds[j] for j in js], [udraws_gp[j] for j in js], kwj, device=device, seed=seed)
+                if dev_bridge:
+                    bfs = bayes_factor_from_logml([sds[j] for j in js], [lml_gp[j] for j in js], kwj, device=device)
+                else:
+                    bfs = bayes_factor_many([sds[j] for j in js], [udraws_gp[j] for j in js], kwj, device=device, seed=seed)
                 for j, v in zip(js, bfs):
                     rows[ok_idx[j]]["Bayes Factor"] = float(v)
                     if return_samples and j in samples:

@@ -163,6 +163,21 @@ def bayes_factor_many(sds, udraws_gp, sampler_kw, device=0, seed=1, chunk=256):
     return np.exp(lml1 - lml0)
 
 
+DEVICE_BRIDGE_MAX_D = 160      # BRIDGE_MAX_D of csrc/bsyn_bridge.cuh: the proposal covariance lives in shared memory
+
+
+def bayes_factor_from_logml(sds, logml_gp, sampler_kw, device=0):
+    """Bayes factors when the gp_grid launch already produced its bridge-sampling log marginal likelihoods on the device
+    (bsyn_sample's `bridge_logml` sink): ONE nointeraction launch with the same sink, nothing but 2 n doubles comes back.
+    Returns bf[n]."""
+    b0 = _lib.Batch(sds, model="nointeraction", device=device)
+    try:
+        res0 = b0.sample(want_bridge=True, want_qdraws=False, want_sampler_params=False, **sampler_kw)
+    finally:
+        b0.close()
+    return np.exp(np.asarray(logml_gp) - res0["bridge_logml"])
+
+
 def bayes_factor(sd, udraws_full, sampler_kw, device=0, seed=1):
     """BF of the interaction model over the no-interaction model for one experiment (R/bayesynergy.R:332-337)."""
     return float(bayes_factor_many([sd], [udraws_full], sampler_kw, device=device, seed=seed)[0])

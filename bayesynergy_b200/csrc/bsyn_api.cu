@@ -15,6 +15,7 @@
 
 #include "bsyn_nuts.cuh"
 #include "bsyn_post.cuh"
+#include "bsyn_bridge.cuh"
 #include "bsyn_kernels_decl.h"
 
 using namespace bsyn;
@@ -771,6 +772,46 @@ extern "C" int bsyn_sample_device(bsyn_batch *b, const bsyn_sampler_args *args, 
     return BSYN_OK;
 }
 
+// Bridge-sampling log marginal likelihood of every problem from the unconstrained draws d_udraws[n][chains][ns][ld_u]
+// resident on the device (bsyn_bridge.cuh): proposal fit + point list, ONE batched value-only log_prob launch, iterative scheme.
+static int device_bridge(bsyn_batch *b, const double *d_udraws, long long ld_u, int chains, int ns, uint64_t seed, double *logml,
+                         int32_t *niter)
+{
+    if (b->maxD > BRIDGE_MAX_D) return fail(BSYN_ERR_UNSUPPORTED, "bridge sampling on the device supports up to 160 parameters");
+    const int n_fit = ns / 2, n_it = ns - n_fit;
+    if (n_fit < 8 || n_it < 8) return fail(BSYN_ERR_ARG, "bridge sampling needs at least 16 saved draws per chain");
+    if ((long long)chains * n_it > BULK_MAX_DRAWS) return fail(BSYN_ERR_UNSUPPORTED, "bridge sampling: more than 8192 draws in the second halves");
+    const size_t npt = (size_t)chains * n_it * 2, n = (size_t)b->n;
+    const int ldp = b->maxD;
+    DevBuf<double> d_pts, d_lq, d_lp, d_lml;
+    DevBuf<int> d_idx, d_st, d_nit;
+    if (d_pts.alloc(n * npt * ldp) != cudaSuccess || d_lq.alloc(n * npt) != cudaSuccess || d_lp.alloc(n * npt) != cudaSuccess ||
+        d_lml.alloc(n) != cudaSuccess || d_idx.alloc(n * npt) != cudaSuccess || d_st.alloc(n * npt) != cudaSuccess || d_nit.alloc(n) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BSYN_ERR_ALLOC, "bridge sampling: device buffers");
+    }
+    BridgeParams bp{};
+    bp.udraws = d_udraws; bp.ld_u = ld_u; bp.chains = chains; bp.ns = ns; bp.seed = seed;
+    bp.pts = d_pts; bp.ld_pts = ldp; bp.pidx = d_idx; bp.lq = d_lq; bp.lp = d_lp; bp.lp_status = d_st; bp.logml = d_lml; bp.niter = d_nit;
+    bp.maxiter = 1000; bp.tol = 1e-10;
+    const size_t sb1 = bridge_prep_smem(b->maxD), sb2 = bridge_iter_smem(chains * n_it, b->maxD);
+    CK(cudaFuncSetAttribute(bridge_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb1));
+    CK(cudaFuncSetAttribute(bridge_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb2));
+    const int grid = std::max(1, std::min(b->n, b->num_sms * 2));
+    bridge_prep_kernel<<<std::max(1, std::min(b->n, b->num_sms)), BRIDGE_THREADS, sb1, b->stream>>>(b->d_descs, b->n, bp);
+    ++g_launches;
+    CK(cudaGetLastError());
+    int rc = launch_logp(b, (int)(n * npt), d_idx, d_pts, ldp, 1, d_lp, nullptr, d_st, nullptr, 0, b->stream);
+    if (rc) return rc;
+    bridge_iter_kernel<<<grid, BRIDGE_THREADS, sb2, b->stream>>>(b->d_descs, b->n, bp);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(logml, d_lml, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+    if (niter) CK(cudaMemcpyAsync(niter, d_nit, sizeof(int) * n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return BSYN_OK;
+}
+
 extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const bsyn_sample_sinks *sinks, int64_t *total_grad_evals)
 {
     if (!b || !args || !sinks) return fail(BSYN_ERR_ARG, "bsyn_sample: null argument");
@@ -809,8 +850,9 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
         ds.ld_draws = sinks->draws ? sinks->ld_draws : b->maxOut;
         if ((rc = alloc0(&ds.draws, nrows * ds.ld_draws, "draws (use the summary / surfaces sinks for large screens)"))) return rc;
     }
-    if (sinks->udraws) {
-        ds.ld_u = sinks->ld_udraws;
+    if (sinks->bridge_logml && args->save_warmup) return fail(BSYN_ERR_ARG, "bsyn_sample: bridge_logml needs save_warmup = 0");
+    if (sinks->udraws || sinks->bridge_logml) {
+        ds.ld_u = sinks->udraws ? sinks->ld_udraws : b->maxD;
         if ((rc = alloc0(&ds.udraws, nrows * ds.ld_u, "udraws"))) return rc;
     }
     if (sinks->cpo_mean) {
@@ -886,6 +928,8 @@ extern "C" int bsyn_sample(bsyn_batch *b, const bsyn_sampler_args *args, const b
             }
         }
         if (e != cudaSuccess) rc = fail(BSYN_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
+        if (rc == BSYN_OK && sinks->bridge_logml)
+            rc = device_bridge(b, ds.udraws, ds.ld_u, args->chains, (int)n_save, args->seed ^ 0x5bd1e995u, sinks->bridge_logml, sinks->bridge_niter);
     }
     return rc;
 }

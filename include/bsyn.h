@@ -195,6 +195,14 @@ typedef struct bsyn_sample_sinks {
      * Up to 8192 pooled sampling draws per problem. */
     double *surfaces;
     double *lpml;
+    /* bridge-sampling log marginal likelihood of every problem (Meng & Wong 1996, normal proposal: what
+     * bridgesampling::bridge_sampler(fit) returns as $logml, R/bayesynergy.R:332-335), computed on the device from the
+     * unconstrained draws of this call, which stay in HBM: proposal fit on the first half of every chain, ONE batched
+     * log_prob launch at the second-half draws and the proposal draws of all problems, iterative scheme.  [n_problems];
+     * bridge_niter (may be NULL): iterations of the scheme.  Needs save_warmup = 0, <= 160 parameters, <= 8192 draws in
+     * the second halves.  The Bayes factor of R/bayesynergy.R:336 is exp(logml(gp_grid batch) - logml(nointeraction batch)). */
+    double *bridge_logml;
+    int32_t *bridge_niter;
     /* device time of the sampling launch in ms (attr "elapsed_time" is this, split by the leapfrog counts of chain_stats) */
     float *elapsed_ms;
 } bsyn_sample_sinks;

@@ -216,3 +216,32 @@ def test_screen_bayes_factor_and_samples(built):
     # (bridge sampling in 115 dimensions from 1200 draws is noisy: the strict check is the same-draws one above)
     d = np.abs(np.log(bfs) - ref)
     assert np.median(d) < 1.5 and d.max() < 8.0, (np.log(bfs), ref)
+
+
+@pytest.mark.gpu
+def test_device_bridge_matches_host_estimator(built, datasets):
+    """The bridge-sampling estimator run entirely on the device (bsyn_sample's bridge_logml sink: proposal fit, batched
+    log_prob, iterative scheme) against the host estimator of bridge.py on the SAME posterior draws.  The two differ only
+    in their proposal draws (Philox on the device, numpy on the host), i.e. by Monte Carlo error of the estimator."""
+    from bayesynergy_b200 import _lib
+    from bayesynergy_b200.bridge import bridge_logml_many
+    from bayesynergy_b200.dataprep import prepare, synthetic_experiment
+    y, x = datasets["mathews:ispinesib + ibrutinib"]
+    sds = [prepare(y, x), prepare(*datasets["mathews:canertinib + ibrutinib"])]
+    for model, tol in (("gp_grid", 0.25), ("nointeraction", 0.05)):
+        b = _lib.Batch(sds, model=model)
+        res = b.sample(chains=4, iter=2000, warmup=1000, seed=5, want_udraws=True, want_bridge=True, want_qdraws=False)
+        host, _ = bridge_logml_many(b, [res["udraws"][k] for k in range(2)], seed=3)
+        host2, _ = bridge_logml_many(b, [res["udraws"][k] for k in range(2)], seed=4)      # the host's own proposal noise
+        b.close()
+        dev = res["bridge_logml"]
+        assert np.isfinite(dev).all() and (res["bridge_niter"] > 0).all() and (res["bridge_niter"] < 1000).all()
+        assert np.abs(dev - host).max() < max(tol, 4 * np.abs(host - host2).max()), (model, dev, host, host2)
+    # 10 x 10 grid (D = 115): one batched launch over several experiments
+    sds = [prepare(*synthetic_experiment(40 + k)) for k in range(4)]
+    b = _lib.Batch(sds)
+    res = b.sample(chains=4, iter=1000, warmup=500, seed=8, want_udraws=True, want_bridge=True, want_qdraws=False)
+    host, _ = bridge_logml_many(b, [res["udraws"][k] for k in range(4)], seed=3)
+    b.close()
+    assert np.isfinite(res["bridge_logml"]).all()
+    assert np.abs(res["bridge_logml"] - host).max() < 2.0, (res["bridge_logml"], host)     # 115 dimensions, 2000 draws: noisy
