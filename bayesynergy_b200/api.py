@@ -502,7 +502,6 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
             tries += 1
         if want_bf:
             # cfg4: "two models per combination" -- one nointeraction launch over every fitted experiment and one batched
-            # log_prob launch per model for all bridge points (bridge.bayes_factor_many)
             # log_prob launch per model for all bridge points; with <= 160 parameters the whole estimator runs on the device
             # and only the log marginal likelihoods come back (bsyn_sample's bridge_logml sink), else bridge.bayes_factor_many
             from .bridge import bayes_factor_many, bayes_factor_from_logml
