@@ -118,7 +118,7 @@ def test_synergyscreen_sampling_retry_raises_adapt_delta(monkeypatch, built):
     from bayesynergy_b200 import api
     seen = []
 
-    def fake_fit(sds, kw, device, max_treedepth, want_samples=False, want_udraws=False):
+    def fake_fit(sds, kw, device, max_treedepth, **sinks):
         seen.append((len(sds), kw["adapt_delta"]))
         n = len(sds)
         rc = np.array([0, 1, 0]) if len(seen) == 1 else np.zeros(n, dtype=int)
