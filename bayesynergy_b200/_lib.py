@@ -23,7 +23,7 @@ EXPORTS = [
     "bsyn_batch_create", "bsyn_batch_destroy", "bsyn_last_error", "bsyn_version", "bsyn_num_params",
     "bsyn_num_outputs", "bsyn_num_param_blocks", "bsyn_param_block", "bsyn_max_params", "bsyn_max_outputs", "bsyn_num_problems", "bsyn_logp_grad",
     "bsyn_logp_grad_device", "bsyn_write_array", "bsyn_unconstrain", "bsyn_sampler_defaults", "bsyn_sample",
-    "bsyn_sample_device", "bsyn_ess", "bsyn_bulk_ess", "bsyn_sample_to_ess", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare", "bsyn_output_name",
+    "bsyn_sample_device", "bsyn_ess", "bsyn_bulk_ess", "bsyn_sample_to_ess", "bsyn_ess_target_defaults", "bsyn_launch_count", "bsyn_advi_defaults", "bsyn_advi", "bsyn_prepare", "bsyn_output_name",
 ]
 VI_NAMES = ["status", "eta", "iterations", "elbo", "converged", "n_grad", "n_lp", "_reserved"]
 
@@ -60,6 +60,16 @@ class BsynSinks(C.Structure):
                 ("surfaces", C.POINTER(C.c_double)), ("lpml", C.POINTER(C.c_double)),
                 ("bridge_logml", C.POINTER(C.c_double)), ("bridge_niter", C.POINTER(C.c_int32)),
                 ("elapsed_ms", C.POINTER(C.c_float))]
+
+
+class BsynEssTarget(C.Structure):
+    _fields_ = [("target_ess", C.c_double), ("q1", C.c_int32), ("q2", C.c_int32), ("max_rounds", C.c_int32),
+                ("retry_adapt_delta", C.c_double), ("retry_warmup", C.c_int32), ("retry_rounds", C.c_int32)]
+
+
+class BsynEssRun(C.Structure):
+    _fields_ = [("total_grad_evals", C.c_int64), ("elapsed_ms", C.c_float), ("phase1_ms", C.c_float),
+                ("rounds", C.c_int32), ("n_retried", C.c_int32)]
 
 
 class BsynAdviArgs(C.Structure):
@@ -116,9 +126,10 @@ def load():
                                      C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.bsyn_ess.argtypes = [vp, C.c_int32, dp, dp]
     L.bsyn_bulk_ess.argtypes = [vp, C.c_int32, dp, dp, dp]
-    L.bsyn_sample_to_ess.argtypes = [vp, C.POINTER(BsynSamplerArgs), C.c_double, C.c_int32, C.c_int32, C.c_int32,
-                                     C.POINTER(BsynSinks), dp, ip, C.POINTER(C.c_int64), C.POINTER(C.c_float),
-                                     C.POINTER(C.c_int32)]
+    L.bsyn_ess_target_defaults.argtypes = [C.POINTER(BsynEssTarget)]
+    L.bsyn_ess_target_defaults.restype = None
+    L.bsyn_sample_to_ess.argtypes = [vp, C.POINTER(BsynSamplerArgs), C.POINTER(BsynEssTarget), C.POINTER(BsynSinks), dp, ip,
+                                     C.POINTER(BsynEssRun)]
     i32p = C.POINTER(C.c_int32)
     L.bsyn_prepare.argtypes = [dp, dp, C.c_int32, C.c_int32, dp, i32p, dp, i32p, dp, ip, i32p, i32p, i32p]
     L.bsyn_output_name.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
@@ -401,16 +412,22 @@ class Batch:
                "bsyn_sample_device")
         return ng.value, ms.value
 
-    def sample_to_ess(self, target=400.0, q=("VUS_syn", "VUS_ant"), block=150, max_rounds=8, want_summary=False,
-                      want_qdraws=False, **kw):
+    def sample_to_ess(self, target=400.0, q=("VUS_syn", "VUS_ant"), block=150, max_rounds=6, retry_rounds=6,
+                      retry_adapt_delta=0.99, retry_warmup=150, want_summary=False, want_qdraws=False, **kw):
         """Sample every experiment until min over `q` of its rank-normalised bulk ESS reaches `target`
         (bsyn_sample_to_ess): warm-up + `block` draws per chain, then extension launches of `block` draws over the
-        experiments still below the target.  kw: sampler arguments (chains, warmup, seed, adapt_delta ...)."""
+        experiments still below the target (phase 1, up to max_rounds launches); what is left re-adapts its step size to
+        `retry_adapt_delta` and is extended up to `retry_rounds` more times (phase 2).  kw: sampler arguments."""
         kw = dict(kw)
         kw.setdefault("warmup", 1000)
         kw["iter"] = kw["warmup"] + block
         a = self.sampler_args(**kw)
-        n, ch, ld = self.n, a.chains, block * max_rounds
+        t = BsynEssTarget()
+        load().bsyn_ess_target_defaults(C.byref(t))
+        qi = [Q_NAMES.index(x) if isinstance(x, str) else int(x) for x in q]
+        t.target_ess, t.q1, t.q2, t.max_rounds = float(target), qi[0], qi[1], max_rounds
+        t.retry_adapt_delta, t.retry_warmup, t.retry_rounds = retry_adapt_delta, retry_warmup, retry_rounds
+        n, ch, ld = self.n, a.chains, block * (max_rounds + retry_rounds)
         s = BsynSinks()
         res = {}
         if want_summary:
@@ -423,11 +440,11 @@ class Batch:
             s.qdraws = _dp(res["qdraws"])
         ess = np.empty(n)
         nd = np.empty(n, dtype=np.int32)
-        ng, ms, rounds = C.c_int64(), C.c_float(), C.c_int32()
-        qi = [Q_NAMES.index(x) if isinstance(x, str) else int(x) for x in q]
-        _check(load().bsyn_sample_to_ess(self.h, C.byref(a), float(target), qi[0], qi[1], max_rounds, C.byref(s), _dp(ess),
-                                         _ip(nd), C.byref(ng), C.byref(ms), C.byref(rounds)), "bsyn_sample_to_ess")
-        res.update(ess=ess, draws_per_chain=nd, n_grad=ng.value, kernel_ms=ms.value, rounds=rounds.value)
+        run = BsynEssRun()
+        _check(load().bsyn_sample_to_ess(self.h, C.byref(a), C.byref(t), C.byref(s), _dp(ess), _ip(nd), C.byref(run)),
+               "bsyn_sample_to_ess")
+        res.update(ess=ess, draws_per_chain=nd, n_grad=run.total_grad_evals, kernel_ms=run.elapsed_ms,
+                   phase1_ms=run.phase1_ms, rounds=run.rounds, n_retried=run.n_retried)
         return res
 
     def bulk_ess(self, q):

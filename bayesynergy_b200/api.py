@@ -538,35 +538,48 @@ def synergyscreen(experiments, return_samples=False, max_retries=3, bayesynergy_
 
 
 def screen_to_ess(sds, target=400.0, batch=None, device=0, chains=4, warmup=1000, block=150, max_rounds=6, seed=1,
-                  adapt_delta=0.9, retry_adapt_delta=0.99, retry_block=300, retry_rounds=6, want_summary=True):
+                  adapt_delta=0.9, retry="refit", retry_adapt_delta=0.99, retry_rounds=6, retry_block=300, retry_warmup=150,
+                  want_summary=True):
     """north_star's target run: sample every prepared experiment until min(bulk-ESS(VUS_syn), bulk-ESS(VUS_ant)) >=
-    `target` (rank-normalised, on the device).
+    `target` (rank-normalised, on the device; bsyn_sample_to_ess).
 
-    Phase 1 (bsyn_sample_to_ess): warm-up + `block` draws per chain for everything, then extension launches over the
-    experiments still below the target -- chains resume from their adapted state -- up to `max_rounds` launches.
-    Phase 2, the reference's remedy for what is left (R/synergyscreen.R:149-171: refit with adapt_delta = 0.99): the few
-    experiments still below the target (divergent / funnel-shaped posteriors) are refitted from scratch in one small
-    batch with `retry_adapt_delta` and extended the same way.
+    Phase 1: warm-up + `block` draws per chain for everything, then extension launches over the experiments still below
+    the target -- chains resume from their adapted state -- up to `max_rounds` launches.
+    Phase 2, the reference's remedy for what is left (R/synergyscreen.R:149-171: adapt_delta = 0.99), `retry_rounds`
+    launches at most, in one of two forms:
+      retry="refit"  (what the reference does) the experiments still below the target are refitted FROM SCRATCH in one
+                     small batch at `retry_adapt_delta` (new initial values, full warm-up, blocks of `retry_block`); the
+                     fit with the larger ESS is kept.  Slower (the small batch is latency-bound), reaches more of them:
+                     a fresh start also re-draws which mode each chain of a multimodal posterior falls into.
+      retry="resume" inside the same bsyn_sample_to_ess call: their chains resume, re-adapt the STEP SIZE to
+                     `retry_adapt_delta` for `retry_warmup` iterations (metric kept) and append blocks; earlier draws stay
+                     pooled with the new ones.  Cheaper; chains stuck in different modes stay there (R-hat > 1.05).
+      retry=None     no phase 2.
     `batch`: an existing _lib.Batch of `sds` (kept open); else one is created and closed here.
-    Returns dict(ess, draws_per_chain, summary, chain_stats, n_grad, kernel_ms, rounds, n_retry, reached)."""
+    Returns dict(ess, draws_per_chain, summary, chain_stats, n_grad, kernel_ms, phase1_ms, phase2_ms, rounds, n_retry,
+    reached)."""
+    if retry not in ("refit", "resume", None):
+        raise ValueError('retry must be "refit", "resume" or None')
     own = batch is None
     b = _lib.Batch(sds, device=device) if own else batch
     try:
         r = b.sample_to_ess(target=target, block=block, max_rounds=max_rounds, chains=chains, warmup=warmup, seed=seed,
-                            adapt_delta=adapt_delta, want_summary=want_summary)
+                            adapt_delta=adapt_delta, want_summary=want_summary,
+                            retry_rounds=retry_rounds if retry == "resume" else 0, retry_adapt_delta=retry_adapt_delta,
+                            retry_warmup=retry_warmup)
     finally:
         if own:
             b.close()
     ess, nd = r["ess"].copy(), r["draws_per_chain"].copy()
-    out = dict(ess=ess, draws_per_chain=nd, n_grad=r["n_grad"], kernel_ms=r["kernel_ms"], rounds=r["rounds"], n_retry=0,
-               summary=r.get("summary"), chain_stats=r.get("chain_stats"), phase1_ms=r["kernel_ms"], phase2_ms=0.0,
-               reached_phase1=int((ess >= target).sum()))
+    out = dict(ess=ess, draws_per_chain=nd, n_grad=r["n_grad"], kernel_ms=r["kernel_ms"], rounds=r["rounds"],
+               n_retry=int(r["n_retried"]), summary=r.get("summary"), chain_stats=r.get("chain_stats"),
+               phase1_ms=r["phase1_ms"], phase2_ms=r["kernel_ms"] - r["phase1_ms"], retry=retry)
     left = np.where(~(ess >= target))[0]
-    if len(left) and retry_rounds > 0:
+    if retry == "refit" and len(left) and retry_rounds > 0:
         b2 = _lib.Batch([sds[k] for k in left], device=device)
         try:
-            r2 = b2.sample_to_ess(target=target, block=retry_block, max_rounds=retry_rounds, chains=chains, warmup=warmup,
-                                  seed=seed + 7777, adapt_delta=retry_adapt_delta, want_summary=want_summary)
+            r2 = b2.sample_to_ess(target=target, block=retry_block, max_rounds=retry_rounds, retry_rounds=0, chains=chains,
+                                  warmup=warmup, seed=seed + 7777, adapt_delta=retry_adapt_delta, want_summary=want_summary)
         finally:
             b2.close()
         better = np.nan_to_num(r2["ess"], nan=-1.0) > np.nan_to_num(ess[left], nan=-1.0)

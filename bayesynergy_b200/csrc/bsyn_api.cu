@@ -1114,41 +1114,62 @@ static __global__ void select_below_kernel(const double *__restrict__ e1, const 
     }
 }
 
-extern "C" int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, double target_ess, int32_t q1, int32_t q2,
-                                  int32_t max_rounds, const bsyn_sample_sinks *sinks, double *ess, int32_t *draws_per_chain,
-                                  int64_t *total_grad_evals, float *elapsed_ms, int32_t *rounds)
+extern "C" void bsyn_ess_target_defaults(bsyn_ess_target *t)
 {
-    if (!b || !args) return fail(BSYN_ERR_ARG, "bsyn_sample_to_ess: null argument");
+    t->target_ess = 400.0; t->q1 = BSYN_Q_VUS_SYN; t->q2 = BSYN_Q_VUS_ANT; t->max_rounds = 6;
+    t->retry_adapt_delta = 0.99; t->retry_warmup = 150; t->retry_rounds = 6;
+}
+
+extern "C" int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, const bsyn_ess_target *tg,
+                                  const bsyn_sample_sinks *sinks, double *ess, int32_t *draws_per_chain, bsyn_ess_run *run)
+{
+    if (!b || !args || !tg) return fail(BSYN_ERR_ARG, "bsyn_sample_to_ess: null argument");
     if (int rc0 = check_sampler_args(args)) return rc0;
-    const int block = args->iter - args->warmup;
+    const int block = args->iter - args->warmup, q1 = tg->q1, q2 = tg->q2;
+    const int max_rounds = tg->max_rounds, retry_rounds = std::max(0, tg->retry_rounds), R = max_rounds + retry_rounds;
+    const double target_ess = tg->target_ess;
     if (args->thin != 1 || args->save_warmup || block < 8 || max_rounds < 1 || q1 < 0 || q1 >= BSYN_NQ || q2 < 0 || q2 >= BSYN_NQ ||
         !(target_ess > 0))
         return fail(BSYN_ERR_ARG, "bsyn_sample_to_ess: needs thin = 1, save_warmup = 0, iter - warmup >= 8, max_rounds >= 1");
-    if ((long long)block * max_rounds * args->chains > BULK_MAX_DRAWS)
-        return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample_to_ess: chains x (iter - warmup) x max_rounds exceeds 8192 pooled draws");
-    if (sinks && (sinks->draws || sinks->udraws || sinks->cpo_mean || sinks->inv_metric))
+    if (retry_rounds > 0 && (!(tg->retry_adapt_delta > 0 && tg->retry_adapt_delta < 1) || tg->retry_warmup < 20))
+        return fail(BSYN_ERR_ARG, "bsyn_sample_to_ess: retry_adapt_delta must lie in (0,1) and retry_warmup must be >= 20");
+    if ((long long)block * R * args->chains > BULK_MAX_DRAWS)
+        return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample_to_ess: chains x (iter - warmup) x (max_rounds + retry_rounds) exceeds 8192 pooled draws");
+    if (sinks && (sinks->draws || sinks->udraws || sinks->cpo_mean || sinks->inv_metric || sinks->init_u || sinks->f_mean || sinks->surfaces ||
+                  sinks->lpml || sinks->bridge_logml))
         return fail(BSYN_ERR_UNSUPPORTED, "bsyn_sample_to_ess: only the qdraws / sampler_params / summary / chain_stats sinks");
     CK(cudaSetDevice(b->device));
-    const int n = b->n, ld_save = block * max_rounds;
+    const int n = b->n, ld_save = block * R;
     DevBuf<double> d_e1, d_e2, d_ess;
     DevBuf<int> d_lists, d_cnt;
     CK(d_e1.alloc(4 * (size_t)n)); CK(d_e2.alloc(4 * (size_t)n)); CK(d_ess.alloc(n));
     CK(d_lists.alloc(2 * (size_t)n)); CK(d_cnt.alloc(1));
     if (!b->d_nsp) CK(cudaMalloc(&b->d_nsp, sizeof(int) * n));
-    const size_t ebytes = bulk_ess_smem_bytes(block * max_rounds * args->chains);
+    const size_t ebytes = bulk_ess_smem_bytes(block * R * args->chains);
     CK(cudaFuncSetAttribute(bulk_ess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ebytes));
     DevSinks ds;
     int64_t tot_grad = 0;
-    float tot_ms = 0.f;
-    int n_active = n, r = 0;
+    float tot_ms = 0.f, phase1_ms = 0.f;
+    int n_active = n, r = 0, n_retried = 0;
     const int *list = nullptr;       // device list of the active problems (null = all)
     for (;; ++r) {
         bsyn_sampler_args a = *args;
         RunPlan plan;
-        plan.ld_save = ld_save; plan.isave0 = r * block; plan.resume_out = (r + 1 < max_rounds); plan.summary = false;
+        plan.ld_save = ld_save; plan.isave0 = r * block; plan.resume_out = (r + 1 < R); plan.summary = false;
         if (r > 0) {
             a.warmup = 0; a.iter = block; a.seed = args->seed + 0x9E3779B97F4A7C15ull * (uint64_t)r;
             plan.resume_in = true; plan.d_list = list; plan.n_list = n_active;
+        }
+        if (r == max_rounds) {
+            // phase 2, the reference's remedy for fits with warnings (R/synergyscreen.R:149-157: adapt_delta = 0.99): the chains of
+            // what is still below the target resume, re-adapt their STEP SIZE to the stricter adapt_delta for retry_warmup
+            // iterations (init_stepsize + dual averaging; the adapted metric is kept: no metric window), then append blocks
+            a.warmup = tg->retry_warmup; a.iter = tg->retry_warmup + block; a.adapt_delta = tg->retry_adapt_delta;
+            a.adapt_init_buffer = tg->retry_warmup; a.adapt_window = 0; a.adapt_term_buffer = 0;
+            n_retried = n_active;
+            phase1_ms = tot_ms;
+        } else if (r > max_rounds) {
+            a.adapt_delta = tg->retry_adapt_delta;
         }
         int64_t ng = 0;
         float ms = 0.f;
@@ -1178,9 +1199,10 @@ extern "C" int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, 
         CK(cudaEventElapsedTime(&ms2, e0, e1));
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         tot_ms += ms + ms2;
-        if (n_next == 0 || r + 1 >= max_rounds) { ++r; break; }
+        if (n_next == 0 || r + 1 >= R) { ++r; break; }
         list = list_out; n_active = n_next;
     }
+    if (r <= max_rounds) phase1_ms = tot_ms;
     b->last_chains = args->chains; b->last_nsave = ld_save; b->last_nskip = 0; b->last_var_ns = true;
     {   // summaries over each problem's own number of draws
         int rc;
@@ -1202,8 +1224,6 @@ extern "C" int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, 
     }
     CK(cudaStreamSynchronize(b->stream));
     if (draws_per_chain) for (int k = 0; k < n; ++k) draws_per_chain[k] = nsp[k];
-    if (total_grad_evals) *total_grad_evals = tot_grad;
-    if (elapsed_ms) *elapsed_ms = tot_ms;
-    if (rounds) *rounds = r;
+    if (run) { run->total_grad_evals = tot_grad; run->elapsed_ms = tot_ms; run->phase1_ms = phase1_ms; run->rounds = r; run->n_retried = n_retried; }
     return BSYN_OK;
 }

@@ -609,9 +609,9 @@ __global__ void __launch_bounds__(32 * NW) __maxnreg__(MINB) nuts_kernel(const F
                 eps = sp.stepsize0;
                 need_istep = 1;            // base_hmc::init_stepsize runs before the first transition ...
                 if (sp.init_u) store_user_vec<CPL>(F, pd, cell, q, sp.init_u + cg * sp.ld_im);
-                if (sp.resume_in && init_try == 0) {   // ... unless the chain resumes with its adapted step size
-                    eps = sp.resume[cg * sp.resume_stride + 2 * VS];
-                    need_istep = 0;
+                if (sp.resume_in && init_try == 0) {   // ... unless the chain resumes with its adapted step size; a resumed
+                    eps = sp.resume[cg * sp.resume_stride + 2 * VS];   // chain that re-adapts (warmup > 0: a stricter adapt_delta)
+                    need_istep = (nw > 0) ? 1 : 0;                     // restarts the dual averaging from it, as Stan does
                 }
                 istep_tag = 0xFFFFFF00u;
                 mu = 0.0; sbar = 0.0; xbar = 0.0; cnt = 0.0; wn = 0.0;

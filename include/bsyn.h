@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BSYN_VERSION 200
+#define BSYN_VERSION 201
 
 enum {
     BSYN_OK = 0,
@@ -220,20 +220,37 @@ int bsyn_sample_device(bsyn_batch *b, const bsyn_sampler_args *args, int64_t *to
                        float *elapsed_ms, const double **d_qdraws, const double **d_sampler_params,
                        const double **d_summary);
 
-/* ESS-target control (north_star's target: every combination sampled to an ESS of 400): runs the sampler with `args`
- * (warm-up + a first block of iter - warmup sampling draws), computes on the device the rank-normalised bulk ESS of
- * the generated scalars q1 and q2 (e.g. BSYN_Q_VUS_SYN, BSYN_Q_VUS_ANT) for every problem, and relaunches the sampler
- * over the problems whose min(ESS) is still below `target_ess`: their chains resume from the last position, adapted
- * step size and (diagonal) metric and append another block of draws, up to `max_rounds` launches.  This is the
- * batched form of the reference's rerun of `failed` experiments (R/synergyscreen.R:97-103): a smaller launch per
- * round, nothing refitted from scratch.  diag_e only; chains * (iter - warmup) * max_rounds <= 8192.
- * Sinks: qdraws / sampler_params use a row stride of (iter - warmup) * max_rounds draws per chain (unused slots 0),
- * summary is over each problem's own draws; the draws / udraws / cpo_mean / inv_metric sinks must be NULL.
- * ess[n_problems] (min over q1, q2 at the problem's last check), draws_per_chain[n_problems], rounds: may be NULL.
- * elapsed_ms: device time of all sampler and ESS launches. */
-int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, double target_ess, int32_t q1, int32_t q2,
-                       int32_t max_rounds, const bsyn_sample_sinks *sinks, double *ess, int32_t *draws_per_chain,
-                       int64_t *total_grad_evals, float *elapsed_ms, int32_t *rounds);
+/* ESS-target control (north_star's target: every combination sampled to an ESS of 400).
+ * Phase 1: the sampler runs with `args` (warm-up + a first block of iter - warmup sampling draws); on the device the
+ * rank-normalised bulk ESS of the generated scalars q1 and q2 (e.g. BSYN_Q_VUS_SYN, BSYN_Q_VUS_ANT) is computed for every
+ * problem, and the sampler is relaunched over the problems whose min(ESS) is still below `target_ess`: their chains RESUME
+ * (last position, adapted step size and diagonal metric) and append another block, up to `max_rounds` launches -- the
+ * batched form of the reference's rerun of `failed` experiments (R/synergyscreen.R:97-103), nothing refitted from scratch.
+ * Phase 2, the reference's remedy for fits with warnings (adapt_delta = 0.99, R/synergyscreen.R:149-157): what is still
+ * below the target resumes once more, re-adapts its STEP SIZE to `retry_adapt_delta` for `retry_warmup` iterations
+ * (init_stepsize + dual averaging; the adapted metric is kept) and is extended up to `retry_rounds` more times
+ * (retry_rounds = 0: no phase 2).  diag_e only; chains * (iter - warmup) * (max_rounds + retry_rounds) <= 8192. */
+typedef struct bsyn_ess_target {
+    double target_ess;           /* 400 */
+    int32_t q1, q2;              /* BSYN_Q_VUS_SYN, BSYN_Q_VUS_ANT */
+    int32_t max_rounds;          /* 6: launches of phase 1 */
+    double retry_adapt_delta;    /* 0.99 */
+    int32_t retry_warmup;        /* 150 */
+    int32_t retry_rounds;        /* 6 */
+} bsyn_ess_target;
+typedef struct bsyn_ess_run {
+    int64_t total_grad_evals;
+    float elapsed_ms;            /* device time of all sampler and ESS launches */
+    float phase1_ms;
+    int32_t rounds;              /* sampler launches made */
+    int32_t n_retried;           /* problems that entered phase 2 */
+} bsyn_ess_run;
+void bsyn_ess_target_defaults(bsyn_ess_target *t);
+/* Sinks: qdraws / sampler_params use a row stride of (iter - warmup) * (max_rounds + retry_rounds) draws per chain (unused
+ * slots 0), summary is over each problem's own draws; every other sink must be NULL.  ess[n_problems] (min over q1, q2 at
+ * the problem's last check), draws_per_chain[n_problems], run: may be NULL. */
+int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, const bsyn_ess_target *target,
+                       const bsyn_sample_sinks *sinks, double *ess, int32_t *draws_per_chain, bsyn_ess_run *run);
 
 /* Rank-normalisation-free split-chain bulk ESS (Geyer initial positive sequence on the pooled split chains,
  * as rstan::summary's n_eff) of generated scalar `q` for every problem, computed on the device from the

@@ -87,7 +87,11 @@ int main(int argc, char **argv)
         CHECK(bsyn_unconstrain(NULL, 0, d1, d1) == BSYN_ERR_ARG);
         CHECK(bsyn_sample(NULL, &sa, &sk, &ng) == BSYN_ERR_ARG);
         CHECK(bsyn_sample_device(NULL, &sa, &ng, &ms, NULL, NULL, NULL) == BSYN_ERR_ARG);
-        CHECK(bsyn_sample_to_ess(NULL, &sa, 400.0, BSYN_Q_VUS_SYN, BSYN_Q_VUS_ANT, 4, &sk, d1, i1, &ng, &ms, i1) == BSYN_ERR_ARG);
+        bsyn_ess_target et;
+        bsyn_ess_run er;
+        bsyn_ess_target_defaults(&et); ++n_calls;
+        CHECK(et.target_ess == 400.0 && et.q1 == BSYN_Q_VUS_SYN && et.q2 == BSYN_Q_VUS_ANT && et.retry_adapt_delta == 0.99);
+        CHECK(bsyn_sample_to_ess(NULL, &sa, &et, &sk, d1, i1, &er) == BSYN_ERR_ARG);
         CHECK(bsyn_ess(NULL, 0, d1, d1) == BSYN_ERR_ARG);
         CHECK(bsyn_bulk_ess(NULL, 0, d1, d1, d1) == BSYN_ERR_ARG);
         CHECK(bsyn_advi(NULL, &va, &vk, &ng, &ms) == BSYN_ERR_ARG);
@@ -150,9 +154,14 @@ int main(int argc, char **argv)
         float ms = 0.f;
         const double *dq = NULL, *dsp = NULL, *dsum = NULL;
         CHECK(bsyn_sample_device(b, &sa, &ng, &ms, &dq, &dsp, &dsum) == BSYN_OK && dq && dsp && dsum && ms > 0);
-        int32_t ndraw[1], rounds = 0;
+        int32_t ndraw[1];
+        bsyn_ess_target et;
+        bsyn_ess_run er;
+        bsyn_ess_target_defaults(&et);
+        et.target_ess = 50.0; et.q1 = BSYN_Q_RVUS_F; et.q2 = BSYN_Q_RVUS_P0; et.max_rounds = 4; et.retry_rounds = 2; et.retry_warmup = 50;
         sa.iter = 150; sa.warmup = 100;
-        CHECK(bsyn_sample_to_ess(b, &sa, 50.0, BSYN_Q_RVUS_F, BSYN_Q_RVUS_P0, 4, NULL, ess, ndraw, &ng, &ms, &rounds) == BSYN_OK && rounds >= 1 && ndraw[0] >= 50);
+        CHECK(bsyn_sample_to_ess(b, &sa, &et, NULL, ess, ndraw, &er) == BSYN_OK && er.rounds >= 1 && ndraw[0] >= 50 && er.elapsed_ms > 0 &&
+              er.phase1_ms <= er.elapsed_ms);
         /* device-pointer variant: exercised with a NULL batch only (this client has no CUDA runtime of its own) */
         CHECK(bsyn_logp_grad_device(NULL, 1, idx, u, D, 1, lp, g, st, NULL) == BSYN_ERR_ARG);
         /* ADVI */

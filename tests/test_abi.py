@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(built):
         assert hasattr(L, name), f"{name} declared in include/bsyn.h but not exported by libbsyn.so"
     for name in _lib.EXPORTS:
         assert name in declared
-    assert L.bsyn_version() == 200
+    assert L.bsyn_version() == 201
 
 
 def test_no_cpu_fallback(built, datasets):

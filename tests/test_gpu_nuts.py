@@ -236,8 +236,9 @@ def test_sample_to_ess_extends_only_what_is_below_target(built):
     sds = [prepare(*synthetic_experiment(1000 + k)) for k in range(n)]
     b = _lib.Batch(sds)
     block, rounds_max = 150, 6
-    r = b.sample_to_ess(target=400.0, block=block, max_rounds=rounds_max, chains=4, warmup=300, seed=5, want_summary=True,
-                        want_qdraws=True)
+    r = b.sample_to_ess(target=400.0, block=block, max_rounds=rounds_max, retry_rounds=0, chains=4, warmup=300, seed=5,
+                        want_summary=True, want_qdraws=True)
+    assert r["n_retried"] == 0 and abs(r["phase1_ms"] - r["kernel_ms"]) < 1e-6 * r["kernel_ms"]
     nd, ess = r["draws_per_chain"], r["ess"]
     assert r["rounds"] >= 1 and (nd % block == 0).all() and nd.min() >= block and nd.max() <= block * rounds_max
     assert nd.max() == block * r["rounds"]
@@ -269,17 +270,40 @@ def test_sample_to_ess_extends_only_what_is_below_target(built):
 
 
 def test_screen_to_ess_two_phases(built):
-    """api.screen_to_ess: phase 1 (extension launches) then the reference's remedy for what is left (a refit at
-    adapt_delta 0.99).  A deliberately small phase-1 budget forces phase 2 to run."""
+    """api.screen_to_ess: phase 1 (extension launches), then the reference's remedy for what is left: the same chains
+    resume, re-adapt their step size to adapt_delta 0.99 and go on.  A deliberately small phase-1 budget forces phase 2."""
     from bayesynergy_b200.api import screen_to_ess
     from bayesynergy_b200.dataprep import synthetic_experiment
-    n = 32
+    from bayesynergy_b200.diagnostics import bulk_ess
+    n, block = 32, 100
     sds = [prepare(*synthetic_experiment(2000 + k)) for k in range(n)]
-    r = screen_to_ess(sds, target=900.0, chains=4, warmup=300, block=100, max_rounds=2, seed=9, retry_block=250,
-                      retry_rounds=6)
-    assert r["ess"].shape == (n,) and r["summary"].shape == (n, 12, 2) and r["chain_stats"].shape == (n, 4, 8)
-    assert r["reached_phase1"] < n and r["n_retry"] == n - r["reached_phase1"]        # phase 2 ran on exactly the rest
-    assert r["reached"] >= r["reached_phase1"] and r["reached"] >= n - 4
+    b = _lib.Batch(sds)
+    r = screen_to_ess(sds, target=900.0, batch=b, chains=4, warmup=300, block=block, max_rounds=2, seed=9, retry="resume",
+                      retry_warmup=100, retry_rounds=8)
+    nd, ess = r["draws_per_chain"], r["ess"]
+    assert ess.shape == (n,) and r["summary"].shape == (n, 12, 2) and r["chain_stats"].shape == (n, 4, 8)
+    assert 0 < r["n_retry"] <= n and r["n_retry"] == int((nd > 2 * block).sum())      # phase 2 ran on exactly what was left
+    assert r["rounds"] > 2 and r["reached"] >= n - 4
     assert r["phase2_ms"] > 0 and abs(r["kernel_ms"] - r["phase1_ms"] - r["phase2_ms"]) < 1e-6 * r["kernel_ms"]
-    assert (r["draws_per_chain"] >= 100).all() and np.isfinite(r["summary"][:, Q.index("rVUS_f"), 0]).all()
-    assert ((r["summary"][:, Q.index("rVUS_f"), 0] > 0) & (r["summary"][:, Q.index("rVUS_f"), 0] < 100)).all()
+    assert (nd >= block).all() and (nd % block == 0).all() and nd.max() == block * r["rounds"]
+    f = r["summary"][:, Q.index("rVUS_f"), 0]
+    assert np.isfinite(f).all() and ((f > 0) & (f < 100)).all()
+    # the chains of a retried experiment ended with a smaller step size than those that stopped in phase 1 (delta 0.99 vs 0.9)
+    eps = r["chain_stats"][:, :, 0]
+    retried = nd > 2 * block
+    if retried.any() and (~retried).any():
+        assert np.median(eps[retried]) < np.median(eps[~retried])
+    # the pooled draws (phase 1 + phase 2) are what the ESS on the device was computed from
+    e_syn, _, _ = b.bulk_ess("VUS_syn")
+    e_ant, _, _ = b.bulk_ess("VUS_ant")
+    assert np.allclose(np.fmin(e_syn, e_ant), ess, rtol=1e-6)
+    b.close()
+    # retry="refit": what phase 1 leaves is fitted again from scratch in a small batch; the better of the two fits is kept
+    r1 = screen_to_ess(sds, target=900.0, chains=4, warmup=300, block=block, max_rounds=2, seed=9, retry=None)
+    r2 = screen_to_ess(sds, target=900.0, chains=4, warmup=300, block=block, max_rounds=2, seed=9, retry="refit",
+                       retry_block=250, retry_rounds=6)
+    assert r1["n_retry"] == 0 and r1["phase2_ms"] == 0 and r1["reached"] < n
+    assert r2["n_retry"] == n - r1["reached"] and r2["phase2_ms"] > 0 and abs(r2["phase1_ms"] - r1["kernel_ms"]) < 0.5 * r1["kernel_ms"]
+    assert (r2["ess"] >= r1["ess"] - 1e-9).all() and r2["reached"] >= n - 4
+    with pytest.raises(ValueError):
+        screen_to_ess(sds, retry="again")
