@@ -22,7 +22,7 @@ static __constant__ double c_exp[16] = {
     6755399441055744.0,             // [11] 1.5 * 2^52
     -6.93147180369123816490e-01,    // [12] -ln2 hi
     -1.90821492927058770002e-10,    // [13] -ln2 lo
-    709.0, -708.0};
+    708.0, -708.0};
 
 // Library log / exp / log10 for rarely executed paths (LPTN tails, > 4 replicates per cell, generated
 // quantities): out of line, so that their ~100-instruction bodies are not replicated at every inlined site.
@@ -85,22 +85,30 @@ __device__ __forceinline__ double fast_rsqrt(double d)
     y = fma(y * fma(0.375, e, 0.5), e, y);   // y (1 + e/2 + 3 e^2 / 8): third order, ~2^-58 from a 2^-20 seed
     return y;
 }
-// exp(x): x is clamped to [-708, 709] (results stay normal: exp(-708) = 3e-308 stands in for 0, exp(709) =
-// 8e307 for inf -- both only feed 1/(1+E)-type expressions here); NaN propagates.
+// exp(x): x is clamped to [-708, 708] (results stay normal: exp(-708) = 3e-308 stands in for 0, exp(708) =
+// 3e307 for inf -- both only feed 1/(1+E)-type expressions here); NaN propagates.
 __device__ __forceinline__ double fast_exp(double x)
 {
-    const double xc = fmax(fmin(x, c_exp[14]), c_exp[15]);
+    // clamp on the sign-magnitude form: ONE compare of |x| against an immediate and two integer selects (fmin / fmax on
+    // doubles cost ~16 instructions per call in SASS: DSETP.MIN/MAX + NaN-quieting LOP3s + register-pair shuffling)
+    const int hx = __double2hiint(x);
+    const bool big = fabs(x) > 708.0;          // false for NaN, which flows on and is restored at the end
+    const double xc = __hiloint2double(big ? ((hx & 0x80000000) | 0x40862000) : hx, big ? 0 : __double2loint(x));
     const double magic = c_exp[11];            // (t + magic) - magic rounds t to an integer
     const double tm = fma(xc, c_exp[10], magic);
     const double t = tm - magic;
     double r = fma(t, c_exp[12], xc);
     r = fma(t, c_exp[13], r);
-    // Estrin evaluation of 1 + r + a2 r^2 + ... + a11 r^11 (a_k = c_exp[11 - k]): dependent depth 4 instead of 12
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double q0 = 1.0 + r, q1 = fma(c_exp[8], r, c_exp[9]), q2 = fma(c_exp[6], r, c_exp[7]);
-    const double q3 = fma(c_exp[4], r, c_exp[5]), q4 = fma(c_exp[2], r, c_exp[3]), q5 = fma(c_exp[0], r, c_exp[1]);
-    const double s0 = fma(q1, r2, q0), s1 = fma(q3, r2, q2), s2 = fma(q5, r2, q4);
-    const double p = fma(s2, r8, fma(s1, r4, s0));
+    // 1 + r + a2 r^2 + ... + a11 r^11 (a_k = c_exp[11 - k]) as even and odd Horner chains in r^2: every DFMA has exactly one
+    // coefficient, which is then a constant-bank operand (two-coefficient DFMAs, as in an Estrin scheme, make the compiler
+    // hold the coefficients in registers); 12 FP64 instructions, dependent depth 7
+    const double r2 = r * r, q0 = 1.0 + r;
+    double ev = fma(c_exp[1], r2, c_exp[3]);   // a10 r2 + a8
+    double od = fma(c_exp[0], r2, c_exp[2]);   // a11 r2 + a9
+    ev = fma(ev, r2, c_exp[5]); od = fma(od, r2, c_exp[4]);
+    ev = fma(ev, r2, c_exp[7]); od = fma(od, r2, c_exp[6]);
+    ev = fma(ev, r2, c_exp[9]); od = fma(od, r2, c_exp[8]);
+    const double p = fma(fma(od, r, ev), r2, q0);
     const int k = __double2loint(tm);           // the integer t (low word of t + magic)
     const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
     return (x != x) ? x : res;

@@ -17,8 +17,10 @@ namespace bsyn {
 #define BSYN_LN10 2.30258509299404568402
 #define BSYN_LOG_PI 1.14472988584940017414
 #define BSYN_LOG_2 0.69314718055994530942
-#define BSYN_SQRT3 1.73205080756887729353
-#define BSYN_SQRT5 2.23606797749978969641
+// constant-bank operands in device code (a 64-bit literal costs two moves at every use)
+static __constant__ double c_kern[3] = {1.73205080756887729353, 2.23606797749978969641, 2.30258509299404568402};
+#define BSYN_SQRT3 c_kern[0]
+#define BSYN_SQRT5 c_kern[1]
 // lgamma(2.25) - lgamma(1) - lgamma(1.25)  (beta(1,1.25) normaliser) = log(1.25)
 #define BSYN_BETA_C 0.22314355131420927
 #define BSYN_IG55_C 4.869135731822556          /* 5 log 5 - lgamma(5) */
@@ -240,7 +242,7 @@ __device__ __forceinline__ bool gp_forward(const OptV<SP> &F, const ProbS &P, co
     const int n = h ? n2 : n1;
     bool ok = true;
     {
-        double *const Lc = h ? L2c : L1c;
+        double *const Lc = L1c + h * (C::OFF_L2C - C::OFF_WS);   // (arithmetic, not a select: the compiler re-derives a select per column)
         const double dg = h ? (1.0 + 1e-10) : (sigf + 1e-10);
         double a[NM];
         static_for<0, NM>([&](auto kc) {
@@ -270,7 +272,7 @@ __device__ __forceinline__ bool gp_forward(const OptV<SP> &F, const ProbS &P, co
                 a[j + 1] = fma(-a[k], l.y, a[j + 1]);
             });
         });
-        double *const Lr = h ? L2r : L1r;
+        double *const Lr = L1r + h * (C::OFF_L2R - C::OFF_L1R);
         if (r < NM) {
             static_for<0, NM / 2>([&](auto pc) {
                 constexpr int k = 2 * decltype(pc)::value;
@@ -587,7 +589,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         const bool d1 = lane < n1;
         const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
         lam = th[d1 ? SL_LA1 : SL_LA2];
-        const double earg = BSYN_LN10 * sl * (smem[P.xs + lane] - mm);
+        const double earg = c_kern[2] * sl * (smem[P.xs + lane] - mm);
         gfin = earg <= 709.782712893384;
         const double Em = fast_exp(earg);
         om = fast_rcp(1.0 + Em);
@@ -758,7 +760,7 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
                 for (int j = 0; j < n1; ++j) pmbar = fma(Ws[i + j * n2], pm[j], pmbar);
             }
             const double sl = th[d1 ? SL_SL1 : SL_SL2], mm = th[d1 ? SL_M1 : SL_M2];
-            const double c = pmbar * (1.0 - lam) * BSYN_LN10 * (1.0 - om) * om;   // (1-la) E ln10/(1+E)^2
+            const double c = pmbar * (1.0 - lam) * c_kern[2] * (1.0 - om) * om;   // (1-la) E ln10/(1+E)^2
             const double dla = pmbar * (1.0 - om);            // d/d la = E/(1+E)
             const double dsl = -c * (smem[P.xs + lane] - mm); // d/d slope
             const double dm = c * sl;                         // d/d log10_ec50
@@ -852,10 +854,10 @@ __device__ __forceinline__ bool warp_logp_grad(const Flags &F, const ProbS &P, c
         {
             const int h = lane >> 4, r = lane & 15;
             const int n = h ? n2 : n1;
-            const double *const Lr = h ? L2r : L1r;
-            const double *const Sm = h ? Ts : Zs;
-            double *const Yb = h ? Ws : Tt;
-            double *const Xb = h ? Lb2 : Lb1;
+            const double *const Lr = L1r + h * (C::OFF_L2R - C::OFF_L1R);
+            const double *const Sm = Zs + h * (C::OFF_TS - C::OFF_ZS);
+            double *const Yb = Tt + h * (C::OFF_WS - C::OFF_TT);
+            double *const Xb = Lb1 + h * (C::OFF_LB2 - C::OFF_LB1);
             const double *const idg = invd + h * 16;
             double sv[NM];
             // Stage B: column r of Y = L^-T S;  S[rr, r] = P[max, min] (P stored [a + b*NM], lower part valid)
