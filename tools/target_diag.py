@@ -17,7 +17,8 @@ n = int(os.environ.get("N_COMBOS", "1332"))
 rounds = int(os.environ.get("MAX_ROUNDS", "13"))
 sds = [prepare(*synthetic_experiment(k)) for k in range(n)]
 b = _lib.Batch(sds)
-r = b.sample_to_ess(target=400.0, block=150, max_rounds=rounds, chains=4, warmup=1000, seed=1000, want_summary=True)
+r = b.sample_to_ess(target=400.0, block=150, max_rounds=rounds, retry_rounds=0, chains=4, warmup=1000, seed=1000,
+                    want_summary=True)
 nd, ess = r["draws_per_chain"], r["ess"]
 out = dict(n=n, rounds=r["rounds"], kernel_s=r["kernel_ms"] * 1e-3, n_grad=r["n_grad"],
            reached=int((ess >= 400).sum()), draws_hist={int(k): int(v) for k, v in zip(*np.unique(nd, return_counts=True))})
