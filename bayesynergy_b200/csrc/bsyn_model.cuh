@@ -245,6 +245,9 @@ __device__ __forceinline__ bool gp_forward(const OptV<SP> &F, const ProbS &P, co
         double *const Lc = L1c + h * (C::OFF_L2C - C::OFF_WS);   // (arithmetic, not a select: the compiler re-derives a select per column)
         const double dg = h ? (1.0 + 1e-10) : (sigf + 1e-10);
         double a[NM];
+        // (measured dead ends, profiles/r02_ab_nuts_v11_split.txt: writing the diagonal to shared memory and loading row r
+        // unconditionally -- no selects, 60 instructions fewer -- is 4 % SLOWER, the store -> barrier -> load round trip sits
+        // on the critical path; packing i + j * NM into the cell word, 50 instructions fewer, is neutral)
         static_for<0, NM>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             const double lo = (r < n && k < r) ? Lc[k * NM + r] : 0.0;
