@@ -61,6 +61,16 @@ template <class T> struct DevBuf {
     operator T *() const { return p; }
 };
 
+// a pair of timing events that is destroyed on every return path
+struct EvPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    EvPair() = default;
+    EvPair(const EvPair &) = delete;
+    EvPair &operator=(const EvPair &) = delete;
+    ~EvPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    cudaError_t create() { const cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
+};
+
 struct bsyn_batch {
     int device = 0;
     int n = 0;
@@ -734,9 +744,9 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
         CK(cudaMemsetAsync(b->d_sp, 0, sizeof(double) * nrows * BSYN_NSP, b->stream));
         CK(cudaMemsetAsync(b->d_chain_stats, 0, sizeof(double) * (size_t)b->n * a->chains * 8, b->stream));
     }
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, b->stream));
+    EvPair ev;
+    CK(ev.create());
+    CK(cudaEventRecord(ev.a, b->stream));
     CK(ops->nuts(nw, tick, grid, bytes, b->stream, b->F, b->d_descs, b->d_dpool, b->d_ipool, b->d_tri, sp));
     ++g_launches;
     // per-problem posterior summaries (mean, sd over all chains and saved sampling draws)
@@ -747,11 +757,10 @@ static int run_sampler(bsyn_batch *b, const bsyn_sampler_args *a, const DevSinks
         ++g_launches;
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(e1, b->stream));
+    CK(cudaEventRecord(ev.b, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
     if (elapsed_ms) *elapsed_ms = ms;
     unsigned long long ng = 0;
     CK(cudaMemcpy(&ng, b->d_gradctr, sizeof(ng), cudaMemcpyDeviceToHost));
@@ -1178,9 +1187,9 @@ extern "C" int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, 
         tot_grad += ng;
         // rank-normalised bulk ESS of q1 and q2 over the (r + 1) * block draws of the active problems
         const int ns_now = (r + 1) * block;
-        cudaEvent_t e0, e1;
-        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-        CK(cudaEventRecord(e0, b->stream));
+        EvPair ev;
+        CK(ev.create());
+        CK(cudaEventRecord(ev.a, b->stream));
         const int grid = std::max(1, std::min(n_active, b->num_sms * 4));
         const size_t eb = bulk_ess_smem_bytes(ns_now * args->chains);
         bulk_ess_kernel<<<grid, BULK_THREADS, eb, b->stream>>>(b->d_qdraws, n_active, list, args->chains, ld_save, 0, ns_now, nullptr, q1, d_e1);
@@ -1191,13 +1200,12 @@ extern "C" int bsyn_sample_to_ess(bsyn_batch *b, const bsyn_sampler_args *args, 
                                                                                                        b->d_nsp, list_out, d_cnt);
         g_launches += 3;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(e1, b->stream));
+        CK(cudaEventRecord(ev.b, b->stream));
         int n_next = 0;
         CK(cudaMemcpyAsync(&n_next, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
         float ms2 = 0.f;
-        CK(cudaEventElapsedTime(&ms2, e0, e1));
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        CK(cudaEventElapsedTime(&ms2, ev.a, ev.b));
         tot_ms += ms + ms2;
         if (n_next == 0 || r + 1 >= R) { ++r; break; }
         list = list_out; n_active = n_next;
