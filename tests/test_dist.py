@@ -131,3 +131,65 @@ def test_synergyscreen_sampling_retry_raises_adapt_delta(monkeypatch, built):
         out = api.synergyscreen(_toy_experiments(3))
     assert seen == [(3, 0.9), (1, 0.99)]
     assert len(out["screenSummary"]) == 3 and "failed" not in out
+
+
+class _FakeEssBatch:
+    """Stands in for _lib.Batch in the host logic of api.screen_to_ess (no GPU): records the calls, returns scripted results."""
+    log = []
+
+    def __init__(self, sds, device=0, **kw):
+        self.sds = list(sds)
+        self.n = len(self.sds)
+
+    def sample_to_ess(self, target=400.0, block=150, max_rounds=6, retry_rounds=6, want_summary=False, **kw):
+        from bayesynergy_b200._lib import BSYN_NQ
+        first = not any(c[0] == "fit" for c in _FakeEssBatch.log)
+        _FakeEssBatch.log.append(("fit", self.n, retry_rounds, kw.get("adapt_delta"), kw.get("seed")))
+        if first:      # the whole screen: experiments 1 and 3 stay below the target
+            ess = np.array([500.0, 120.0, 800.0, np.nan, 450.0])[:self.n]
+            rounds, ms, ng = 3, 100.0, 1000
+        else:          # the refit of (1, 3): 1 recovers, 3 gets a worse-than-nothing 50
+            ess = np.array([410.0, 50.0])[:self.n]
+            rounds, ms, ng = 2, 40.0, 300
+        res = dict(ess=ess, draws_per_chain=np.full(self.n, block * rounds, dtype=np.int32), n_grad=ng, kernel_ms=ms,
+                   phase1_ms=ms if retry_rounds == 0 else 0.75 * ms, rounds=rounds,
+                   n_retried=0 if retry_rounds == 0 else int((~(ess >= target)).sum()))
+        if want_summary:
+            res["summary"] = np.full((self.n, BSYN_NQ, 2), 1.0 if first else 2.0)
+            res["chain_stats"] = np.full((self.n, 4, 8), 1.0 if first else 2.0)
+        return res
+
+    def close(self):
+        _FakeEssBatch.log.append(("close", self.n))
+
+
+def test_screen_to_ess_host_logic(monkeypatch):
+    """api.screen_to_ess without a GPU: retry="refit" refits exactly what phase 1 left, at adapt_delta 0.99 with another seed,
+    keeps the better of the two fits per experiment and adds the counters up; retry="resume" / None make one library call."""
+    from bayesynergy_b200 import api, _lib
+    monkeypatch.setattr(_lib, "Batch", _FakeEssBatch)
+    sds = [f"sd{k}" for k in range(5)]
+    _FakeEssBatch.log = []
+    r = api.screen_to_ess(sds, target=400.0, seed=3, retry="refit")
+    fits = [c for c in _FakeEssBatch.log if c[0] == "fit"]
+    assert [(c[1], c[2], c[3]) for c in fits] == [(5, 0, 0.9), (2, 0, 0.99)] and fits[0][4] != fits[1][4]
+    assert [c for c in _FakeEssBatch.log if c[0] == "close"] == [("close", 5), ("close", 2)]     # both batches closed
+    assert r["n_retry"] == 2 and r["reached"] == 4 and r["rounds"] == 5 and r["n_grad"] == 1300
+    assert r["kernel_ms"] == 140.0 and r["phase1_ms"] == 100.0 and r["phase2_ms"] == 40.0
+    assert r["ess"][1] == 410.0 and r["ess"][3] == 50.0             # NaN counts as worse than any number
+    assert r["summary"][1, 0, 0] == 2.0 and r["summary"][3, 0, 0] == 2.0 and r["summary"][0, 0, 0] == 1.0
+    assert r["draws_per_chain"][1] == 600 and r["draws_per_chain"][0] == 450   # the refit runs blocks of retry_block = 300
+    for mode, rr in (("resume", 6), (None, 0)):
+        _FakeEssBatch.log = []
+        r = api.screen_to_ess(sds, target=400.0, retry=mode)
+        fits = [c for c in _FakeEssBatch.log if c[0] == "fit"]
+        assert [(c[1], c[2]) for c in fits] == [(5, rr)]
+        assert r["reached"] == 3 and r["n_retry"] == (2 if mode else 0)
+        assert abs(r["phase1_ms"] + r["phase2_ms"] - r["kernel_ms"]) < 1e-9
+    with pytest.raises(ValueError):
+        api.screen_to_ess(sds, retry="again")
+    # a batch handed in by the caller is left open
+    _FakeEssBatch.log = []
+    b = _FakeEssBatch(sds)
+    api.screen_to_ess(sds, batch=b, retry=None)
+    assert ("close", 5) not in _FakeEssBatch.log
