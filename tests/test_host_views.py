@@ -101,3 +101,82 @@ def test_surface_grids_are_column_major():
     s = np.stack([np.arange(ncf + 4, dtype=float) + 100 * k for k in range(3)])
     f, p0, d = api._surface_grids(SD, s)
     assert f.shape == (4, 3) and f[1, 0] == 1 and f[0, 1] == 4 and p0[3, 2] == 100 + 11 and d[0, 0] == 200
+
+
+def _mathews_sd():
+    m = json.load(open(os.path.join(ROOT, "tests", "golden", "mathews_DLBCL.json")))
+    e = m["ispinesib + ibrutinib"]
+    return prepare(np.array(e["y"]), np.array(e["x"]).reshape(2, -1).T), e
+
+
+def test_diagnose_maps_sampler_warnings_to_messages():
+    """R/bayesynergy.R:210-214: any rstan warning makes returnCode 1; api._diagnose restates the warnings rstan raises."""
+    from bayesynergy_b200._lib import Q_NAMES, BSYN_NQ
+    rng = np.random.default_rng(1)
+    chains, n = 4, 400
+    q = rng.normal(size=(chains, n, BSYN_NQ))
+    sp = np.zeros((chains, n, 7))
+    sp[:, :, 2] = 5
+    cs = np.zeros((chains, 8))
+    msgs, ndiv = api._diagnose(sp, cs, q, 10)
+    assert msgs == [] and ndiv == 0
+    sp[0, :3, 4] = 1
+    sp[1, :7, 2] = 10
+    cs[2, 6] = 1
+    msgs, ndiv = api._diagnose(sp, cs, q, 10)
+    assert ndiv == 3 and msgs[0] == "There were 3 divergent transitions after warmup."
+    assert msgs[1].startswith("There were 7 transitions after warmup that exceeded the maximum treedepth")
+    assert msgs[2].startswith("Initialization failed") and len(msgs) == 3
+    q2 = q.copy()
+    q2[0, :, Q_NAMES.index("VUS_ant")] += 5.0                       # one chain elsewhere: R-hat
+    msgs, _ = api._diagnose(np.zeros((chains, n, 7)), np.zeros((chains, 8)), q2, 10)
+    assert len(msgs) == 1 and "R-hat" in msgs[0]
+    q3 = q.copy()
+    q3[:, :, Q_NAMES.index("s")] = np.cumsum(q3[:, :, Q_NAMES.index("s")], axis=1) * 0.01 + q3[:, :1, Q_NAMES.index("s")] * 0  # random walk
+    msgs, _ = api._diagnose(np.zeros((chains, n, 7)), np.zeros((chains, 8)), q3, 10)
+    assert len(msgs) == 1 and ("ESS" in msgs[0] or "R-hat" in msgs[0])
+
+
+def test_outlier_rule_and_object_fields():
+    """R/bayesynergy.R:305-314 (residual > 3 x observation noise => warning, returnCode 1) and the fields of the object."""
+    import warnings
+    from bayesynergy_b200._lib import BSYN_NQ
+    sd, e = _mathews_sd()
+    ncf = (sd.n1 + 1) * (sd.n2 + 1)
+    f_cells = np.zeros(ncf)
+    f_cells[sd.ii_obs - 1] = sd.y                    # a surface through the data: no outlier
+    assert api._outlier_message(sd, f_cells, 0.1, 0.005) is None
+    f_bad = f_cells.copy()
+    f_bad[sd.ii_obs[3] - 1] += 0.9
+    msg = api._outlier_message(sd, f_bad, 0.1, 0.005)
+    assert msg and "more than three times the observation noise" in msg
+    rng = np.random.default_rng(2)
+    chains, n = 4, 200
+    names = output_names(sd, "gp_grid")
+    draws = rng.random((chains, n, len(names)))
+    post = api._posterior_from_draws(sd, draws, rng.normal(size=chains * n))
+    post["s"] = 0.1 * post["s"]                      # observation noise scale ~ 0.05
+    surf = np.zeros((3, ncf + 3))
+    surf[0, :ncf] = f_cells
+    options = dict(type=3, lower_asymptotes=True, method="sampling", bayes_factor=False, heteroscedastic=True, robust=False,
+                   pcprior=False, lambda_=0.005, nu=1.5, pcprior_hypers=(1, 0.1, 1, 0.2))
+    meta = dict(y=sd.y, x=np.zeros((sd.N, 2)), drug_names=["A", "B"], experiment_ID="e", units=["uM", "uM"])
+    q = rng.normal(size=(chains, n, BSYN_NQ))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")               # a clean fit raises no warning
+        obj = api._assemble_object(sd, meta, post, surf, -12.5, np.zeros((chains, n, 7)), np.zeros((chains, 8)), q, options, 10)
+    assert obj["returnCode"] == 0 and "messages" not in obj and obj["LPML"] == -12.5 and np.isnan(obj["divergent"])
+    assert set(obj) >= {"posterior", "posterior_mean", "data", "model", "returnCode", "LPML", "divergent"}
+    assert obj["posterior_mean"]["f"].shape == (sd.n2 + 1, sd.n1 + 1) and obj["model"]["nu"] == 1.5
+    assert "z" not in obj["posterior_mean"] and isinstance(obj["posterior_mean"]["ell"], float)
+    assert np.array_equal(obj["data"]["indices"], sd.ii_obs)
+    surf[0, :ncf] = f_bad
+    sp = np.zeros((chains, n, 7))
+    sp[0, 0, 4] = 1
+    with pytest.warns(UserWarning):
+        obj = api._assemble_object(sd, meta, post, surf, -12.5, sp, np.zeros((chains, 8)), q, options, 10)
+    assert obj["returnCode"] == 1 and obj["divergent"] == 1 and len(obj["messages"]) == 2
+    options["method"] = "vb"                          # no sampler diagnostics for a variational fit
+    surf[0, :ncf] = f_cells
+    obj = api._assemble_object(sd, meta, post, surf, -1.0, None, None, None, options, 10)
+    assert obj["returnCode"] == 0 and obj["model"]["method"] == "vb"
