@@ -193,3 +193,46 @@ def test_screen_to_ess_host_logic(monkeypatch):
     b = _FakeEssBatch(sds)
     api.screen_to_ess(sds, batch=b, retry=None)
     assert ("close", 5) not in _FakeEssBatch.log
+
+
+def test_synergyscreen_sharded_world2_gloo(tmp_path):
+    """synergyscreen(rank, world_size) + gather_screen under torchrun, world_size 2, gloo: each rank fits only its shard
+    (the device work is faked -- this is the host logic of SURVEY 8e), listIDs stay global, rank 0 holds all rows in order."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, json
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np
+        import torch.distributed as dist
+        from bayesynergy_b200 import api
+        from bayesynergy_b200._lib import Q_NAMES, BSYN_NQ
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        seen = []
+        def fake_fit(sds, kw, device, max_treedepth, **sinks):
+            seen.append(len(sds))
+            S = np.ones((len(sds), BSYN_NQ, 2))
+            S[:, Q_NAMES.index("s"), 0] = 0.1
+            return dict(summary=S, chain_stats=np.zeros((len(sds), 4, 8))), np.zeros(len(sds), dtype=int)
+        api._fit_batch = fake_fit
+        api.prepare = lambda y, x, **kw: ("sd", len(y))
+        y = np.linspace(1, 0.2, 9)
+        x = np.array([[a, b] for a in (0.0, 1.0, 2.0) for b in (0.0, 1.0, 2.0)])
+        exps = [dict(y=y, x=x, drug_names=[f"A{{k}}", f"B{{k}}"], experiment_ID=f"e{{k}}") for k in range(7)]
+        local = api.synergyscreen(exps, rank=rank, world_size=world, device=0)
+        out = api.gather_screen(local, world)
+        json.dump(dict(seen=seen, n_local=len(local["screenSummary"])), open({str(tmp_path)!r} + f"/r{{rank}}.json", "w"))
+        if rank == 0:
+            json.dump([[r["listID"], r["Experiment ID"]] for r in out["screenSummary"]], open({str(tmp_path / 'out.json')!r}, "w"))
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+    r0, r1 = json.load(open(tmp_path / "r0.json")), json.load(open(tmp_path / "r1.json"))
+    assert r0["seen"] == [4] and r1["seen"] == [3] and r0["n_local"] == 4 and r1["n_local"] == 3
+    rows = json.load(open(tmp_path / "out.json"))
+    assert rows == [[k + 1, f"e{k}"] for k in range(7)]
