@@ -14,7 +14,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from bayesynergy_b200 import _lib  # noqa: E402
 from bayesynergy_b200.dataprep import prepare, synthetic_experiment, output_names  # noqa: E402

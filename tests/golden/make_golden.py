@@ -6,7 +6,7 @@ datasets and a synthetic 10x10x3 experiment, over kernels x likelihoods x option
 These are SELF-DERIVED golden vectors (the reference has none: SURVEY.md §4/§8c; parity unpinned).  They pin
 (i) the C oracle's hand adjoints against autograd and (ii) the CUDA path against both.
 
-    python tools/make_golden.py
+    python tests/golden/make_golden.py
 """
 import itertools
 import json
@@ -15,7 +15,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from bayesynergy_b200.dataprep import prepare, synthetic_experiment  # noqa: E402
 from oracle.torch_oracle import log_prob_grad, DomainError, _kernel_mats  # noqa: E402
@@ -86,7 +86,7 @@ def main():
                       cond=kernel_cond(sd, u, "gp_grid"),
                       note="SURVEY.md Appendix E: lp = -61.1325359718674"))
     with open(os.path.join(ROOT, "tests/golden/logp_golden.json"), "w") as f:
-        json.dump(dict(generator="tools/make_golden.py (torch float64 autograd)", cases=cases), f)
+        json.dump(dict(generator="tests/golden/make_golden.py (torch float64 autograd)", cases=cases), f)
     print(len(cases), "cases")
 
 
